@@ -59,7 +59,9 @@ def forward(sd: Dict, mel: np.ndarray, cfg: O.OracleConfig = O.V1) -> np.ndarray
         c.num_dilations[j] = len(dil)
         for m, d in enumerate(dil):
             c.resblock_dilations[j][m] = d
-    names = [n for n, *_ in O.conv_layers(cfg)]
+    allnames = [n for n, *_ in O.conv_layers(cfg)]
+    names = (["conv_pre"] + [n for n in allnames if n.startswith("ups.")]
+             + [n for n in allnames if n.startswith("resblocks.")] + ["conv_post"])
     ptrs = (ctypes.c_void_p * (2 * len(names)))()
     keep = []
     for i, n in enumerate(names):
