@@ -1,0 +1,135 @@
+/* hfg.h -- C ABI of the B200-native HiFiGAN generator engine (libhfg_b200.so).
+ *
+ * This is the drop-in boundary for iris-tts's vocoder hot path.  The reference
+ * has no FFI for this path: its "plugin API" is Python function signatures that
+ * end in torch library calls.  Each entry point below names the reference code
+ * it replaces (paths relative to the reference tree):
+ *
+ *   hfg_create            HiFiGANModel.__init__ graph construction
+ *                         src/iris/hifigan_pretrained.py:77-121
+ *                         (and the Keras twin, src/iris/vocoder.py:59-101)
+ *   hfg_set_weight_norm   nn.utils.weight_norm re-parametrisation, folded ONCE
+ *                         here instead of on every forward
+ *                         src/iris/hifigan_pretrained.py:49,55,92,100,119
+ *   hfg_set_weight        load_state_dict of already-folded tensors
+ *                         src/iris/hifigan_pretrained.py:190 ; Keras
+ *                         load_weights, src/iris/vocoder.py:167-170
+ *   hfg_finalize          .eval().to(device)   src/iris/hifigan_pretrained.py:202-204
+ *   hfg_forward           HiFiGANModel.forward src/iris/hifigan_pretrained.py:123-143
+ *                         incl. the H2D/D2H copies of HiFiGANGenerator.__call__
+ *                         (:228, :235) when host pointers are passed
+ *   hfg_run_layer         one F.conv1d / F.conv_transpose1d call of that forward
+ *                         (:67, :69, :124, :128, :140) -- for per-layer parity
+ *   hfg_get_tap           forward hooks on submodules (test-only visibility)
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success or a negative hfg_status; the message for the last failure on the
+ * calling thread is hfg_last_error().  Nothing throws across the ABI.  A handle
+ * is not thread-safe (one CUDA stream per handle); use one handle per thread or
+ * per device.  There is no CPU fallback: without a CUDA device hfg_create fails.
+ */
+#ifndef HFG_H_
+#define HFG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFG_ABI_VERSION 1
+#define HFG_MAX_UPSAMPLES 8
+#define HFG_MAX_KERNELS 8
+#define HFG_MAX_DILATIONS 8
+
+typedef enum hfg_status {
+    HFG_OK = 0,
+    HFG_ERR_INVALID = -1,   /* bad argument / shape / name            */
+    HFG_ERR_CUDA = -2,      /* a CUDA runtime or driver call failed   */
+    HFG_ERR_STATE = -3,     /* call order (e.g. forward before finalize) */
+    HFG_ERR_NOMEM = -4,     /* device or host allocation failed       */
+    HFG_ERR_UNSUPPORTED = -5
+} hfg_status;
+
+/* Arithmetic the convolutions run in.  Outputs are always fp32. */
+typedef enum hfg_precision {
+    HFG_PREC_FP32 = 0,    /* fp32 FFMA on CUDA cores, fp32 activations (bit-faithful class)  */
+    HFG_PREC_BF16 = 1,    /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulation        */
+    HFG_PREC_BF16X3 = 2   /* tcgen05, operands split hi+lo bf16, 3 MMAs: fp32-class accuracy */
+} hfg_precision;
+
+/* hfg_forward flags */
+#define HFG_MEL_ON_DEVICE 1u    /* mel is a device pointer (default: host)   */
+#define HFG_WAVE_ON_DEVICE 2u   /* wave is a device pointer (default: host)  */
+#define HFG_KEEP_TAPS 4u        /* keep copies of intermediate activations for hfg_get_tap */
+#define HFG_NO_SYNC 8u          /* device pointers only: enqueue and return; call hfg_sync */
+
+/* The six constructor arguments of the reference generator
+ * (hifigan_pretrained.py:77-85 / vocoder.py:59-68). */
+typedef struct hfg_config {
+    int32_t in_channels;                 /* 80 */
+    int32_t upsample_initial_channel;    /* 512 (V1) */
+    int32_t num_upsamples;
+    int32_t upsample_rates[HFG_MAX_UPSAMPLES];
+    int32_t upsample_kernel_sizes[HFG_MAX_UPSAMPLES];
+    int32_t num_kernels;
+    int32_t resblock_kernel_sizes[HFG_MAX_KERNELS];
+    int32_t num_dilations[HFG_MAX_KERNELS];
+    int32_t resblock_dilations[HFG_MAX_KERNELS][HFG_MAX_DILATIONS];
+} hfg_config;
+
+typedef struct hfg_engine hfg_engine;
+
+int hfg_abi_version(void);
+const char* hfg_last_error(void);
+
+/* Number of CUDA devices visible (0 if none / no driver). */
+int hfg_device_count(void);
+
+int hfg_create(const hfg_config* cfg, int device, hfg_engine** out);
+void hfg_destroy(hfg_engine* e);
+
+/* Layer names are the reference's state-dict prefixes: "conv_pre", "ups.<i>",
+ * "resblocks.<n>.convs1.<m>", "resblocks.<n>.convs2.<m>", "conv_post".
+ * Host fp32 pointers in torch layout: Conv1d weight [C_out][C_in][k],
+ * ConvTranspose1d weight [C_in][C_out][k]; g has dim-0 entries; bias [C_out]. */
+int hfg_set_weight_norm(hfg_engine* e, const char* layer, const float* g, const float* v, const float* bias);
+int hfg_set_weight(hfg_engine* e, const char* layer, const float* w, const float* bias);
+/* Shape query so callers can validate checkpoints: dims = {d0, d1, k}. */
+int hfg_layer_shape(const hfg_engine* e, const char* layer, int32_t dims[3], int32_t* is_transposed);
+int hfg_num_layers(const hfg_engine* e);
+int hfg_layer_name(const hfg_engine* e, int index, char* buf, size_t buflen);
+
+/* Repack + upload; every layer must have been set. */
+int hfg_finalize(hfg_engine* e);
+
+/* mel [B][in_channels][T] fp32 -> wave [B][T*hop] fp32. */
+int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wave,
+                int32_t precision, uint32_t flags);
+int hfg_sync(hfg_engine* e);
+int32_t hfg_hop(const hfg_engine* e);
+
+/* Device bytes hfg_forward needs for (B, T) in the given precision. */
+size_t hfg_workspace_bytes(const hfg_engine* e, int32_t B, int32_t T, int32_t precision);
+
+/* The engine's CUDA stream (a cudaStream_t) for event timing by the caller. */
+void* hfg_stream(hfg_engine* e);
+/* Kernels launched by this handle since creation (bench "gpu_launches"). */
+uint64_t hfg_launch_count(const hfg_engine* e);
+
+/* One conv layer in isolation, host pointers, reference layouts:
+ * x [B][C_in][L] -> y [B][C_out][L_out]; pre_lrelu applies leaky_relu(.,0.1) to x first. */
+int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, int32_t L,
+                  int32_t pre_lrelu, float* y, int32_t precision);
+
+/* After hfg_forward(..., HFG_KEEP_TAPS): copy an intermediate activation to
+ * host as fp32 [B][C][L] (reference layout).  Names: "conv_pre", "ups.<i>",
+ * "resblocks.<3i>" (first ResBlock of each stage), "stage.<i>", "conv_post".
+ * Pass out == NULL to query the element count via *n. */
+int hfg_get_tap(hfg_engine* e, const char* name, float* out, size_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFG_H_ */

@@ -1,0 +1,837 @@
+// libhfg_b200: the C-ABI engine behind include/hfg.h.
+//
+// Host-side graph of the reference generator (src/iris/hifigan_pretrained.py:77-143)
+// lowered to a cached plan of CUDA launches per (B, T, precision).  Weight-norm is folded
+// once at load (:49,55,92,100,119 re-run it on every forward).  There is no CPU path:
+// every entry point that computes requires a CUDA device.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "hfg_internal.h"
+
+namespace hfg {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return HFG_ERR_CUDA;
+}
+#define CK(expr)                                              \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);   \
+    } while (0)
+#define RET(expr)                     \
+    do {                              \
+        int _r = (expr);              \
+        if (_r != HFG_OK) return _r;  \
+    } while (0)
+
+struct Layer {
+    std::string name;
+    bool transposed = false;
+    int cin = 0, cout = 0, k = 0, dil = 1, stride = 1, pad = 0;
+    bool is_post = false;
+    bool set = false;
+    std::vector<float> w;     // folded, torch layout
+    std::vector<float> bias;
+    // GEMM form
+    int taps = 0, tap_off0 = 0, tap_step = 0, Np = 0, ups_s = 1, ups_p = 0;
+    int cin_pad = 0, kc = 64;
+    // device packs
+    float* d_w32 = nullptr;            // [taps][Cin][Np]  (conv_post: [k][C])
+    float* d_bias = nullptr;           // [Cout]
+    __nv_bfloat16* d_wb_hi = nullptr;  // [taps*Np][cin_pad]
+    __nv_bfloat16* d_wb_lo = nullptr;
+};
+
+enum StepKind { S_CONV32, S_UMMA, S_POST32, S_POSTBF, S_ACCUM, S_SPLIT, S_MEL_CL32, S_MEL_CLBF, S_TAP };
+
+struct Step {
+    StepKind kind;
+    ConvParams cp;
+    UmmaLaunch ul;
+    // misc operands
+    const float* f_in = nullptr;
+    float* f_out = nullptr;
+    const __nv_bfloat16* b_in = nullptr;
+    const __nv_bfloat16* b_in_lo = nullptr;
+    __nv_bfloat16* b_out = nullptr;
+    __nv_bfloat16* b_out_lo = nullptr;
+    const float* w = nullptr;
+    const float* bias = nullptr;
+    int B = 0, L = 0, C = 0, k = 0, cpad = 0;
+    int flag0 = 0, flag1 = 0;
+    float fval = 0.f;
+    size_t n = 0;
+    std::string tap_name;
+};
+
+struct Plan {
+    std::vector<Step> steps;
+    float* mel_dev = nullptr;   // [B][Cin][T] staging when the caller passes a host pointer
+    float* wave_dev = nullptr;  // [B][T*hop]
+    size_t bytes = 0;
+    bool keep_taps = false;
+};
+
+struct Tap {
+    float* dev = nullptr;  // channels-last [B][L][C] (C==1: [B][L])
+    int B = 0, C = 0, L = 0;
+};
+
+}  // namespace
+}  // namespace hfg
+
+using namespace hfg;
+
+struct hfg_engine {
+    hfg_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<Layer> layers;
+    std::map<std::string, int> index;
+    bool finalized = false;
+    int hop = 1;
+    // workspace
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;
+    std::map<std::string, Tap> taps;
+    uint64_t launches = 0;
+    // run_layer scratch
+    uint8_t* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace hfg {
+namespace {
+
+int get_padding(int k, int d) { return (k * d - d) / 2; }  // hifigan_pretrained.py:61-62
+
+int validate_cfg(const hfg_config& c) {
+    if (c.in_channels <= 0 || c.upsample_initial_channel <= 0) return fail(HFG_ERR_INVALID, "config: channels must be positive");
+    if (c.num_upsamples <= 0 || c.num_upsamples > HFG_MAX_UPSAMPLES) return fail(HFG_ERR_INVALID, "config: num_upsamples out of range");
+    if (c.num_kernels <= 0 || c.num_kernels > HFG_MAX_KERNELS) return fail(HFG_ERR_INVALID, "config: num_kernels out of range");
+    if (c.upsample_initial_channel % (1 << c.num_upsamples) != 0)
+        return fail(HFG_ERR_INVALID, "config: upsample_initial_channel must be divisible by 2^num_upsamples");
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+        if (u <= 0 || k < u || (k - u) % 2 != 0) return fail(HFG_ERR_INVALID, "config: upsample kernel must be >= rate with even difference");
+    }
+    for (int j = 0; j < c.num_kernels; ++j) {
+        if (c.resblock_kernel_sizes[j] <= 0 || c.resblock_kernel_sizes[j] % 2 == 0)
+            return fail(HFG_ERR_INVALID, "config: resblock kernel sizes must be odd");
+        if (c.num_dilations[j] <= 0 || c.num_dilations[j] > HFG_MAX_DILATIONS) return fail(HFG_ERR_INVALID, "config: num_dilations out of range");
+        for (int m = 0; m < c.num_dilations[j]; ++m)
+            if (c.resblock_dilations[j][m] <= 0) return fail(HFG_ERR_INVALID, "config: dilations must be positive");
+    }
+    const int c_last = c.upsample_initial_channel >> c.num_upsamples;
+    if (c_last < 8 || c_last > 128 || (c_last & (c_last - 1)) != 0)
+        return fail(HFG_ERR_UNSUPPORTED, "config: final channel count must be a power of two in [8, 128]");
+    if (c.in_channels % 8 != 0) return fail(HFG_ERR_UNSUPPORTED, "config: in_channels must be a multiple of 8");
+    return HFG_OK;
+}
+
+void add_layer(hfg_engine* e, Layer L) {
+    if (L.is_post) {
+        L.taps = L.k; L.tap_off0 = -L.pad; L.tap_step = 1; L.Np = 1;
+    } else if (!L.transposed) {
+        L.taps = L.k; L.tap_off0 = -L.pad; L.tap_step = L.dil; L.Np = L.cout; L.ups_s = 1; L.ups_p = 0;
+    } else {
+        L.taps = (L.k + L.stride - 1) / L.stride; L.tap_off0 = 0; L.tap_step = -1;
+        L.Np = L.stride * L.cout; L.ups_s = L.stride; L.ups_p = L.pad;
+    }
+    L.kc = (L.cin % 64 == 0 || L.cin > 64) ? 64 : 32;
+    L.cin_pad = (L.cin + L.kc - 1) / L.kc * L.kc;
+    e->index[L.name] = (int)e->layers.size();
+    e->layers.push_back(std::move(L));
+}
+
+void build_layers(hfg_engine* e) {
+    const hfg_config& c = e->cfg;
+    const int c0 = c.upsample_initial_channel;
+    char buf[64];
+    {   // conv_pre  hifigan_pretrained.py:92-94
+        Layer L; L.name = "conv_pre"; L.cin = c.in_channels; L.cout = c0; L.k = 7; L.pad = 3;
+        add_layer(e, L);
+    }
+    int hop = 1;
+    for (int i = 0; i < c.num_upsamples; ++i) {   // :98-109
+        Layer L; snprintf(buf, sizeof buf, "ups.%d", i); L.name = buf; L.transposed = true;
+        L.cin = c0 >> i; L.cout = c0 >> (i + 1); L.k = c.upsample_kernel_sizes[i]; L.stride = c.upsample_rates[i];
+        L.pad = (L.k - L.stride) / 2;
+        hop *= L.stride;
+        add_layer(e, L);
+    }
+    e->hop = hop;
+    int n = 0;
+    for (int i = 0; i < c.num_upsamples; ++i) {   // :111-116, ResBlock :41-59
+        const int ch = c0 >> (i + 1);
+        for (int j = 0; j < c.num_kernels; ++j, ++n) {
+            const int k = c.resblock_kernel_sizes[j];
+            for (int m = 0; m < c.num_dilations[j]; ++m) {
+                const int d = c.resblock_dilations[j][m];
+                Layer a; snprintf(buf, sizeof buf, "resblocks.%d.convs1.%d", n, m); a.name = buf;
+                a.cin = a.cout = ch; a.k = k; a.dil = d; a.pad = get_padding(k, d);
+                add_layer(e, a);
+                Layer b; snprintf(buf, sizeof buf, "resblocks.%d.convs2.%d", n, m); b.name = buf;
+                b.cin = b.cout = ch; b.k = k; b.dil = 1; b.pad = get_padding(k, 1);
+                add_layer(e, b);
+            }
+        }
+    }
+    {   // conv_post :119
+        Layer L; L.name = "conv_post"; L.cin = c0 >> c.num_upsamples; L.cout = 1; L.k = 7; L.pad = 3; L.is_post = true;
+        add_layer(e, L);
+    }
+}
+
+Layer* find_layer(hfg_engine* e, const char* name) {
+    if (!name) return nullptr;
+    auto it = e->index.find(name);
+    return it == e->index.end() ? nullptr : &e->layers[it->second];
+}
+
+void free_layer_dev(Layer& L) {
+    cudaFree(L.d_w32); cudaFree(L.d_bias); cudaFree(L.d_wb_hi); cudaFree(L.d_wb_lo);
+    L.d_w32 = L.d_bias = nullptr; L.d_wb_hi = L.d_wb_lo = nullptr;
+}
+
+inline uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat16_rn
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+
+int upload_layer(Layer& L) {
+    free_layer_dev(L);
+    const int Cin = L.cin, Cout = L.cout, k = L.k;
+    CK(cudaMalloc(&L.d_bias, sizeof(float) * Cout));
+    CK(cudaMemcpy(L.d_bias, L.bias.data(), sizeof(float) * Cout, cudaMemcpyHostToDevice));
+    if (L.is_post) {
+        std::vector<float> p((size_t)k * Cin);
+        for (int j = 0; j < k; ++j)
+            for (int ci = 0; ci < Cin; ++ci) p[(size_t)j * Cin + ci] = L.w[(size_t)ci * k + j];   // w[0][ci][j]
+        CK(cudaMalloc(&L.d_w32, p.size() * sizeof(float)));
+        CK(cudaMemcpy(L.d_w32, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return HFG_OK;
+    }
+    // generic GEMM form  W'[j][ci][n]
+    std::vector<float> p((size_t)L.taps * Cin * L.Np, 0.f);
+    if (!L.transposed) {
+        for (int co = 0; co < Cout; ++co)
+            for (int ci = 0; ci < Cin; ++ci)
+                for (int j = 0; j < k; ++j) p[((size_t)j * Cin + ci) * L.Np + co] = L.w[((size_t)co * Cin + ci) * k + j];
+    } else {
+        const int s = L.stride;
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int co = 0; co < Cout; ++co)
+                for (int kk = 0; kk < k; ++kk) {
+                    const int n = kk / s, r = kk % s;
+                    p[((size_t)n * Cin + ci) * L.Np + r * Cout + co] = L.w[((size_t)ci * Cout + co) * k + kk];
+                }
+    }
+    CK(cudaMalloc(&L.d_w32, p.size() * sizeof(float)));
+    CK(cudaMemcpy(L.d_w32, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // tensor-core pack: [taps*Np][cin_pad] bf16 hi/lo, K-major
+    std::vector<uint16_t> hi((size_t)L.taps * L.Np * L.cin_pad, 0), lo(hi.size(), 0);
+    for (int j = 0; j < L.taps; ++j)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int n = 0; n < L.Np; ++n) {
+                const float v = p[((size_t)j * Cin + ci) * L.Np + n];
+                const uint16_t h = f2bf(v);
+                const size_t o = ((size_t)j * L.Np + n) * L.cin_pad + ci;
+                hi[o] = h;
+                lo[o] = f2bf(v - bf2f(h));
+            }
+    CK(cudaMalloc(&L.d_wb_hi, hi.size() * 2));
+    CK(cudaMalloc(&L.d_wb_lo, lo.size() * 2));
+    CK(cudaMemcpy(L.d_wb_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.d_wb_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    return HFG_OK;
+}
+
+ConvGeom geom_of(const Layer& L, int B, int Lin) {
+    ConvGeom g;
+    g.B = B; g.Lin = Lin; g.Cin = L.cin; g.Cout = L.cout;
+    g.Lout = L.transposed ? (Lin - 1) * L.stride - 2 * L.pad + L.k : Lin;
+    g.Mrows = L.transposed ? Lin + L.taps - 1 : Lin;
+    g.Np = L.Np; g.taps = L.taps; g.tap_off0 = L.tap_off0; g.tap_step = L.tap_step;
+    g.ups_s = L.ups_s; g.ups_p = L.ups_p;
+    return g;
+}
+
+ConvParams conv32(const Layer& L, int B, int Lin, const float* x, float* y, const float* res, int pre_lrelu,
+                  int accumulate, float out_div) {
+    const ConvGeom g = geom_of(L, B, Lin);
+    ConvParams p;
+    memset(&p, 0, sizeof p);
+    p.x = x; p.w = L.d_w32; p.bias = L.d_bias; p.y = y; p.res = res;
+    p.B = B; p.Lin = Lin; p.Cin = L.cin; p.Lout = g.Lout; p.Cout = L.cout; p.Mrows = g.Mrows; p.Np = g.Np;
+    p.taps = g.taps; p.tap_off0 = g.tap_off0; p.tap_step = g.tap_step; p.ups_s = g.ups_s; p.ups_p = g.ups_p;
+    p.pre_lrelu = pre_lrelu; p.accumulate = accumulate; p.out_div = out_div;
+    return p;
+}
+
+// ---------------------------------------------------------------------------
+// Workspace arena (bump allocator, 256-byte aligned)
+// ---------------------------------------------------------------------------
+struct Bump {
+    uint8_t* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t count) {
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += (count * sizeof(T) + 255) / 256 * 256;
+        return p;
+    }
+};
+
+size_t stage_elems_max(const hfg_engine* e, int B, int T) {
+    size_t mx = 0;
+    size_t L = (size_t)T;
+    for (int i = 0; i < e->cfg.num_upsamples; ++i) {
+        L *= e->cfg.upsample_rates[i];
+        mx = std::max(mx, (size_t)B * L * (e->cfg.upsample_initial_channel >> (i + 1)));
+    }
+    return mx;
+}
+
+int env_flag(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+// Builds (or, with base == nullptr, only sizes) the launch plan.
+//
+// fp32 family: raw fp32 streams everywhere, leaky_relu fused into the consumer's load.
+// tensor-core family: every conv reads ACTIVATED bf16 planes (leaky_relu applied by the
+// producer's epilogue) through TMA; residual / MRF streams stay fp32.  Stages narrower than
+// 32 channels (V2's tail) are bandwidth-bound and run on the fp32 family inside a
+// tensor-core plan.
+int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* base, Plan* plan, size_t* bytes_out) {
+    typedef __nv_bfloat16 bf;
+    const hfg_config& c = e->cfg;
+    const bool x3 = prec == HFG_PREC_BF16X3;
+    const int npass = x3 ? 3 : 1;
+    const int a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
+    const int c0 = c.upsample_initial_channel;
+    const int NU = c.num_upsamples;
+    // number of leading stages (after conv_pre) that run on tensor cores; -1: conv_pre is fp32 too
+    int n_tc = -1;
+    if (prec != HFG_PREC_FP32 && c0 % 32 == 0) {
+        n_tc = 0;
+        while (n_tc < NU && (c0 >> (n_tc + 1)) % 32 == 0) ++n_tc;
+    }
+    const bool any_tc = n_tc >= 0;
+    const bool any_32 = n_tc < NU;   // some stage (or everything) runs on the fp32 family
+
+    Bump bump{base};
+    const size_t smax = stage_elems_max(e, B, T);
+    const size_t n_pre = (size_t)B * T * c0;
+    const Layer& pre = e->layers[e->index["conv_pre"]];
+    const Layer& post = e->layers[e->index["conv_post"]];
+    const bool real = base != nullptr;
+    auto push = [&](Step&& s) { if (real) plan->steps.push_back(std::move(s)); };
+    auto tap = [&](const char* name, const float* src, int C, int L) {
+        if (!keep_taps) return;
+        Step s{}; s.kind = S_TAP; s.tap_name = name; s.f_in = src; s.B = B; s.C = C; s.L = L;
+        push(std::move(s));
+    };
+    char nm[64];
+    auto layer = [&](const char* fmt, int a, int b2) -> const Layer& {
+        snprintf(nm, sizeof nm, fmt, a, b2);
+        return e->layers[e->index[nm]];
+    };
+
+    float* mel_dev = bump.take<float>((size_t)B * c.in_channels * T);
+    float* wave_dev = bump.take<float>((size_t)B * T * e->hop);
+    if (real) { plan->mel_dev = mel_dev; plan->wave_dev = wave_dev; plan->keep_taps = keep_taps; }
+
+    // fp32 streams (both families)
+    float* u_raw = bump.take<float>(smax);
+    float* r_raw = bump.take<float>(smax);
+    float* xs = bump.take<float>(smax);
+    float* xt32 = any_32 ? bump.take<float>(smax) : nullptr;
+    float* post_tap = keep_taps ? bump.take<float>((size_t)B * T * e->hop) : nullptr;
+    // fp32-family conv_pre
+    float* mel_cl = !any_tc ? bump.take<float>((size_t)B * T * c.in_channels) : nullptr;
+    float* x0_raw = (n_tc <= 0 || keep_taps) ? bump.take<float>(n_pre) : nullptr;
+    // tensor-core operand planes
+    bf *mel_hi = nullptr, *mel_lo = nullptr, *x0_hi = nullptr, *x0_lo = nullptr, *u_hi = nullptr, *u_lo = nullptr;
+    bf *r_hi = nullptr, *r_lo = nullptr, *xt_hi = nullptr, *xt_lo = nullptr, *s_hi = nullptr, *s_lo = nullptr;
+    if (any_tc) {
+        mel_hi = bump.take<bf>((size_t)B * T * pre.cin_pad);
+        if (x3) mel_lo = bump.take<bf>((size_t)B * T * pre.cin_pad);
+        x0_hi = bump.take<bf>(n_pre);
+        if (x3) x0_lo = bump.take<bf>(n_pre);
+        if (n_tc > 0) {
+            u_hi = bump.take<bf>(smax); r_hi = bump.take<bf>(smax); xt_hi = bump.take<bf>(smax); s_hi = bump.take<bf>(smax);
+            if (x3) { u_lo = bump.take<bf>(smax); r_lo = bump.take<bf>(smax); xt_lo = bump.take<bf>(smax); s_lo = bump.take<bf>(smax); }
+        }
+    }
+
+    auto umma = [&](const Layer& L, int Lin, const bf* xh, const bf* xl, const float* res, float* y_raw, bf* yh, bf* yl,
+                    float* xsp, int xs_read, int xs_write, float out_div) -> int {
+        if (!real) return HFG_OK;
+        Step s{};
+        s.kind = S_UMMA;
+        UmmaConvParams p;
+        memset(&p, 0, sizeof p);
+        p.g = geom_of(L, B, Lin);
+        p.cin_pad = L.cin_pad; p.kc = L.kc; p.npass = npass;
+        p.bias = L.d_bias; p.res = res; p.y_raw = y_raw; p.y_act = yh; p.y_act_lo = x3 ? yl : nullptr;
+        p.xs = xsp; p.xs_read = xs_read; p.xs_write = xs_write; p.out_div = out_div; p.a_per_tap = a_per_tap;
+        RET(plan_conv_umma(&s.ul, p, xh, xl, L.d_wb_hi, L.d_wb_lo));
+        plan->steps.push_back(std::move(s));
+        return HFG_OK;
+    };
+    auto c32 = [&](const Layer& L, int Lin, const float* x, float* y, const float* res, int pre_lrelu, int accumulate, float out_div) {
+        Step s{}; s.kind = S_CONV32; s.cp = conv32(L, B, Lin, x, y, res, pre_lrelu, accumulate, out_div); push(std::move(s));
+    };
+    auto accum = [&](const float* r, size_t ne, int j) {
+        Step s{}; s.kind = S_ACCUM; s.f_out = xs; s.f_in = r; s.n = ne; s.flag0 = j == 0;
+        s.fval = j == c.num_kernels - 1 ? (float)c.num_kernels : 0.f;
+        push(std::move(s));
+    };
+
+    // ---- conv_pre  (:124) ----
+    const float* x_raw = nullptr;           // raw fp32 input of the next upsampler (fp32 family)
+    const bf* xh = nullptr; const bf* xl = nullptr;   // activated planes (tensor-core family)
+    if (any_tc) {
+        { Step s{}; s.kind = S_MEL_CLBF; s.f_in = mel_dev; s.b_out = mel_hi; s.b_out_lo = mel_lo; s.B = B; s.C = c.in_channels;
+          s.L = T; s.cpad = pre.cin_pad; push(std::move(s)); }
+        // raw fp32 copy only for taps or when the first upsampler runs on the fp32 family
+        RET(umma(pre, T, mel_hi, mel_lo, nullptr, x0_raw, n_tc > 0 ? x0_hi : nullptr, n_tc > 0 ? x0_lo : nullptr, nullptr, 0, 0, 0.f));
+        if (x0_raw) tap("conv_pre", x0_raw, c0, T);
+        x_raw = x0_raw; xh = x0_hi; xl = x0_lo;
+    } else {
+        { Step s{}; s.kind = S_MEL_CL32; s.f_in = mel_dev; s.f_out = mel_cl; s.B = B; s.C = c.in_channels; s.L = T; push(std::move(s)); }
+        c32(pre, T, mel_cl, x0_raw, nullptr, 0, 0, 0.f);
+        tap("conv_pre", x0_raw, c0, T);
+        x_raw = x0_raw;
+    }
+
+    int L = T, n = 0;
+    for (int i = 0; i < NU; ++i) {
+        const Layer& up = layer("ups.%d", i, 0);
+        const int ch = up.cout;
+        const int Lin = L;
+        L *= up.stride;
+        const size_t ne = (size_t)B * L * ch;
+        const bool tc_stage = i < n_tc;
+        const bool next_tc = i + 1 < n_tc;   // the next stage reads bf16 planes
+        if (tc_stage) {
+            RET(umma(up, Lin, xh, xl, nullptr, u_raw, u_hi, u_lo, nullptr, 0, 0, 0.f));   // lrelu -> ups  (:127-128)
+            snprintf(nm, sizeof nm, "ups.%d", i);
+            tap(nm, u_raw, ch, L);
+            const bool last_stage = i == NU - 1;
+            const bool want_planes = next_tc || last_stage;   // conv_post reads planes after a tensor-core stage
+            const bool want_raw = !last_stage && !next_tc;    // an fp32-family stage follows: it reads xs
+            for (int j = 0; j < c.num_kernels; ++j, ++n) {
+                const float* rr = u_raw; const bf* rh = u_hi; const bf* rl = u_lo;
+                const int nd = c.num_dilations[j];
+                const bool last_branch = j == c.num_kernels - 1;
+                for (int m = 0; m < nd; ++m) {
+                    const Layer& c1 = layer("resblocks.%d.convs1.%d", n, m);
+                    RET(umma(c1, L, rh, rl, nullptr, nullptr, xt_hi, xt_lo, nullptr, 0, 0, 0.f));   // :66-67 (+ :68 in the epilogue)
+                    const Layer& c2 = layer("resblocks.%d.convs2.%d", n, m);
+                    const bool last = m == nd - 1;
+                    if (!last) {
+                        RET(umma(c2, L, xt_hi, xt_lo, rr, r_raw, r_hi, r_lo, nullptr, 0, 0, 0.f));   // :69-70
+                        rr = r_raw; rh = r_hi; rl = r_lo;
+                    } else if (keep_taps) {
+                        RET(umma(c2, L, xt_hi, xt_lo, rr, r_raw, nullptr, nullptr, nullptr, 0, 0, 0.f));
+                    } else {
+                        // x = xt + x ; xs (+)= x ; on the last branch xs /= num_kernels, planes = lrelu(xs)  (:70,:133-137)
+                        const bool wr = !last_branch || want_raw;
+                        RET(umma(c2, L, xt_hi, xt_lo, rr, nullptr, (last_branch && want_planes) ? s_hi : nullptr,
+                                 (last_branch && want_planes) ? s_lo : nullptr, xs, j > 0, wr,
+                                 last_branch ? (float)c.num_kernels : 0.f));
+                    }
+                }
+                if (keep_taps) {
+                    snprintf(nm, sizeof nm, "resblocks.%d", n);
+                    tap(nm, r_raw, ch, L);
+                    accum(r_raw, ne, j);
+                }
+            }
+            if (keep_taps) {
+                snprintf(nm, sizeof nm, "stage.%d", i);
+                tap(nm, xs, ch, L);
+                if (want_planes) { Step s{}; s.kind = S_SPLIT; s.f_in = xs; s.b_out = s_hi; s.b_out_lo = s_lo; s.n = ne; s.flag0 = 1; push(std::move(s)); }
+            }
+            xh = s_hi; xl = s_lo; x_raw = xs;
+        } else {
+            c32(up, Lin, x_raw, u_raw, nullptr, 1, 0, 0.f);
+            snprintf(nm, sizeof nm, "ups.%d", i);
+            tap(nm, u_raw, ch, L);
+            for (int j = 0; j < c.num_kernels; ++j, ++n) {
+                const float* r = u_raw;
+                const int nd = c.num_dilations[j];
+                for (int m = 0; m < nd; ++m) {
+                    const Layer& c1 = layer("resblocks.%d.convs1.%d", n, m);
+                    c32(c1, L, r, xt32, nullptr, 1, 0, 0.f);
+                    const Layer& c2 = layer("resblocks.%d.convs2.%d", n, m);
+                    const bool last = m == nd - 1;
+                    if (!last || keep_taps) {
+                        c32(c2, L, xt32, r_raw, r, 1, 0, 0.f);
+                        r = r_raw;
+                    } else {
+                        c32(c2, L, xt32, xs, r, 1, j > 0, j == c.num_kernels - 1 ? (float)c.num_kernels : 0.f);
+                    }
+                }
+                if (keep_taps) {
+                    snprintf(nm, sizeof nm, "resblocks.%d", n);
+                    tap(nm, r_raw, ch, L);
+                    accum(r_raw, ne, j);
+                }
+            }
+            snprintf(nm, sizeof nm, "stage.%d", i);
+            tap(nm, xs, ch, L);
+            x_raw = xs; xh = nullptr; xl = nullptr;
+        }
+    }
+    // ---- lrelu -> conv_post -> tanh  (:139-141) ----
+    const bool post_planes = n_tc == NU;
+    for (int pass = keep_taps ? 0 : 1; pass < 2; ++pass) {
+        Step s{};
+        s.w = post.d_w32; s.bias = post.d_bias; s.f_out = pass ? wave_dev : post_tap;
+        s.B = B; s.L = L; s.C = post.cin; s.k = post.k; s.flag0 = 1; s.flag1 = pass;
+        if (post_planes) { s.kind = S_POSTBF; s.b_in = xh; s.b_in_lo = xl; } else { s.kind = S_POST32; s.f_in = x_raw; }
+        push(std::move(s));
+        if (!pass) tap("conv_post", post_tap, 1, L);
+    }
+    if (bytes_out) *bytes_out = bump.off;
+    return HFG_OK;
+}
+
+int store_tap(hfg_engine* e, const Step& s) {
+    Tap& t = e->taps[s.tap_name];
+    const size_t n = (size_t)s.B * s.C * s.L;
+    if ((size_t)t.B * t.C * t.L != n) {
+        cudaFree(t.dev);
+        t.dev = nullptr;
+        CK(cudaMalloc(&t.dev, n * sizeof(float)));
+    }
+    t.B = s.B; t.C = s.C; t.L = s.L;
+    CK(cudaMemcpyAsync(t.dev, s.f_in, n * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    return HFG_OK;
+}
+
+int run_plan(hfg_engine* e, Plan* plan) {
+    cudaStream_t st = e->stream;
+    for (const Step& s : plan->steps) {
+        switch (s.kind) {
+            case S_CONV32: CK(launch_conv_fp32(s.cp, st)); break;
+            case S_UMMA: CK(launch_conv_umma(s.ul, st)); break;
+            case S_POST32: CK(launch_conv_post_fp32(s.f_in, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag0, s.flag1, st)); break;
+            case S_POSTBF: CK(launch_conv_post_bf16(s.b_in, s.b_in_lo, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
+            case S_ACCUM: CK(launch_accum_fp32(s.f_out, s.f_in, s.n, s.flag0, s.fval, st)); break;
+            case S_SPLIT: CK(launch_act_split(s.f_in, s.b_out, s.b_out_lo, s.n, s.flag0, st)); break;
+            case S_MEL_CL32: CK(launch_transpose_cf_to_cl(s.f_in, s.f_out, s.B, s.C, s.L, st)); break;
+            case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, st)); break;
+            case S_TAP: RET(store_tap(e, s)); continue;   // a copy, not one of our kernels
+        }
+        ++e->launches;
+    }
+    return HFG_OK;
+}
+
+int ensure_arena(hfg_engine* e, size_t bytes) {
+    if (bytes <= e->arena_bytes) return HFG_OK;
+    CK(cudaStreamSynchronize(e->stream));
+    e->plans.clear();   // plans hold pointers into the arena
+    cudaFree(e->arena);
+    e->arena = nullptr;
+    e->arena_bytes = 0;
+    cudaError_t err = cudaMalloc(&e->arena, bytes);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HFG_ERR_NOMEM, std::string("workspace allocation failed: ") + cudaGetErrorString(err));
+    }
+    e->arena_bytes = bytes;
+    return HFG_OK;
+}
+
+int check_prec(int prec) {
+    if (prec != HFG_PREC_FP32 && prec != HFG_PREC_BF16 && prec != HFG_PREC_BF16X3) return fail(HFG_ERR_INVALID, "unknown precision");
+    return HFG_OK;
+}
+
+}  // namespace
+}  // namespace hfg
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int hfg_abi_version(void) { return HFG_ABI_VERSION; }
+const char* hfg_last_error(void) { return g_error.c_str(); }
+
+int hfg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hfg_create(const hfg_config* cfg, int device, hfg_engine** out) {
+    if (!cfg || !out) return fail(HFG_ERR_INVALID, "hfg_create: null argument");
+    *out = nullptr;
+    RET(validate_cfg(*cfg));
+    const int n = hfg_device_count();
+    if (n <= 0) return fail(HFG_ERR_CUDA, "hfg_create: no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(HFG_ERR_INVALID, "hfg_create: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "hfg_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+        return fail(HFG_ERR_UNSUPPORTED, buf);
+    }
+    std::unique_ptr<hfg_engine> e(new hfg_engine());
+    e->cfg = *cfg;
+    e->device = device;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    build_layers(e.get());
+    *out = e.release();
+    return HFG_OK;
+}
+
+void hfg_destroy(hfg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& L : e->layers) free_layer_dev(L);
+    for (auto& kv : e->taps) cudaFree(kv.second.dev);
+    cudaFree(e->arena);
+    cudaFree(e->scratch);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int hfg_num_layers(const hfg_engine* e) { return e ? (int)e->layers.size() : 0; }
+
+int hfg_layer_name(const hfg_engine* e, int index, char* buf, size_t buflen) {
+    if (!e || !buf || index < 0 || index >= (int)e->layers.size()) return fail(HFG_ERR_INVALID, "hfg_layer_name: bad argument");
+    const std::string& n = e->layers[index].name;
+    if (n.size() + 1 > buflen) return fail(HFG_ERR_INVALID, "hfg_layer_name: buffer too small");
+    memcpy(buf, n.c_str(), n.size() + 1);
+    return HFG_OK;
+}
+
+int hfg_layer_shape(const hfg_engine* e, const char* layer, int32_t dims[3], int32_t* is_transposed) {
+    if (!e || !dims) return fail(HFG_ERR_INVALID, "hfg_layer_shape: null argument");
+    const Layer* L = find_layer(const_cast<hfg_engine*>(e), layer);
+    if (!L) return fail(HFG_ERR_INVALID, std::string("unknown layer: ") + (layer ? layer : "(null)"));
+    if (L->transposed) { dims[0] = L->cin; dims[1] = L->cout; } else { dims[0] = L->cout; dims[1] = L->cin; }
+    dims[2] = L->k;
+    if (is_transposed) *is_transposed = L->transposed ? 1 : 0;
+    return HFG_OK;
+}
+
+int hfg_set_weight(hfg_engine* e, const char* layer, const float* w, const float* bias) {
+    if (!e || !w || !bias) return fail(HFG_ERR_INVALID, "hfg_set_weight: null argument");
+    Layer* L = find_layer(e, layer);
+    if (!L) return fail(HFG_ERR_INVALID, std::string("unknown layer: ") + (layer ? layer : "(null)"));
+    const size_t n = (size_t)L->cin * L->cout * L->k;
+    L->w.assign(w, w + n);
+    L->bias.assign(bias, bias + L->cout);
+    L->set = true;
+    e->finalized = false;
+    return HFG_OK;
+}
+
+int hfg_set_weight_norm(hfg_engine* e, const char* layer, const float* g, const float* v, const float* bias) {
+    if (!e || !g || !v || !bias) return fail(HFG_ERR_INVALID, "hfg_set_weight_norm: null argument");
+    Layer* L = find_layer(e, layer);
+    if (!L) return fail(HFG_ERR_INVALID, std::string("unknown layer: ") + (layer ? layer : "(null)"));
+    // torch._weight_norm(v, g, dim=0): w = v * (g / ||v||), norm over every dim but 0.
+    // dim 0 is C_out for Conv1d and C_in for ConvTranspose1d.
+    const int rows = L->transposed ? L->cin : L->cout;
+    const size_t cols = (size_t)(L->transposed ? L->cout : L->cin) * L->k;
+    L->w.resize((size_t)rows * cols);
+    for (int r = 0; r < rows; ++r) {
+        double s = 0.0;
+        for (size_t c = 0; c < cols; ++c) { const double x = v[r * cols + c]; s += x * x; }
+        const float scale = g[r] / (float)sqrt(s);
+        for (size_t c = 0; c < cols; ++c) L->w[r * cols + c] = v[r * cols + c] * scale;
+    }
+    L->bias.assign(bias, bias + L->cout);
+    L->set = true;
+    e->finalized = false;
+    return HFG_OK;
+}
+
+int hfg_finalize(hfg_engine* e) {
+    if (!e) return fail(HFG_ERR_INVALID, "hfg_finalize: null engine");
+    CK(cudaSetDevice(e->device));
+    for (auto& L : e->layers)
+        if (!L.set) return fail(HFG_ERR_STATE, "hfg_finalize: layer not set: " + L.name);
+    CK(cudaStreamSynchronize(e->stream));
+    e->plans.clear();
+    for (auto& L : e->layers) RET(upload_layer(L));
+    e->finalized = true;
+    return HFG_OK;
+}
+
+int32_t hfg_hop(const hfg_engine* e) { return e ? e->hop : 0; }
+
+size_t hfg_workspace_bytes(const hfg_engine* e, int32_t B, int32_t T, int32_t precision) {
+    if (!e || B <= 0 || T <= 0 || check_prec(precision) != HFG_OK) return 0;
+    size_t bytes = 0;
+    if (build_plan(const_cast<hfg_engine*>(e), B, T, precision, false, nullptr, nullptr, &bytes) != HFG_OK) return 0;
+    return bytes;
+}
+
+void* hfg_stream(hfg_engine* e) { return e ? (void*)e->stream : nullptr; }
+uint64_t hfg_launch_count(const hfg_engine* e) { return e ? e->launches : 0; }
+
+int hfg_sync(hfg_engine* e) {
+    if (!e) return fail(HFG_ERR_INVALID, "hfg_sync: null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return HFG_OK;
+}
+
+int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wave, int32_t precision, uint32_t flags) {
+    if (!e || !mel || !wave) return fail(HFG_ERR_INVALID, "hfg_forward: null argument");
+    if (B <= 0 || T <= 0) return fail(HFG_ERR_INVALID, "hfg_forward: B and T must be positive");
+    RET(check_prec(precision));
+    if (!e->finalized) return fail(HFG_ERR_STATE, "hfg_forward: call hfg_finalize first");
+    const bool mel_dev = flags & HFG_MEL_ON_DEVICE, wave_dev = flags & HFG_WAVE_ON_DEVICE;
+    const bool keep = flags & HFG_KEEP_TAPS;
+    if ((flags & HFG_NO_SYNC) && !(mel_dev && wave_dev)) return fail(HFG_ERR_INVALID, "hfg_forward: HFG_NO_SYNC needs device pointers");
+    CK(cudaSetDevice(e->device));
+
+    const auto key = std::make_tuple((int)B, (int)T, (int)precision, keep ? 1 : 0);
+    auto it = e->plans.find(key);
+    if (it == e->plans.end()) {
+        size_t bytes = 0;
+        RET(build_plan(e, B, T, precision, keep, nullptr, nullptr, &bytes));
+        RET(ensure_arena(e, bytes));
+        std::unique_ptr<Plan> plan(new Plan());
+        plan->bytes = bytes;
+        // All plans share the arena from offset 0: they run one after another on one stream.
+        RET(build_plan(e, B, T, precision, keep, e->arena, plan.get(), nullptr));
+        it = e->plans.emplace(key, std::move(plan)).first;
+    }
+    Plan* plan = it->second.get();
+    const size_t mel_bytes = (size_t)B * e->cfg.in_channels * T * sizeof(float);
+    const size_t wave_bytes = (size_t)B * T * e->hop * sizeof(float);
+    CK(cudaMemcpyAsync(plan->mel_dev, mel, mel_bytes, mel_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    RET(run_plan(e, plan));
+    CK(cudaMemcpyAsync(wave, plan->wave_dev, wave_bytes, wave_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    if (!(flags & HFG_NO_SYNC)) CK(cudaStreamSynchronize(e->stream));
+    return HFG_OK;
+}
+
+int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, int32_t L, int32_t pre_lrelu, float* y,
+                  int32_t precision) {
+    if (!e || !x || !y) return fail(HFG_ERR_INVALID, "hfg_run_layer: null argument");
+    if (B <= 0 || L <= 0) return fail(HFG_ERR_INVALID, "hfg_run_layer: B and L must be positive");
+    RET(check_prec(precision));
+    if (!e->finalized) return fail(HFG_ERR_STATE, "hfg_run_layer: call hfg_finalize first");
+    Layer* lay = find_layer(e, layer);
+    if (!lay) return fail(HFG_ERR_INVALID, std::string("unknown layer: ") + (layer ? layer : "(null)"));
+    CK(cudaSetDevice(e->device));
+    const ConvGeom g = geom_of(*lay, B, L);
+    const size_t n_in = (size_t)B * lay->cin * L, n_out = (size_t)B * lay->cout * g.Lout;
+    const size_t n_in_pad = (size_t)B * lay->cin_pad * L;
+    const size_t need = (2 * n_in + 2 * n_out) * sizeof(float) + 4 * n_in_pad * 2 + 16 * 256;
+    if (need > e->scratch_bytes) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->scratch);
+        e->scratch = nullptr; e->scratch_bytes = 0;
+        CK(cudaMalloc(&e->scratch, need));
+        e->scratch_bytes = need;
+    }
+    Bump bump{e->scratch};
+    float* x_cf = bump.take<float>(n_in);
+    float* x_cl = bump.take<float>(n_in);
+    float* y_cl = bump.take<float>(n_out);
+    float* y_cf = bump.take<float>(n_out);
+    __nv_bfloat16* a_hi = bump.take<__nv_bfloat16>(n_in_pad);
+    __nv_bfloat16* a_lo = bump.take<__nv_bfloat16>(n_in_pad);
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(x_cf, x, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (lay->is_post) {
+        CK(launch_transpose_cf_to_cl(x_cf, x_cl, B, lay->cin, L, st));
+        CK(launch_conv_post_fp32(x_cl, lay->d_w32, lay->d_bias, y_cf, B, L, lay->cin, lay->k, pre_lrelu, 0, st));
+        e->launches += 2;
+    } else if (precision == HFG_PREC_FP32) {
+        CK(launch_transpose_cf_to_cl(x_cf, x_cl, B, lay->cin, L, st));
+        ConvParams p = conv32(*lay, B, L, x_cl, y_cl, nullptr, pre_lrelu, 0, 0.f);
+        CK(launch_conv_fp32(p, st));
+        CK(launch_transpose_cl_to_cf(y_cl, y_cf, B, lay->cout, g.Lout, st));
+        e->launches += 3;
+    } else {
+        const bool x3 = precision == HFG_PREC_BF16X3;
+        if (lay->cin_pad != lay->cin) {
+            CK(cudaMemsetAsync(a_hi, 0, n_in_pad * 2, st));
+            CK(cudaMemsetAsync(a_lo, 0, n_in_pad * 2, st));
+            CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, lay->cin, L, lay->cin_pad, st));
+            if (pre_lrelu) return fail(HFG_ERR_UNSUPPORTED, "hfg_run_layer: pre_lrelu on a channel-padded layer");
+        } else {
+            CK(launch_transpose_cf_to_cl(x_cf, x_cl, B, lay->cin, L, st));
+            CK(launch_act_split(x_cl, a_hi, x3 ? a_lo : nullptr, n_in, pre_lrelu, st));
+            ++e->launches;
+        }
+        UmmaConvParams p;
+        memset(&p, 0, sizeof p);
+        p.g = g; p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1;
+        p.bias = lay->d_bias; p.y_raw = y_cl; p.a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
+        UmmaLaunch ul;
+        RET(plan_conv_umma(&ul, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo));
+        CK(launch_conv_umma(ul, st));
+        CK(launch_transpose_cl_to_cf(y_cl, y_cf, B, lay->cout, g.Lout, st));
+        e->launches += 3;
+    }
+    CK(cudaMemcpyAsync(y, y_cf, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return HFG_OK;
+}
+
+int hfg_get_tap(hfg_engine* e, const char* name, float* out, size_t* n) {
+    if (!e || !name || !n) return fail(HFG_ERR_INVALID, "hfg_get_tap: null argument");
+    auto it = e->taps.find(name);
+    if (it == e->taps.end()) return fail(HFG_ERR_INVALID, std::string("no such tap (run hfg_forward with HFG_KEEP_TAPS): ") + name);
+    const Tap& t = it->second;
+    const size_t cnt = (size_t)t.B * t.C * t.L;
+    if (!out) { *n = cnt; return HFG_OK; }
+    if (*n < cnt) return fail(HFG_ERR_INVALID, "hfg_get_tap: buffer too small");
+    CK(cudaSetDevice(e->device));
+    float* tmp = nullptr;
+    CK(cudaMalloc(&tmp, cnt * sizeof(float)));
+    cudaError_t err = t.C == 1 ? cudaMemcpyAsync(tmp, t.dev, cnt * sizeof(float), cudaMemcpyDeviceToDevice, e->stream)
+                               : launch_transpose_cl_to_cf(t.dev, tmp, t.B, t.C, t.L, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out, tmp, cnt * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(tmp);
+    if (err != cudaSuccess) return cuda_fail(err, "hfg_get_tap");
+    *n = cnt;
+    return HFG_OK;
+}
+
+}  // extern "C"

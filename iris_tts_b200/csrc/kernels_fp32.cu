@@ -1,0 +1,393 @@
+// fp32 CUDA-core kernel family (HFG_PREC_FP32): exact-fp32 FFMA convolutions on
+// channels-last activations.  This is the bit-faithful-class path and the A/B
+// baseline every tensor-core kernel is checked against on the device.
+//
+// Replaces the ATen library calls of the reference forward:
+//   F.conv1d            src/iris/hifigan_pretrained.py:67,69,124,140
+//   F.conv_transpose1d  src/iris/hifigan_pretrained.py:128
+//   F.leaky_relu        :66,68,127,139   (fused: applied while staging x in smem)
+//   x = xt + x          :70              (fused: residual add in the epilogue)
+//   xs += .. ; xs / 3   :133-137         (fused: accumulate / divide in the epilogue)
+//   torch.tanh          :141             (fused into conv_post)
+#include <algorithm>
+
+#include "hfg_internal.h"
+
+namespace hfg {
+
+namespace {
+
+constexpr int kMaxDevices = 64;
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * kLreluSlope; }
+
+// ---------------------------------------------------------------------------
+// Generic channels-last direct convolution (see ConvParams).
+//   block: 256 threads = NTX (along N) x NTY (along M); thread tile 8 rows x TC cols
+//   smem : x tile [TILE_M + span][CI] (lrelu applied while staging), W tile [taps][CI][TILE_N]
+// ---------------------------------------------------------------------------
+constexpr int kCI = 8;   // input channels staged per iteration
+constexpr int kTT = 8;   // rows per thread
+
+template <int NTX, int TC>
+__global__ void __launch_bounds__(256, 2) conv_cl_fp32_kernel(const ConvParams p) {
+    constexpr int NTY = 256 / NTX;
+    constexpr int TILE_M = NTY * kTT;
+    constexpr int TILE_N = NTX * TC;
+    constexpr int NQ = TC / 4;
+    extern __shared__ __align__(16) float smem[];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % NTX, ty = tid / NTX;
+    const int m0 = blockIdx.x * TILE_M;
+    const int n0 = blockIdx.y * TILE_N;
+    const int b = blockIdx.z;
+
+    const int taps = p.taps;
+    const int last_off = p.tap_off0 + (taps - 1) * p.tap_step;
+    const int lo = min(p.tap_off0, last_off);
+    const int span = max(p.tap_off0, last_off) - lo;
+    const int rows_in = TILE_M + span;
+
+    float* in_s = smem;                       // [rows_in][kCI]
+    float* w_s = smem + ((rows_in * kCI + 3) & ~3);  // [taps][kCI][TILE_N]
+
+    const float* __restrict__ x = static_cast<const float*>(p.x) + (size_t)b * p.Lin * p.Cin;
+    const float* __restrict__ w = static_cast<const float*>(p.w);
+
+    float acc[kTT][TC];
+#pragma unroll
+    for (int i = 0; i < kTT; ++i)
+#pragma unroll
+        for (int c = 0; c < TC; ++c) acc[i][c] = 0.f;
+
+    for (int ci0 = 0; ci0 < p.Cin; ci0 += kCI) {
+        __syncthreads();
+        for (int idx = tid; idx < rows_in * 2; idx += 256) {
+            const int r = idx >> 1, h = idx & 1;
+            const int t = m0 + lo + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < p.Lin) {
+                v = __ldg(reinterpret_cast<const float4*>(x + (size_t)t * p.Cin + ci0 + h * 4));
+                if (p.pre_lrelu) { v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w); }
+            }
+            *reinterpret_cast<float4*>(in_s + r * kCI + h * 4) = v;
+        }
+        for (int idx = tid; idx < taps * kCI * (TILE_N / 4); idx += 256) {
+            const int c4 = idx % (TILE_N / 4);
+            const int rc = idx / (TILE_N / 4);
+            const int j = rc / kCI, ci = rc % kCI;
+            const int n = n0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < p.Np) v = __ldg(reinterpret_cast<const float4*>(w + ((size_t)j * p.Cin + ci0 + ci) * p.Np + n));
+            *reinterpret_cast<float4*>(w_s + rc * TILE_N + c4 * 4) = v;
+        }
+        __syncthreads();
+
+        for (int j = 0; j < taps; ++j) {
+            const int rbase = p.tap_off0 + j * p.tap_step - lo + ty;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 a[kTT];
+#pragma unroll
+                for (int i = 0; i < kTT; ++i)
+                    a[i] = *reinterpret_cast<const float4*>(in_s + (rbase + i * NTY) * kCI + h * 4);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 wv[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        wv[q] = *reinterpret_cast<const float4*>(w_s + ((j * kCI + h * 4 + c) * TILE_N) + q * NTX * 4 + tx * 4);
+#pragma unroll
+                    for (int i = 0; i < kTT; ++i) {
+                        const float av = c == 0 ? a[i].x : c == 1 ? a[i].y : c == 2 ? a[i].z : a[i].w;
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            acc[i][q * 4 + 0] = fmaf(av, wv[q].x, acc[i][q * 4 + 0]);
+                            acc[i][q * 4 + 1] = fmaf(av, wv[q].y, acc[i][q * 4 + 1]);
+                            acc[i][q * 4 + 2] = fmaf(av, wv[q].z, acc[i][q * 4 + 2]);
+                            acc[i][q * 4 + 3] = fmaf(av, wv[q].w, acc[i][q * 4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // Epilogue: scatter (m, n) -> (t_out, co), bias, residual, accumulate, divide, activations.
+    float* __restrict__ y = static_cast<float*>(p.y);
+    const float* __restrict__ res = static_cast<const float*>(p.res);
+#pragma unroll
+    for (int i = 0; i < kTT; ++i) {
+        const int m = m0 + ty + i * NTY;
+        if (m >= p.Mrows) continue;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int n = n0 + q * NTX * 4 + tx * 4;
+            if (n >= p.Np) continue;
+            int r = 0, co = n;
+            if (p.ups_s > 1) { r = n / p.Cout; co = n - r * p.Cout; }
+            const int t_out = m * p.ups_s + r - p.ups_p;
+            if (t_out < 0 || t_out >= p.Lout) continue;
+            const size_t idx = ((size_t)b * p.Lout + t_out) * p.Cout + co;
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+            float4 v = make_float4(acc[i][q * 4 + 0] + bv.x, acc[i][q * 4 + 1] + bv.y,
+                                   acc[i][q * 4 + 2] + bv.z, acc[i][q * 4 + 3] + bv.w);
+            if (res) {
+                const float4 rv = *reinterpret_cast<const float4*>(res + idx);
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            }
+            if (p.accumulate) {
+                const float4 ov = *reinterpret_cast<const float4*>(y + idx);
+                v.x = ov.x + v.x; v.y = ov.y + v.y; v.z = ov.z + v.z; v.w = ov.w + v.w;
+            }
+            if (p.out_div > 0.f) {
+                v.x = __fdiv_rn(v.x, p.out_div); v.y = __fdiv_rn(v.y, p.out_div);
+                v.z = __fdiv_rn(v.z, p.out_div); v.w = __fdiv_rn(v.w, p.out_div);
+            }
+            if (p.post_lrelu) { v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w); }
+            if (p.post_tanh) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            *reinterpret_cast<float4*>(y + idx) = v;
+        }
+    }
+}
+
+template <int NTX, int TC>
+cudaError_t launch_conv_variant(const ConvParams& p, cudaStream_t s) {
+    constexpr int NTY = 256 / NTX;
+    constexpr int TILE_M = NTY * kTT;
+    constexpr int TILE_N = NTX * TC;
+    const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
+    const int span = abs(last_off - p.tap_off0);
+    const int rows_in = TILE_M + span;
+    const size_t smem = (size_t)(((rows_in * kCI + 3) & ~3) + p.taps * kCI * TILE_N) * sizeof(float);
+    static size_t configured[kMaxDevices] = {};  // per-instantiation, per-device high-water mark
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev % kMaxDevices]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_cl_fp32_kernel<NTX, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev % kMaxDevices] = smem;
+    }
+    dim3 grid((p.Mrows + TILE_M - 1) / TILE_M, (p.Np + TILE_N - 1) / TILE_N, p.B);
+    conv_cl_fp32_kernel<NTX, TC><<<grid, 256, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// conv_post: lrelu -> Conv1d(C -> 1, k) -> tanh.  Bandwidth-bound: smem halo
+// staging with float4 loads, G = C/4 lanes per output sample, warp-shuffle
+// reduction over the G lanes, results staged in smem for a coalesced store.
+// ---------------------------------------------------------------------------
+constexpr int kPostTile = 256;
+
+__device__ __forceinline__ float4 load4(const float* x, const float*, size_t i) {
+    return __ldg(reinterpret_cast<const float4*>(x + i));
+}
+// bf16 planes: value = hi (+ lo when the bf16x3 low-order plane is present)
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, size_t i) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(x + i));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    float4 v = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    if (x_lo) {
+        const uint2 ul = __ldg(reinterpret_cast<const uint2*>(x_lo + i));
+        const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&ul.x);
+        const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(&ul.y);
+        v.x += __low2float(c); v.y += __high2float(c); v.z += __low2float(d); v.w += __high2float(d);
+    }
+    return v;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) conv_post_kernel(const TIn* __restrict__ x, const TIn* __restrict__ x_lo,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ wave, int L, int C, int k, int pre_lrelu,
+                                                        int apply_tanh) {
+    extern __shared__ __align__(16) float smem[];
+    const int pad = (k - 1) / 2;
+    const int rows = kPostTile + k - 1;
+    float* in_s = smem;                 // [rows][C]
+    float* w_s = in_s + rows * C;       // [k][C]
+    float* out_s = w_s + k * C;         // [kPostTile]
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * kPostTile;
+    const int b = blockIdx.y;
+    const size_t xoff = (size_t)b * L * C;
+    const int c4n = C / 4;
+    for (int idx = tid; idx < rows * c4n; idx += 256) {
+        const int r = idx / c4n, c4 = idx - r * c4n;
+        const int t = t0 - pad + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < L) {
+            v = load4(x, x_lo, xoff + (size_t)t * C + c4 * 4);
+            if (pre_lrelu) { v.x = lrelu(v.x); v.y = lrelu(v.y); v.z = lrelu(v.z); v.w = lrelu(v.w); }
+        }
+        *reinterpret_cast<float4*>(in_s + r * C + c4 * 4) = v;
+    }
+    for (int idx = tid; idx < k * C; idx += 256) w_s[idx] = __ldg(w + idx);
+    __syncthreads();
+    const int G = c4n;                       // lanes per output (power of two <= 32)
+    const int lane_in_g = tid % G;
+    const int groups = 256 / G;
+    const float bv = __ldg(bias);
+    for (int o = tid / G; o < kPostTile; o += groups) {
+        float s = 0.f;
+        for (int j = 0; j < k; ++j) {
+            const float4 a = *reinterpret_cast<const float4*>(in_s + (o + j) * C + lane_in_g * 4);
+            const float4 ww = *reinterpret_cast<const float4*>(w_s + j * C + lane_in_g * 4);
+            s = fmaf(a.x, ww.x, s); s = fmaf(a.y, ww.y, s); s = fmaf(a.z, ww.z, s); s = fmaf(a.w, ww.w, s);
+        }
+        for (int d = G / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane_in_g == 0) {
+            s += bv;
+            out_s[o] = apply_tanh ? tanhf(s) : s;
+        }
+    }
+    __syncthreads();
+    const int t = t0 + tid;
+    if (t < L) wave[(size_t)b * L + t] = out_s[tid];
+}
+
+// [B][R][Cc] -> [B][Cc][R] tiled transpose (used for mel in / taps out).
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const float* ib = in + (size_t)b * R * Cc;
+    float* ob = out + (size_t)b * R * Cc;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < Cc) ? ib[(size_t)r * Cc + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) ob[(size_t)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+// mel [B][C][L] fp32 -> [B][L][Cpad] bf16 hi (+ lo) planes, channels >= C zero.
+__global__ void mel_to_cl_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, int C, int L, int Cpad) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+    const float* ib = in + (size_t)b * C * L;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, l = l0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && l < L) ? ib[(size_t)c * L + l] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        if (l < L && c < Cpad) {
+            const float v = tile[threadIdx.x][i];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const size_t o = ((size_t)b * L + l) * Cpad + c;
+            hi[o] = h;
+            if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
+}
+
+__global__ void accum_fp32_kernel(float* __restrict__ xs, const float* __restrict__ r, size_t n4, int first, float div) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(r)[i];
+        if (!first) {
+            const float4 o = reinterpret_cast<const float4*>(xs)[i];
+            v.x = o.x + v.x; v.y = o.y + v.y; v.z = o.z + v.z; v.w = o.w + v.w;
+        }
+        if (div > 0.f) {
+            v.x = __fdiv_rn(v.x, div); v.y = __fdiv_rn(v.y, div); v.z = __fdiv_rn(v.z, div); v.w = __fdiv_rn(v.w, div);
+        }
+        reinterpret_cast<float4*>(xs)[i] = v;
+    }
+}
+
+__global__ void act_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 size_t n, int apply_lrelu) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (apply_lrelu) v = lrelu(v);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+cudaError_t launch_transpose(const float* in, float* out, int B, int R, int Cc, cudaStream_t s) {
+    dim3 grid((Cc + 31) / 32, (R + 31) / 32, B);
+    dim3 block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(in, out, R, Cc);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_conv_fp32(const ConvParams& p, cudaStream_t s) {
+    if (p.Cin % kCI != 0 || p.Np % 4 != 0 || p.Cout % 4 != 0) return cudaErrorInvalidValue;
+    if (p.Np >= 128) return launch_conv_variant<16, 8>(p, s);   // 128 rows x 128 cols
+    if (p.Np >= 64) return launch_conv_variant<16, 4>(p, s);    // 128 rows x 64 cols
+    return launch_conv_variant<8, 4>(p, s);                     // 256 rows x 32 cols
+}
+
+template <typename TIn>
+static cudaError_t launch_conv_post_t(const TIn* x, const TIn* x_lo, const float* w, const float* bias, float* wave,
+                                      int B, int L, int C, int k, int pre_lrelu, int apply_tanh, cudaStream_t s) {
+    const int c4n = C / 4;
+    if (C % 4 != 0 || c4n > 32 || (c4n & (c4n - 1)) != 0) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)((kPostTile + k - 1) * C + k * C + kPostTile) * sizeof(float);
+    static size_t configured[kMaxDevices] = {};  // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && smem > configured[dev % kMaxDevices]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_post_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev % kMaxDevices] = smem;
+    }
+    dim3 grid((L + kPostTile - 1) / kPostTile, B);
+    conv_post_kernel<TIn><<<grid, 256, smem, s>>>(x, x_lo, w, bias, wave, L, C, k, pre_lrelu, apply_tanh);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post_fp32(const float* x, const float* w, const float* bias, float* wave,
+                                  int B, int L, int C, int k, int pre_lrelu, int apply_tanh, cudaStream_t s) {
+    return launch_conv_post_t<float>(x, nullptr, w, bias, wave, B, L, C, k, pre_lrelu, apply_tanh, s);
+}
+// Tensor-core modes hand conv_post the already-activated bf16 plane(s).
+cudaError_t launch_conv_post_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const float* w, const float* bias,
+                                  float* wave, int B, int L, int C, int k, int apply_tanh, cudaStream_t s) {
+    return launch_conv_post_t<__nv_bfloat16>(x_hi, x_lo, w, bias, wave, B, L, C, k, 0, apply_tanh, s);
+}
+
+cudaError_t launch_transpose_cf_to_cl(const float* in, float* out, int B, int C, int L, cudaStream_t s) {
+    return launch_transpose(in, out, B, C, L, s);
+}
+cudaError_t launch_transpose_cl_to_cf(const float* in, float* out, int B, int C, int L, cudaStream_t s) {
+    return launch_transpose(in, out, B, L, C, s);
+}
+
+cudaError_t launch_mel_to_cl_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int L, int Cpad,
+                                  cudaStream_t s) {
+    dim3 grid((L + 31) / 32, (Cpad + 31) / 32, B);
+    dim3 block(32, 8);
+    mel_to_cl_bf16_kernel<<<grid, block, 0, s>>>(in, hi, lo, C, L, Cpad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_accum_fp32(float* xs, const float* r, size_t n, int first, float div, cudaStream_t s) {
+    if (n % 4 != 0) return cudaErrorInvalidValue;
+    const size_t n4 = n / 4;
+    const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 16);
+    accum_fp32_kernel<<<blocks, 256, 0, s>>>(xs, r, n4, first, div);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_act_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, int apply_lrelu, cudaStream_t s) {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    act_split_kernel<<<blocks, 256, 0, s>>>(x, hi, lo, n, apply_lrelu);
+    return cudaGetLastError();
+}
+
+}  // namespace hfg
