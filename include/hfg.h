@@ -118,6 +118,17 @@ void* hfg_stream(hfg_engine* e);
 /* Kernels launched by this handle since creation (bench "gpu_launches"). */
 uint64_t hfg_launch_count(const hfg_engine* e);
 
+/* Per-launch device timing for roofline reports (bench.py): when enabled, every kernel launch
+ * of the following hfg_forward calls is bracketed by CUDA events on the engine's stream.  Records
+ * accumulate over forwards until hfg_profile_enable(e, 1) is called again; record i describes launch i: the reference layer it computes
+ * (state-dict prefix, or the kernel's own name for layout helpers), the kernel family, its device
+ * time, and the layer's algorithmic work F_l = 2*Cin*Cout*k*L*B flop and
+ * Q_l = activations in + out + weights bytes (no reference counterpart: the reference has no timers). */
+int hfg_profile_enable(hfg_engine* e, int on);
+int hfg_profile_count(const hfg_engine* e);
+int hfg_profile_get(hfg_engine* e, int i, char* layer, size_t layer_len, char* kernel, size_t kernel_len,
+                    float* ms, double* flops, double* bytes);
+
 /* One conv layer in isolation, host pointers, reference layouts:
  * x [B][C_in][L] -> y [B][C_out][L_out]; pre_lrelu applies leaky_relu(.,0.1) to x first. */
 int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, int32_t L,

@@ -81,6 +81,9 @@ struct Step {
     float fval = 0.f;
     size_t n = 0;
     std::string tap_name;
+    // profiling: reference layer this launch belongs to and its algorithmic work
+    std::string label;
+    double flops = 0.0, bytes = 0.0;
 };
 
 struct Plan {
@@ -115,6 +118,12 @@ struct hfg_engine {
     std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;
     std::map<std::string, Tap> taps;
     uint64_t launches = 0;
+    // per-launch event timing (hfg_profile_*)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    struct ProfRec { std::string label; int kind; double flops, bytes; size_t ev0, ev1; };
+    std::vector<ProfRec> prof_recs;   // accumulated over forwards since hfg_profile_enable(1)
+    size_t prof_used = 0;             // events consumed from the pool
     // run_layer scratch
     uint8_t* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -390,6 +399,13 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         }
     }
 
+    // F_l = 2*Cin*Cout*k*L (L = L_out for Conv1d, L_in for ConvTranspose1d); Q_l = activations in + out + weights
+    auto work = [&](Step& s, const Layer& L, int Lin, int act_bytes) {
+        const double Lout = L.transposed ? (double)Lin * L.stride : (double)Lin;
+        s.label = L.name;
+        s.flops = 2.0 * L.cin * L.cout * L.k * (L.transposed ? (double)Lin : Lout) * B;
+        s.bytes = ((double)L.cin * Lin + (double)L.cout * Lout) * B * act_bytes + (double)L.cin * L.cout * L.k * act_bytes;
+    };
     auto umma = [&](const Layer& L, int Lin, const bf* xh, const bf* xl, const float* res, float* y_raw, bf* yh, bf* yl,
                     float* xsp, int xs_read, int xs_write, float out_div) -> int {
         if (!real) return HFG_OK;
@@ -402,11 +418,14 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.bias = L.d_bias; p.res = res; p.y_raw = y_raw; p.y_act = yh; p.y_act_lo = x3 ? yl : nullptr;
         p.xs = xsp; p.xs_read = xs_read; p.xs_write = xs_write; p.out_div = out_div; p.a_per_tap = a_per_tap;
         RET(plan_conv_umma(&s.ul, p, xh, xl, L.d_wb_hi, L.d_wb_lo));
+        work(s, L, Lin, 2);
         plan->steps.push_back(std::move(s));
         return HFG_OK;
     };
     auto c32 = [&](const Layer& L, int Lin, const float* x, float* y, const float* res, int pre_lrelu, int accumulate, float out_div) {
-        Step s{}; s.kind = S_CONV32; s.cp = conv32(L, B, Lin, x, y, res, pre_lrelu, accumulate, out_div); push(std::move(s));
+        Step s{}; s.kind = S_CONV32; s.cp = conv32(L, B, Lin, x, y, res, pre_lrelu, accumulate, out_div);
+        work(s, L, Lin, 4);
+        push(std::move(s));
     };
     auto accum = [&](const float* r, size_t ne, int j) {
         Step s{}; s.kind = S_ACCUM; s.f_out = xs; s.f_in = r; s.n = ne; s.flag0 = j == 0;
@@ -518,6 +537,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.w = post.d_w32; s.bias = post.d_bias; s.f_out = pass ? wave_dev : post_tap;
         s.B = B; s.L = L; s.C = post.cin; s.k = post.k; s.flag0 = 1; s.flag1 = pass;
         if (post_planes) { s.kind = S_POSTBF; s.b_in = xh; s.b_in_lo = xl; } else { s.kind = S_POST32; s.f_in = x_raw; }
+        work(s, post, L, post_planes ? 2 : 4);
         push(std::move(s));
         if (!pass) tap("conv_post", post_tap, 1, L);
     }
@@ -538,8 +558,30 @@ int store_tap(hfg_engine* e, const Step& s) {
     return HFG_OK;
 }
 
+const char* kind_label(StepKind k) {
+    switch (k) {
+        case S_CONV32: return "conv_cl_fp32";
+        case S_UMMA: return "conv_umma";
+        case S_POST32: case S_POSTBF: return "conv_post";
+        case S_ACCUM: return "accum";
+        case S_SPLIT: return "act_split";
+        case S_MEL_CL32: return "transpose";
+        case S_MEL_CLBF: return "mel_to_cl_bf16";
+        default: return "copy";
+    }
+}
+
 int run_plan(hfg_engine* e, Plan* plan) {
     cudaStream_t st = e->stream;
+    size_t nev = e->prof_used;
+    if (e->profiling) {
+        while (e->prof_events.size() < nev + plan->steps.size() + 1) {
+            cudaEvent_t ev;
+            CK(cudaEventCreate(&ev));
+            e->prof_events.push_back(ev);
+        }
+        CK(cudaEventRecord(e->prof_events[nev++], st));
+    }
     for (const Step& s : plan->steps) {
         switch (s.kind) {
             case S_CONV32: CK(launch_conv_fp32(s.cp, st)); break;
@@ -550,10 +592,17 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_SPLIT: CK(launch_act_split(s.f_in, s.b_out, s.b_out_lo, s.n, s.flag0, st)); break;
             case S_MEL_CL32: CK(launch_transpose_cf_to_cl(s.f_in, s.f_out, s.B, s.C, s.L, st)); break;
             case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, st)); break;
-            case S_TAP: RET(store_tap(e, s)); continue;   // a copy, not one of our kernels
+            case S_TAP: RET(store_tap(e, s)); break;   // a copy, not one of our kernels
         }
-        ++e->launches;
+        if (s.kind != S_TAP) ++e->launches;
+        if (e->profiling) {
+            CK(cudaEventRecord(e->prof_events[nev], st));
+            e->prof_recs.push_back({s.label.empty() ? std::string(kind_label(s.kind)) : s.label, (int)s.kind, s.flops, s.bytes,
+                                    nev - 1, nev});
+            ++nev;
+        }
     }
+    e->prof_used = nev;
     return HFG_OK;
 }
 
@@ -625,6 +674,7 @@ void hfg_destroy(hfg_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& L : e->layers) free_layer_dev(L);
     for (auto& kv : e->taps) cudaFree(kv.second.dev);
+    for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     cudaFree(e->arena);
     cudaFree(e->scratch);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -707,6 +757,32 @@ size_t hfg_workspace_bytes(const hfg_engine* e, int32_t B, int32_t T, int32_t pr
 
 void* hfg_stream(hfg_engine* e) { return e ? (void*)e->stream : nullptr; }
 uint64_t hfg_launch_count(const hfg_engine* e) { return e ? e->launches : 0; }
+
+int hfg_profile_enable(hfg_engine* e, int on) {
+    if (!e) return fail(HFG_ERR_INVALID, "hfg_profile_enable: null engine");
+    // (re)enabling starts a fresh record list; disabling keeps the records readable
+    e->profiling = on != 0;
+    if (on) { e->prof_recs.clear(); e->prof_used = 0; }
+    return HFG_OK;
+}
+
+int hfg_profile_count(const hfg_engine* e) { return e ? (int)e->prof_recs.size() : 0; }
+
+int hfg_profile_get(hfg_engine* e, int i, char* layer, size_t layer_len, char* kernel, size_t kernel_len, float* ms,
+                    double* flops, double* bytes) {
+    if (!e || i < 0 || i >= (int)e->prof_recs.size()) return fail(HFG_ERR_INVALID, "hfg_profile_get: bad index");
+    CK(cudaSetDevice(e->device));
+    const auto& r = e->prof_recs[i];
+    if (layer && layer_len) { strncpy(layer, r.label.c_str(), layer_len - 1); layer[layer_len - 1] = 0; }
+    if (kernel && kernel_len) { strncpy(kernel, kind_label((StepKind)r.kind), kernel_len - 1); kernel[kernel_len - 1] = 0; }
+    if (ms) {
+        CK(cudaEventSynchronize(e->prof_events[r.ev1]));
+        CK(cudaEventElapsedTime(ms, e->prof_events[r.ev0], e->prof_events[r.ev1]));
+    }
+    if (flops) *flops = r.flops;
+    if (bytes) *bytes = r.bytes;
+    return HFG_OK;
+}
 
 int hfg_sync(hfg_engine* e) {
     if (!e) return fail(HFG_ERR_INVALID, "hfg_sync: null engine");

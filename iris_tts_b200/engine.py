@@ -267,6 +267,21 @@ class Engine:
         _abi.check(self._lib.hfg_get_tap(self._h, name.encode(), out.ctypes.data, ctypes.byref(n)))
         return out.reshape(shape) if shape is not None else out
 
+    # -- per-launch timing ---------------------------------------------------
+    def profile(self, on: bool = True) -> None:
+        _abi.check(self._lib.hfg_profile_enable(self._h, int(on)))
+
+    def profile_records(self) -> List[Dict[str, object]]:
+        """Launches since profile(True): layer, kernel family, device ms, algorithmic flop and bytes."""
+        out = []
+        lay = ctypes.create_string_buffer(64)
+        ker = ctypes.create_string_buffer(32)
+        ms, fl, by = ctypes.c_float(), ctypes.c_double(), ctypes.c_double()
+        for i in range(int(self._lib.hfg_profile_count(self._h))):
+            _abi.check(self._lib.hfg_profile_get(self._h, i, lay, 64, ker, 32, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by)))
+            out.append({"layer": lay.value.decode(), "kernel": ker.value.decode(), "ms": ms.value, "flops": fl.value, "bytes": by.value})
+        return out
+
     # -- introspection ------------------------------------------------------
     @property
     def stream(self) -> int:
