@@ -283,7 +283,7 @@ def run_ours(args):
         secondary = {"dtype": "bf16", "value": samples_per_step * args.steps / (ms2 * 1e-3), "unit": "samples/s",
                      "ms_per_step": ms2 / args.steps, "layer_roofline_ms": rl2 * 1e3, "layer_roofline_frac": rl2 * 1e3 / (ms2 / args.steps),
                      "roofline": roofline_from_records(recs2, peaks),
-                     "tolerance": "max-abs 5e-2 vs oracle on loud weights (tests/test_gpu_parity.py); 1e-3 at default init"}
+                     "tolerance": "max-abs 1.5e-1 vs oracle on loud weights (tests/test_gpu_parity.py); 1e-3 at default init"}
 
     if rank != 0:
         if world > 1:

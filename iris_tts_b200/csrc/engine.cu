@@ -4,6 +4,7 @@
 // lowered to a cached plan of CUDA launches per (B, T, precision).  Weight-norm is folded
 // once at load (:49,55,92,100,119 re-run it on every forward).  There is no CPU path:
 // every entry point that computes requires a CUDA device.
+#include <cuda_profiler_api.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -124,6 +125,7 @@ struct hfg_engine {
     struct ProfRec { std::string label; int kind; double flops, bytes; size_t ev0, ev1; };
     std::vector<ProfRec> prof_recs;   // accumulated over forwards since hfg_profile_enable(1)
     size_t prof_used = 0;             // events consumed from the pool
+    std::vector<std::string> ncu_layers;   // HFG_NCU_LAYERS: bracket these layers with cudaProfilerStart/Stop
     // run_layer scratch
     uint8_t* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -583,6 +585,8 @@ int run_plan(hfg_engine* e, Plan* plan) {
         CK(cudaEventRecord(e->prof_events[nev++], st));
     }
     for (const Step& s : plan->steps) {
+        const bool ncu = !e->ncu_layers.empty() && std::find(e->ncu_layers.begin(), e->ncu_layers.end(), s.label) != e->ncu_layers.end();
+        if (ncu) cudaProfilerStart();
         switch (s.kind) {
             case S_CONV32: CK(launch_conv_fp32(s.cp, st)); break;
             case S_UMMA: CK(launch_conv_umma(s.ul, st)); break;
@@ -594,6 +598,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, st)); break;
             case S_TAP: RET(store_tap(e, s)); break;   // a copy, not one of our kernels
         }
+        if (ncu) cudaProfilerStop();
         if (s.kind != S_TAP) ++e->launches;
         if (e->profiling) {
             CK(cudaEventRecord(e->prof_events[nev], st));
@@ -664,6 +669,13 @@ int hfg_create(const hfg_config* cfg, int device, hfg_engine** out) {
     e->device = device;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     build_layers(e.get());
+    if (const char* nl = getenv("HFG_NCU_LAYERS")) {   // profiling aid: ncu --profile-from-start off captures only these
+        std::string cur;
+        for (const char* c = nl;; ++c) {
+            if (*c == ',' || *c == 0) { if (!cur.empty()) e->ncu_layers.push_back(cur); cur.clear(); if (!*c) break; }
+            else cur.push_back(*c);
+        }
+    }
     *out = e.release();
     return HFG_OK;
 }

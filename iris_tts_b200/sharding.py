@@ -1,0 +1,128 @@
+"""Multi-GPU partitioning of the vocoder hot path (one process per GPU, torch.distributed).
+
+The reference is single-device (src/iris/hifigan_pretrained.py:203-204) and has no batch or
+sequence parallelism; both modes below follow from the structure of HiFiGANModel.forward
+(:123-143): no op mixes batch items, and every output sample depends on at most +-12.63 mel
+frames of input (probed on the reference), so
+
+* a batch of utterances shards into contiguous slices with NO collective on the data path;
+* one long mel splits along time into chunks extended by a HALO of 16 frames on every inner
+  edge (>= 13 is exact); each rank synthesises its chunk, drops ``halo*hop`` samples per
+  extended edge, and ONE gather (NCCL over NVLink on GPUs, gloo in the CPU tests) stitches
+  the waveform on the destination rank.  True sequence edges keep the model's zero padding.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+HALO_FRAMES = 16
+
+
+def batch_shards(batch: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous [start, stop) utterance ranges, sizes differing by at most one; ranks beyond the batch get empty ranges."""
+    if world <= 0:
+        raise ValueError("world must be positive")
+    base, rem = divmod(max(batch, 0), world)
+    out, s = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((s, s + n))
+        s += n
+    return out
+
+
+@dataclasses.dataclass(frozen=True)
+class TimeChunk:
+    start: int      # first mel frame this rank is responsible for
+    stop: int       # one past the last
+    lo: int         # first frame actually fed to the generator (start - halo, clipped)
+    hi: int         # one past the last frame fed (stop + halo, clipped)
+
+    @property
+    def frames(self) -> int:
+        return self.stop - self.start
+
+    @property
+    def trim_front(self) -> int:
+        return self.start - self.lo
+
+    @property
+    def trim_back(self) -> int:
+        return self.hi - self.stop
+
+
+def time_chunks(frames: int, world: int, halo: int = HALO_FRAMES) -> List[TimeChunk]:
+    """Split ``frames`` mel frames into ``world`` contiguous chunks with receptive-field halos on inner edges."""
+    if halo < 0:
+        raise ValueError("halo must be non-negative")
+    out = []
+    for s, e in batch_shards(frames, world):
+        if e == s:
+            out.append(TimeChunk(s, e, s, e))
+        else:
+            out.append(TimeChunk(s, e, max(0, s - halo), min(frames, e + halo)))
+    return out
+
+
+def synthesize_chunk(synth: Callable, mel, chunk: TimeChunk, hop: int):
+    """Run ``synth`` (mel tensor [1, C, t] -> wave tensor [1, 1, t*hop]) on one chunk and drop the halo samples."""
+    import torch
+
+    if chunk.frames == 0:
+        return torch.empty(0, dtype=torch.float32, device=mel.device)
+    wav = synth(mel[:, :, chunk.lo:chunk.hi]).reshape(-1)
+    return wav[chunk.trim_front * hop: wav.numel() - chunk.trim_back * hop]
+
+
+def synthesize_longform(synth: Callable, mel, hop: int = 256, group=None, dst: int = 0, halo: int = HALO_FRAMES,
+                        all_ranks: bool = False):
+    """Time-sharded synthesis of ONE long mel across the ranks of ``group``.
+
+    ``mel``: tensor [1, C, T] or [C, T], identical on every rank, on the device ``synth`` computes on.
+    Returns the stitched waveform tensor [T*hop] on rank ``dst`` (every rank with ``all_ranks``), ``None`` elsewhere.
+    Exactly one collective: ``gather`` (``all_gather`` with ``all_ranks``) of ``ceil(T/world)*hop`` fp32 samples per rank.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if mel.dim() == 2:
+        mel = mel.unsqueeze(0)
+    if mel.dim() != 3 or mel.shape[0] != 1:
+        raise ValueError(f"long-form synthesis takes one utterance [1, C, T], got {tuple(mel.shape)}")
+    T = int(mel.shape[2])
+    if not (dist.is_available() and dist.is_initialized()):
+        return synthesize_chunk(synth, mel, TimeChunk(0, T, 0, T), hop)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    chunks = time_chunks(T, world, halo)
+    mine = synthesize_chunk(synth, mel, chunks[rank], hop)
+    slot = max(c.frames for c in chunks) * hop
+    buf = torch.zeros(slot, dtype=torch.float32, device=mel.device)
+    buf[: mine.numel()] = mine
+    if all_ranks:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf, group=group)
+    else:
+        parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, parts, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        if rank != dst:
+            return None
+    return torch.cat([p[: c.frames * hop] for p, c in zip(parts, chunks)])
+
+
+def synthesize_batch_sharded(synth: Callable, mel, group=None):
+    """Batch-sharded synthesis: this rank's contiguous slice of ``mel`` [B, C, T] -> ([b, 1, T*hop] tensor, (start, stop)).
+    No collective: callers keep per-rank outputs (bench.py) or write them into disjoint slices of a shared host buffer."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    s, e = batch_shards(int(mel.shape[0]), world)[rank]
+    if e == s:
+        return None, (s, e)
+    return synth(mel[s:e]), (s, e)

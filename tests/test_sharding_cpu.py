@@ -1,0 +1,115 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes run the sharding code with the ORACLE standing in for the
+CUDA generator (tests may use oracle/ as the checker).  Covers SURVEY.md section 8(e): batch shards need no
+collective; a long mel split along time with a 16-frame halo and one gather equals the unchunked forward."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from iris_tts_b200 import sharding
+from oracle import hifigan_oracle as O
+
+
+def test_batch_shards_are_contiguous_and_balanced():
+    assert sharding.batch_shards(16, 8) == [(2 * i, 2 * i + 2) for i in range(8)]
+    assert sharding.batch_shards(5, 4) == [(0, 2), (2, 3), (3, 4), (4, 5)]
+    assert sharding.batch_shards(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]      # B < n_gpu: idle ranks
+    assert sharding.batch_shards(0, 2) == [(0, 0), (0, 0)]
+    with pytest.raises(ValueError):
+        sharding.batch_shards(4, 0)
+
+
+def test_time_chunks_cover_the_mel_with_halos_on_inner_edges_only():
+    ch = sharding.time_chunks(10336, 8)            # BASELINE config 4: 120 s over 8 GPUs
+    assert [c.frames for c in ch] == [1292] * 8
+    assert ch[0].lo == 0 and ch[0].trim_front == 0 and ch[0].trim_back == 16
+    assert ch[7].hi == 10336 and ch[7].trim_back == 0 and ch[7].trim_front == 16
+    assert all(c.trim_front == 16 and c.trim_back == 16 for c in ch[1:7])
+    assert sum(c.frames for c in ch) == 10336
+    ragged = sharding.time_chunks(101, 4)
+    assert [c.frames for c in ragged] == [26, 25, 25, 25] and ragged[-1].stop == 101
+    tiny = sharding.time_chunks(3, 4)
+    assert [c.frames for c in tiny] == [1, 1, 1, 0]
+    assert tiny[1].lo == 0 and tiny[1].hi == 3     # halo clipped at the true sequence edges
+
+
+def test_single_process_longform_is_the_plain_forward():
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    mel = torch.from_numpy(O.synthetic_mel(1, 40, seed=3))
+    synth = lambda m: O.forward(sd, m, O.V2)  # noqa: E731
+    out = sharding.synthesize_longform(synth, mel, hop=256)
+    assert torch.equal(out, synth(mel).reshape(-1))
+
+
+def test_chunked_equals_unchunked_and_halo_requirement():
+    """Receptive field of the generator is +-12.63 frames: halo 16 is exact to fp32 noise, halo 4 is not."""
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    mel = torch.from_numpy(O.synthetic_mel(1, 120, seed=9, realistic=True))
+    synth = lambda m: O.forward(sd, m, O.V2)  # noqa: E731
+    full = synth(mel).reshape(-1)
+
+    def stitched(halo):
+        return torch.cat([sharding.synthesize_chunk(synth, mel, c, 256) for c in sharding.time_chunks(120, 3, halo)])
+
+    assert stitched(16).shape == full.shape
+    # fp32 noise only (oneDNN picks different blockings per length; loud weights put the output at std 0.2)
+    assert float((stitched(16) - full).abs().max()) <= 5e-6
+    assert float((stitched(4) - full).abs().max()) > 1e-4
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sd = O.random_state_dict(O.V2, seed=0, loud=True)
+        synth = lambda m: O.forward(sd, m, O.V2)  # noqa: E731
+        # long-form: odd length so the two chunks differ in size (exercises the padded gather slot)
+        mel = torch.from_numpy(O.synthetic_mel(1, 75, seed=11, realistic=True))
+        out = sharding.synthesize_longform(synth, mel, hop=256)
+        out_all = sharding.synthesize_longform(synth, mel[0], hop=256, all_ranks=True)
+        # batch shards: 3 utterances over 2 ranks, no collective
+        melb = torch.from_numpy(O.synthetic_mel(3, 20, seed=12))
+        part, (s, e) = sharding.synthesize_batch_sharded(synth, melb)
+        q.put((rank, None if out is None else out.numpy(), out_all.numpy(), part.numpy(), (s, e)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_longform_gather_and_batch_shards():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(world):
+        r = q.get(timeout=240)
+        results[r[0]] = r[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    full = O.forward(sd, torch.from_numpy(O.synthetic_mel(1, 75, seed=11, realistic=True)), O.V2).reshape(-1).numpy()
+    out0, all0, part0, r0 = results[0]
+    out1, all1, part1, r1 = results[1]
+    assert out1 is None and out0.shape == full.shape               # only dst holds the stitched waveform
+    assert np.abs(out0 - full).max() <= 5e-6
+    np.testing.assert_array_equal(all0, all1)
+    np.testing.assert_array_equal(all0, out0)
+    fullb = O.forward(sd, torch.from_numpy(O.synthetic_mel(3, 20, seed=12)), O.V2).numpy()
+    assert (r0, r1) == ((0, 2), (2, 3))
+    assert np.abs(np.concatenate([part0, part1]) - fullb).max() <= 5e-6
