@@ -62,12 +62,14 @@ struct Layer {
     __nv_bfloat16* d_wb_lo = nullptr;
 };
 
-enum StepKind { S_CONV32, S_UMMA, S_POST32, S_POSTBF, S_ACCUM, S_SPLIT, S_MEL_CL32, S_MEL_CLBF, S_TAP };
+enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_POST32, S_POSTBF, S_ACCUM, S_SPLIT, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_TAP };
 
 struct Step {
     StepKind kind;
     ConvParams cp;
     UmmaLaunch ul;
+    Umma2Launch u2;
+    MrfArgs mrf;
     // misc operands
     const float* f_in = nullptr;
     float* f_out = nullptr;
@@ -108,6 +110,7 @@ using namespace hfg;
 struct hfg_engine {
     hfg_config cfg;
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     std::vector<Layer> layers;
     std::map<std::string, int> index;
@@ -335,10 +338,11 @@ int env_flag(const char* name, int dflt) {
 // Builds (or, with base == nullptr, only sizes) the launch plan.
 //
 // fp32 family: raw fp32 streams everywhere, leaky_relu fused into the consumer's load.
-// tensor-core family: every conv reads ACTIVATED bf16 planes (leaky_relu applied by the
-// producer's epilogue) through TMA; residual / MRF streams stay fp32.  Stages narrower than
-// 32 channels (V2's tail) are bandwidth-bound and run on the fp32 family inside a
-// tensor-core plan.
+// tensor-core family: activations exist ONLY as activated bf16 planes P(x) = bf16(lrelu(x)) (+ a lo plane in
+// bf16x3): every conv reads them through TMA, writes them from its epilogue, and the residual add (:70)
+// recovers x by inverting leaky_relu.  The MRF mean (:133-137) is one elementwise pass over the nk branch
+// outputs per stage.  Stages narrower than 32 channels (V2's tail) run on the fp32 family inside a
+// tensor-core plan; the hand-over is the fp32 output of that MRF pass.
 int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* base, Plan* plan, size_t* bytes_out) {
     typedef __nv_bfloat16 bf;
     const hfg_config& c = e->cfg;
@@ -347,6 +351,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     const int a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
     const int c0 = c.upsample_initial_channel;
     const int NU = c.num_upsamples;
+    const int nk = c.num_kernels;
     // number of leading stages (after conv_pre) that run on tensor cores; -1: conv_pre is fp32 too
     int n_tc = -1;
     if (prec != HFG_PREC_FP32 && c0 % 32 == 0) {
@@ -378,26 +383,26 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     float* wave_dev = bump.take<float>((size_t)B * T * e->hop);
     if (real) { plan->mel_dev = mel_dev; plan->wave_dev = wave_dev; plan->keep_taps = keep_taps; }
 
-    // fp32 streams (both families)
-    float* u_raw = bump.take<float>(smax);
-    float* r_raw = bump.take<float>(smax);
-    float* xs = bump.take<float>(smax);
+    // fp32 streams: the fp32 family's working set, and the tap staging buffer of the tensor-core family
+    float* u_raw = any_32 ? bump.take<float>(smax) : nullptr;
+    float* r_raw = any_32 ? bump.take<float>(smax) : nullptr;
+    float* xs = (any_32 || keep_taps) ? bump.take<float>(smax) : nullptr;
     float* xt32 = any_32 ? bump.take<float>(smax) : nullptr;
+    float* tap_tmp = (any_tc && keep_taps) ? bump.take<float>(std::max(smax, n_pre)) : nullptr;
     float* post_tap = keep_taps ? bump.take<float>((size_t)B * T * e->hop) : nullptr;
-    // fp32-family conv_pre
     float* mel_cl = !any_tc ? bump.take<float>((size_t)B * T * c.in_channels) : nullptr;
-    float* x0_raw = (n_tc <= 0 || keep_taps) ? bump.take<float>(n_pre) : nullptr;
+    float* x0_raw = n_tc <= 0 ? bump.take<float>(n_pre) : nullptr;
     // tensor-core operand planes
-    bf *mel_hi = nullptr, *mel_lo = nullptr, *x0_hi = nullptr, *x0_lo = nullptr, *u_hi = nullptr, *u_lo = nullptr;
-    bf *r_hi = nullptr, *r_lo = nullptr, *xt_hi = nullptr, *xt_lo = nullptr, *s_hi = nullptr, *s_lo = nullptr;
+    struct Planes { bf* hi = nullptr; bf* lo = nullptr; };
+    auto take_planes = [&](size_t n) { Planes p; p.hi = bump.take<bf>(n); if (x3) p.lo = bump.take<bf>(n); return p; };
+    Planes mel_p, x0_p, u_p, xt_p, pp[2], s_p, r_p[HFG_MAX_KERNELS];
     if (any_tc) {
-        mel_hi = bump.take<bf>((size_t)B * T * pre.cin_pad);
-        if (x3) mel_lo = bump.take<bf>((size_t)B * T * pre.cin_pad);
-        x0_hi = bump.take<bf>(n_pre);
-        if (x3) x0_lo = bump.take<bf>(n_pre);
+        mel_p = take_planes((size_t)B * T * pre.cin_pad);
+        x0_p = take_planes(n_pre);
         if (n_tc > 0) {
-            u_hi = bump.take<bf>(smax); r_hi = bump.take<bf>(smax); xt_hi = bump.take<bf>(smax); s_hi = bump.take<bf>(smax);
-            if (x3) { u_lo = bump.take<bf>(smax); r_lo = bump.take<bf>(smax); xt_lo = bump.take<bf>(smax); s_lo = bump.take<bf>(smax); }
+            u_p = take_planes(smax); xt_p = take_planes(smax); pp[0] = take_planes(smax); pp[1] = take_planes(smax);
+            s_p = take_planes(smax);
+            for (int j = 0; j < nk; ++j) r_p[j] = take_planes(smax);
         }
     }
 
@@ -408,19 +413,24 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.flops = 2.0 * L.cin * L.cout * L.k * (L.transposed ? (double)Lin : Lout) * B;
         s.bytes = ((double)L.cin * Lin + (double)L.cout * Lout) * B * act_bytes + (double)L.cin * L.cout * L.k * act_bytes;
     };
-    auto umma = [&](const Layer& L, int Lin, const bf* xh, const bf* xl, const float* res, float* y_raw, bf* yh, bf* yl,
-                    float* xsp, int xs_read, int xs_write, float out_div) -> int {
+    // one conv on planes: persistent pipelined kernel where it applies, the v1 kernel otherwise
+    auto umma = [&](const Layer& L, int Lin, Planes x, Planes res, float* y_raw, Planes y) -> int {
         if (!real) return HFG_OK;
         Step s{};
-        s.kind = S_UMMA;
         UmmaConvParams p;
         memset(&p, 0, sizeof p);
         p.g = geom_of(L, B, Lin);
         p.cin_pad = L.cin_pad; p.kc = L.kc; p.npass = npass;
-        p.bias = L.d_bias; p.res = res; p.y_raw = y_raw; p.y_act = yh; p.y_act_lo = x3 ? yl : nullptr;
-        p.xs = xsp; p.xs_read = xs_read; p.xs_write = xs_write; p.out_div = out_div; p.a_per_tap = a_per_tap;
-        RET(plan_conv_umma(&s.ul, p, xh, xl, L.d_wb_hi, L.d_wb_lo));
+        p.bias = L.d_bias; p.res_hi = res.hi; p.res_lo = x3 ? res.lo : nullptr;
+        p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
+        p.a_per_tap = a_per_tap;
         work(s, L, Lin, 2);
+        if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, L.d_wb_hi, L.d_wb_lo, e->sm_count) == HFG_OK) {
+            s.kind = S_UMMA2;
+        } else {
+            s.kind = S_UMMA;
+            RET(plan_conv_umma(&s.ul, p, x.hi, x.lo, L.d_wb_hi, L.d_wb_lo));
+        }
         plan->steps.push_back(std::move(s));
         return HFG_OK;
     };
@@ -431,20 +441,28 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     };
     auto accum = [&](const float* r, size_t ne, int j) {
         Step s{}; s.kind = S_ACCUM; s.f_out = xs; s.f_in = r; s.n = ne; s.flag0 = j == 0;
-        s.fval = j == c.num_kernels - 1 ? (float)c.num_kernels : 0.f;
+        s.fval = j == nk - 1 ? (float)nk : 0.f;
         push(std::move(s));
+    };
+    auto to_raw = [&](Planes p, float* raw, size_t ne) {
+        Step s{}; s.kind = S_P2RAW; s.b_in = p.hi; s.b_in_lo = x3 ? p.lo : nullptr; s.f_out = raw; s.n = ne;
+        push(std::move(s));
+    };
+    auto tap_planes = [&](const char* name, Planes p, int C, int L) {
+        if (!keep_taps) return;
+        to_raw(p, tap_tmp, (size_t)B * L * C);
+        tap(name, tap_tmp, C, L);
     };
 
     // ---- conv_pre  (:124) ----
-    const float* x_raw = nullptr;           // raw fp32 input of the next upsampler (fp32 family)
-    const bf* xh = nullptr; const bf* xl = nullptr;   // activated planes (tensor-core family)
+    const float* x_raw = nullptr;   // raw fp32 input of the next upsampler (fp32 family)
+    Planes xp;                      // activated planes (tensor-core family)
     if (any_tc) {
-        { Step s{}; s.kind = S_MEL_CLBF; s.f_in = mel_dev; s.b_out = mel_hi; s.b_out_lo = mel_lo; s.B = B; s.C = c.in_channels;
+        { Step s{}; s.kind = S_MEL_CLBF; s.f_in = mel_dev; s.b_out = mel_p.hi; s.b_out_lo = mel_p.lo; s.B = B; s.C = c.in_channels;
           s.L = T; s.cpad = pre.cin_pad; push(std::move(s)); }
-        // raw fp32 copy only for taps or when the first upsampler runs on the fp32 family
-        RET(umma(pre, T, mel_hi, mel_lo, nullptr, x0_raw, n_tc > 0 ? x0_hi : nullptr, n_tc > 0 ? x0_lo : nullptr, nullptr, 0, 0, 0.f));
-        if (x0_raw) tap("conv_pre", x0_raw, c0, T);
-        x_raw = x0_raw; xh = x0_hi; xl = x0_lo;
+        RET(umma(pre, T, mel_p, Planes(), x0_raw, n_tc > 0 ? x0_p : Planes()));
+        if (n_tc > 0) tap_planes("conv_pre", x0_p, c0, T); else tap("conv_pre", x0_raw, c0, T);
+        x_raw = x0_raw; xp = x0_p;
     } else {
         { Step s{}; s.kind = S_MEL_CL32; s.f_in = mel_dev; s.f_out = mel_cl; s.B = B; s.C = c.in_channels; s.L = T; push(std::move(s)); }
         c32(pre, T, mel_cl, x0_raw, nullptr, 0, 0, 0.f);
@@ -460,53 +478,46 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         L *= up.stride;
         const size_t ne = (size_t)B * L * ch;
         const bool tc_stage = i < n_tc;
-        const bool next_tc = i + 1 < n_tc;   // the next stage reads bf16 planes
         if (tc_stage) {
-            RET(umma(up, Lin, xh, xl, nullptr, u_raw, u_hi, u_lo, nullptr, 0, 0, 0.f));   // lrelu -> ups  (:127-128)
-            snprintf(nm, sizeof nm, "ups.%d", i);
-            tap(nm, u_raw, ch, L);
             const bool last_stage = i == NU - 1;
+            const bool next_tc = i + 1 < n_tc;
             const bool want_planes = next_tc || last_stage;   // conv_post reads planes after a tensor-core stage
-            const bool want_raw = !last_stage && !next_tc;    // an fp32-family stage follows: it reads xs
-            for (int j = 0; j < c.num_kernels; ++j, ++n) {
-                const float* rr = u_raw; const bf* rh = u_hi; const bf* rl = u_lo;
+            const bool want_raw = (!last_stage && !next_tc) || keep_taps;   // an fp32-family stage follows (or the stage tap)
+            RET(umma(up, Lin, xp, Planes(), nullptr, u_p));   // lrelu -> ups  (:127-128)
+            snprintf(nm, sizeof nm, "ups.%d", i);
+            tap_planes(nm, u_p, ch, L);
+            for (int j = 0; j < nk; ++j, ++n) {
+                Planes xin = u_p;
                 const int nd = c.num_dilations[j];
-                const bool last_branch = j == c.num_kernels - 1;
                 for (int m = 0; m < nd; ++m) {
                     const Layer& c1 = layer("resblocks.%d.convs1.%d", n, m);
-                    RET(umma(c1, L, rh, rl, nullptr, nullptr, xt_hi, xt_lo, nullptr, 0, 0, 0.f));   // :66-67 (+ :68 in the epilogue)
+                    RET(umma(c1, L, xin, Planes(), nullptr, xt_p));               // :66-67 (+ :68 in the epilogue)
                     const Layer& c2 = layer("resblocks.%d.convs2.%d", n, m);
-                    const bool last = m == nd - 1;
-                    if (!last) {
-                        RET(umma(c2, L, xt_hi, xt_lo, rr, r_raw, r_hi, r_lo, nullptr, 0, 0, 0.f));   // :69-70
-                        rr = r_raw; rh = r_hi; rl = r_lo;
-                    } else if (keep_taps) {
-                        RET(umma(c2, L, xt_hi, xt_lo, rr, r_raw, nullptr, nullptr, nullptr, 0, 0, 0.f));
-                    } else {
-                        // x = xt + x ; xs (+)= x ; on the last branch xs /= num_kernels, planes = lrelu(xs)  (:70,:133-137)
-                        const bool wr = !last_branch || want_raw;
-                        RET(umma(c2, L, xt_hi, xt_lo, rr, nullptr, (last_branch && want_planes) ? s_hi : nullptr,
-                                 (last_branch && want_planes) ? s_lo : nullptr, xs, j > 0, wr,
-                                 last_branch ? (float)c.num_kernels : 0.f));
-                    }
+                    Planes xout = m == nd - 1 ? r_p[j] : pp[m & 1];
+                    RET(umma(c2, L, xt_p, xin, nullptr, xout));                   // :69-70
+                    xin = xout;
                 }
-                if (keep_taps) {
-                    snprintf(nm, sizeof nm, "resblocks.%d", n);
-                    tap(nm, r_raw, ch, L);
-                    accum(r_raw, ne, j);
-                }
+                snprintf(nm, sizeof nm, "resblocks.%d", n);
+                tap_planes(nm, r_p[j], ch, L);
             }
-            if (keep_taps) {
-                snprintf(nm, sizeof nm, "stage.%d", i);
-                tap(nm, xs, ch, L);
-                if (want_planes) { Step s{}; s.kind = S_SPLIT; s.f_in = xs; s.b_out = s_hi; s.b_out_lo = s_lo; s.n = ne; s.flag0 = 1; push(std::move(s)); }
+            {   // xs = sum_j r_j ; x = xs / nk  (:133-137)
+                Step s{}; s.kind = S_MRF; s.n = ne;
+                memset(&s.mrf, 0, sizeof s.mrf);
+                for (int j = 0; j < nk; ++j) { s.mrf.hi[j] = r_p[j].hi; s.mrf.lo[j] = x3 ? r_p[j].lo : nullptr; }
+                s.mrf.nk = nk;
+                s.mrf.out_hi = want_planes ? s_p.hi : nullptr;
+                s.mrf.out_lo = (want_planes && x3) ? s_p.lo : nullptr;
+                s.mrf.out_raw = want_raw ? xs : nullptr;
+                push(std::move(s));
             }
-            xh = s_hi; xl = s_lo; x_raw = xs;
+            snprintf(nm, sizeof nm, "stage.%d", i);
+            tap(nm, xs, ch, L);
+            xp = s_p; x_raw = xs;
         } else {
             c32(up, Lin, x_raw, u_raw, nullptr, 1, 0, 0.f);
             snprintf(nm, sizeof nm, "ups.%d", i);
             tap(nm, u_raw, ch, L);
-            for (int j = 0; j < c.num_kernels; ++j, ++n) {
+            for (int j = 0; j < nk; ++j, ++n) {
                 const float* r = u_raw;
                 const int nd = c.num_dilations[j];
                 for (int m = 0; m < nd; ++m) {
@@ -518,7 +529,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                         c32(c2, L, xt32, r_raw, r, 1, 0, 0.f);
                         r = r_raw;
                     } else {
-                        c32(c2, L, xt32, xs, r, 1, j > 0, j == c.num_kernels - 1 ? (float)c.num_kernels : 0.f);
+                        c32(c2, L, xt32, xs, r, 1, j > 0, j == nk - 1 ? (float)nk : 0.f);
                     }
                 }
                 if (keep_taps) {
@@ -529,7 +540,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
             }
             snprintf(nm, sizeof nm, "stage.%d", i);
             tap(nm, xs, ch, L);
-            x_raw = xs; xh = nullptr; xl = nullptr;
+            x_raw = xs; xp = Planes();
         }
     }
     // ---- lrelu -> conv_post -> tanh  (:139-141) ----
@@ -538,7 +549,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         Step s{};
         s.w = post.d_w32; s.bias = post.d_bias; s.f_out = pass ? wave_dev : post_tap;
         s.B = B; s.L = L; s.C = post.cin; s.k = post.k; s.flag0 = 1; s.flag1 = pass;
-        if (post_planes) { s.kind = S_POSTBF; s.b_in = xh; s.b_in_lo = xl; } else { s.kind = S_POST32; s.f_in = x_raw; }
+        if (post_planes) { s.kind = S_POSTBF; s.b_in = xp.hi; s.b_in_lo = x3 ? xp.lo : nullptr; } else { s.kind = S_POST32; s.f_in = x_raw; }
         work(s, post, L, post_planes ? 2 : 4);
         push(std::move(s));
         if (!pass) tap("conv_post", post_tap, 1, L);
@@ -564,6 +575,9 @@ const char* kind_label(StepKind k) {
     switch (k) {
         case S_CONV32: return "conv_cl_fp32";
         case S_UMMA: return "conv_umma";
+        case S_UMMA2: return "conv_umma2";
+        case S_P2RAW: return "planes_to_raw";
+        case S_MRF: return "mrf_combine";
         case S_POST32: case S_POSTBF: return "conv_post";
         case S_ACCUM: return "accum";
         case S_SPLIT: return "act_split";
@@ -590,6 +604,9 @@ int run_plan(hfg_engine* e, Plan* plan) {
         switch (s.kind) {
             case S_CONV32: CK(launch_conv_fp32(s.cp, st)); break;
             case S_UMMA: CK(launch_conv_umma(s.ul, st)); break;
+            case S_UMMA2: CK(launch_conv_umma2(s.u2, st)); break;
+            case S_P2RAW: CK(launch_planes_to_raw(s.b_in, s.b_in_lo, s.f_out, s.n, st)); break;
+            case S_MRF: CK(launch_mrf_combine(s.mrf, s.n, st)); break;
             case S_POST32: CK(launch_conv_post_fp32(s.f_in, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag0, s.flag1, st)); break;
             case S_POSTBF: CK(launch_conv_post_bf16(s.b_in, s.b_in_lo, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
             case S_ACCUM: CK(launch_accum_fp32(s.f_out, s.f_in, s.n, s.flag0, s.fval, st)); break;
@@ -667,6 +684,7 @@ int hfg_create(const hfg_config* cfg, int device, hfg_engine** out) {
     std::unique_ptr<hfg_engine> e(new hfg_engine());
     e->cfg = *cfg;
     e->device = device;
+    e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     build_layers(e.get());
     if (const char* nl = getenv("HFG_NCU_LAYERS")) {   // profiling aid: ncu --profile-from-start off captures only these
@@ -847,7 +865,7 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
     const ConvGeom g = geom_of(*lay, B, L);
     const size_t n_in = (size_t)B * lay->cin * L, n_out = (size_t)B * lay->cout * g.Lout;
     const size_t n_in_pad = (size_t)B * lay->cin_pad * L;
-    const size_t need = (2 * n_in + 2 * n_out) * sizeof(float) + 4 * n_in_pad * 2 + 16 * 256;
+    const size_t need = (2 * n_in + 2 * n_out) * sizeof(float) + 4 * n_in_pad * 2 + 4 * n_out * 2 + 16 * 256;
     if (need > e->scratch_bytes) {
         CK(cudaStreamSynchronize(e->stream));
         cudaFree(e->scratch);
@@ -862,6 +880,8 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
     float* y_cf = bump.take<float>(n_out);
     __nv_bfloat16* a_hi = bump.take<__nv_bfloat16>(n_in_pad);
     __nv_bfloat16* a_lo = bump.take<__nv_bfloat16>(n_in_pad);
+    __nv_bfloat16* y_hi = bump.take<__nv_bfloat16>(n_out);
+    __nv_bfloat16* y_lo = bump.take<__nv_bfloat16>(n_out);
     cudaStream_t st = e->stream;
     CK(cudaMemcpyAsync(x_cf, x, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
     if (lay->is_post) {
@@ -889,10 +909,21 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
         UmmaConvParams p;
         memset(&p, 0, sizeof p);
         p.g = g; p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1;
-        p.bias = lay->d_bias; p.y_raw = y_cl; p.a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
-        UmmaLaunch ul;
-        RET(plan_conv_umma(&ul, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo));
-        CK(launch_conv_umma(ul, st));
+        p.bias = lay->d_bias; p.a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
+        // The forward's production path for this layer: the persistent planes kernel where it applies (its output is the
+        // ACTIVATED plane, inverted back to the raw conv output here), the v1 kernel with an fp32 output otherwise.
+        p.y_act = y_hi; p.y_act_lo = x3 ? y_lo : nullptr;
+        Umma2Launch u2;
+        if (umma2_supported(p) && plan_conv_umma2(&u2, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo, e->sm_count) == HFG_OK) {
+            CK(launch_conv_umma2(u2, st));
+            CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, n_out, st));
+            ++e->launches;
+        } else {
+            p.y_act = nullptr; p.y_act_lo = nullptr; p.y_raw = y_cl;
+            UmmaLaunch ul;
+            RET(plan_conv_umma(&ul, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo));
+            CK(launch_conv_umma(ul, st));
+        }
         CK(launch_transpose_cl_to_cf(y_cl, y_cf, B, lay->cout, g.Lout, st));
         e->launches += 3;
     }

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -88,6 +89,8 @@ struct UmmaConvParams {
     int npass;            // 1: bf16 ; 3: bf16x3 (hi*hi + lo*hi + hi*lo)
     const float* bias;
     const float* res;     // fp32 [B][Lout][Cout] or nullptr
+    const __nv_bfloat16* res_hi;   // residual given as ACTIVATED planes (x recovered by inverting lrelu) or nullptr
+    const __nv_bfloat16* res_lo;
     float* y_raw;         // fp32 or nullptr
     __nv_bfloat16* y_act; // activated (lrelu) output plane or nullptr
     __nv_bfloat16* y_act_lo;
@@ -114,6 +117,33 @@ struct UmmaLaunch {
 int plan_conv_umma(UmmaLaunch* L, const UmmaConvParams& p, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                    const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo);
 cudaError_t launch_conv_umma(const UmmaLaunch& L, cudaStream_t s);
+
+// ---- persistent pipelined variant for plain Conv1d on planes (kernels_umma2.cu) ----
+// in: activated planes (A operand), optional residual planes; out: activated planes only.
+struct Umma2Launch {
+    struct Impl;
+    std::shared_ptr<Impl> impl;
+    int mt = 0, n_a = 0, n_w = 0, n_e = 0, w_resident = 0, grid = 0;
+    size_t smem = 0;
+};
+bool umma2_supported(const UmmaConvParams& p);
+int plan_conv_umma2(Umma2Launch* L, const UmmaConvParams& p, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                    const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int sm_count);
+cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s);
+
+// raw fp32 = inverse-lrelu(hi (+ lo))   (taps, and the hand-over to an fp32-family stage)
+cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t n, cudaStream_t s);
+// MRF combine (hifigan_pretrained.py:133-137) on planes: v = ((x0 + x1) + x2 ...) / nk with x_j = inverse-lrelu(plane j);
+// writes planes of lrelu(v) and/or raw fp32 v.
+struct MrfArgs {
+    const __nv_bfloat16* hi[HFG_MAX_KERNELS];
+    const __nv_bfloat16* lo[HFG_MAX_KERNELS];   // all nullptr in single-plane mode
+    int nk;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    float* out_raw;
+};
+cudaError_t launch_mrf_combine(const MrfArgs& a, size_t n, cudaStream_t s);
 
 void set_error(const std::string& msg);
 

@@ -316,6 +316,73 @@ __global__ void act_split_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     }
 }
 
+__device__ __forceinline__ float inv_lrelu(float p) { return p > 0.f ? p : p * (1.0f / kLreluSlope); }
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i8, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(hi) + i8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { f[2 * t] = __uint_as_float(w[t] << 16); f[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u); }
+    if (lo) {
+        const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lo) + i8);
+        const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { f[2 * t] += __uint_as_float(wl[t] << 16); f[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u); }
+    }
+}
+
+__global__ void planes_to_raw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ raw,
+                                     size_t n8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float f[8];
+        load8(hi, lo, i, f);
+        float4 a = make_float4(inv_lrelu(f[0]), inv_lrelu(f[1]), inv_lrelu(f[2]), inv_lrelu(f[3]));
+        float4 b = make_float4(inv_lrelu(f[4]), inv_lrelu(f[5]), inv_lrelu(f[6]), inv_lrelu(f[7]));
+        reinterpret_cast<float4*>(raw)[2 * i] = a;
+        reinterpret_cast<float4*>(raw)[2 * i + 1] = b;
+    }
+}
+
+__global__ void mrf_combine_kernel(const MrfArgs a, size_t n8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float v[8];
+        load8(a.hi[0], a.lo[0], i, v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = inv_lrelu(v[t]);
+        for (int j = 1; j < a.nk; ++j) {
+            float f[8];
+            load8(a.hi[j], a.lo[j], i, f);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = v[t] + inv_lrelu(f[t]);
+        }
+        const float d = (float)a.nk;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = __fdiv_rn(v[t], d);
+        if (a.out_raw) {
+            reinterpret_cast<float4*>(a.out_raw)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(a.out_raw)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (a.out_hi) {
+            __nv_bfloat162 h[4];
+            float l[8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float x0 = lrelu(v[2 * t]), x1 = lrelu(v[2 * t + 1]);
+                h[t] = __floats2bfloat162_rn(x0, x1);
+                l[2 * t] = x0 - __low2float(h[t]);
+                l[2 * t + 1] = x1 - __high2float(h[t]);
+            }
+            reinterpret_cast<uint4*>(a.out_hi)[i] = *reinterpret_cast<const uint4*>(h);
+            if (a.out_lo) {
+                __nv_bfloat162 hl[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) hl[t] = __floats2bfloat162_rn(l[2 * t], l[2 * t + 1]);
+                reinterpret_cast<uint4*>(a.out_lo)[i] = *reinterpret_cast<const uint4*>(hl);
+            }
+        }
+    }
+}
+
 cudaError_t launch_transpose(const float* in, float* out, int B, int R, int Cc, cudaStream_t s) {
     dim3 grid((Cc + 31) / 32, (R + 31) / 32, B);
     dim3 block(32, 8);
@@ -381,6 +448,22 @@ cudaError_t launch_accum_fp32(float* xs, const float* r, size_t n, int first, fl
     const size_t n4 = n / 4;
     const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 16);
     accum_fp32_kernel<<<blocks, 256, 0, s>>>(xs, r, n4, first, div);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t n, cudaStream_t s) {
+    if (n % 8 != 0) return cudaErrorInvalidValue;
+    const size_t n8 = n / 8;
+    const int blocks = (int)std::min<size_t>((n8 + 255) / 256, 148 * 16);
+    planes_to_raw_kernel<<<blocks, 256, 0, s>>>(hi, lo, raw, n8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mrf_combine(const MrfArgs& a, size_t n, cudaStream_t s) {
+    if (n % 8 != 0 || a.nk < 1 || a.nk > HFG_MAX_KERNELS) return cudaErrorInvalidValue;
+    const size_t n8 = n / 8;
+    const int blocks = (int)std::min<size_t>((n8 + 255) / 256, 148 * 16);
+    mrf_combine_kernel<<<blocks, 256, 0, s>>>(a, n8);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,7 @@
 #include <cstring>
 
 #include "hfg_internal.h"
+#include "umma_ptx.cuh"
 
 namespace hfg {
 
@@ -52,6 +53,8 @@ struct KArgs {
     uint32_t tmem_cols;
     const float* bias;
     const float* res;
+    const __nv_bfloat16* res_hi;
+    const __nv_bfloat16* res_lo;
     float* y_raw;
     __nv_bfloat16* y_act;
     __nv_bfloat16* y_act_lo;
@@ -60,118 +63,7 @@ struct KArgs {
     float out_div;
 };
 
-// ---------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 24); ++i)
-        if (mbar_try_wait(bar, parity)) return;
-    printf("hfg conv_umma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-    __trap();
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// tcgen05.commit implies tcgen05.fence::before_thread_sync
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory matrix descriptor (sm_100 format, version 1).
-//   128-byte rows: SWIZZLE_128B, 8-row groups 1024 B apart ; 64-byte rows: SWIZZLE_64B, 512 B apart.
-// The swizzle XOR acts on absolute smem address bits, so a start address advanced by whole
-// rows (a conv tap) or by 32 B (a K=16 step) addresses the TMA-written tile consistently as
-// long as the tile base is aligned to the swizzle pattern (1024 B here).
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t row_bytes) {
-    const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;   // SWIZZLE_128B : SWIZZLE_64B
-    const uint64_t sbo = (row_bytes * 8u) >> 4;
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * kLreluSlope; }
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
+using namespace ptx;
 
 // ---------------------------------------------------------------------------
 // Kernel
@@ -341,6 +233,24 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
                     for (int i = 0; i < 8; ++i) {
                         const float4 rv = *(reinterpret_cast<const float4*>(a.res + off) + i);
                         v[4 * i + 0] += rv.x; v[4 * i + 1] += rv.y; v[4 * i + 2] += rv.z; v[4 * i + 3] += rv.w;
+                    }
+                }
+                if (a.res_hi) {   // residual carried as activated planes: x = inverse-lrelu(hi (+ lo))
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 u = *(reinterpret_cast<const uint4*>(a.res_hi + off) + i);
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { f[2 * t] = __uint_as_float(w[t] << 16); f[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u); }
+                        if (a.res_lo) {
+                            const uint4 ul = *(reinterpret_cast<const uint4*>(a.res_lo + off) + i);
+                            const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) { f[2 * t] += __uint_as_float(wl[t] << 16); f[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u); }
+                        }
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) v[8 * i + t] += f[t] > 0.f ? f[t] : f[t] * (1.0f / kLreluSlope);
                     }
                 }
                 if (a.y_raw) {
@@ -568,6 +478,8 @@ cudaError_t launch_conv_umma(const UmmaLaunch& L, cudaStream_t s) {
     a.tmem_cols = L.tmem_cols;
     a.bias = p.bias;
     a.res = p.res;
+    a.res_hi = p.res_hi;
+    a.res_lo = p.res_lo;
     a.y_raw = p.y_raw;
     a.y_act = p.y_act;
     a.y_act_lo = p.y_act_lo;

@@ -1,0 +1,515 @@
+// conv_umma2: persistent, software-pipelined tcgen05 implicit-GEMM Conv1d on bf16 operand planes.
+//
+// Same math as conv_umma_kernel (kernels_umma.cu) for the plain (non-transposed) convolutions
+//   F.conv1d  src/iris/hifigan_pretrained.py:67,69   (ResBlock convs1 / convs2)
+// but organised so that an SM never idles between tiles:
+//
+//   * one CTA per SM, looping over (batch item, 128*MT-row block) tiles; N = C_out (<= 256) in one tile
+//   * weights RESIDENT in shared memory for the whole kernel when they fit (C <= 64, and C = 128 with k = 3),
+//     otherwise streamed through a TMA ring as in v1
+//   * A halo tiles (one per 64-channel K-chunk) prefetched through an NA-deep TMA ring, taps = row-shifted
+//     UMMA descriptors into that tile
+//   * TWO accumulator buffers in TMEM (2 * MT * N <= 512 columns): the MMA warp fills buffer (i+1)&1 while
+//     the epilogue warps drain buffer i&1
+//   * epilogue through shared memory: the residual operand planes arrive by TMA into a staging ring, each
+//     thread (one TMEM lane = one time row) combines  acc + bias + x  in place, and the activated bf16
+//     plane(s) leave by TMA store (coalesced, asynchronous, rows >= L clipped by the tensor map)
+//
+// Activations are carried ONLY as activated planes  P(x) = bf16(lrelu(x))  (+ lo = bf16(lrelu(x) - hi) in
+// bf16x3 mode).  leaky_relu is a bijection, so the residual  x = xt + x  (:70) recovers x from the plane:
+// x = p > 0 ? p : p / slope.  No fp32 activation stream exists in the tensor-core modes.
+//
+// Warp roles: 0 = A/W TMA producer, 1 = MMA issuer (+ TMEM alloc), 2 = residual TMA producer, 4..7 = epilogue.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "hfg_internal.h"
+#include "umma_ptx.cuh"
+
+namespace hfg {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kThreads2 = 256;
+constexpr int kMaxA = 6, kMaxW = 6, kMaxE = 8;
+constexpr uint32_t kSmemBudget = 227u * 1024u - 4096u;   // dynamic smem; static barriers/bias live outside
+
+struct K2Args {
+    int B, L, N;
+    int kc, nchunks, taps, tap_off0, tap_step, lo;
+    int planes, npass, mt;
+    int tiles_per_item, total_tiles;
+    int rows_a, a_box_rows, a_pieces;
+    int n_a, n_w, n_e, w_resident, has_res;
+    int ecols, groups;
+    uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
+    uint32_t off_w, off_e;
+    const float* bias;
+};
+
+__device__ __forceinline__ float inv_lrelu(float p) { return p > 0.f ? p : p * (1.0f / kLreluSlope); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                  const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
+                  const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo, const K2Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxW + 2 * kMaxE + 5];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float bias_s[256];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int planes = a.planes;
+    const uint32_t row_bytes = (uint32_t)a.kc * 2u;
+    const uint32_t erow_bytes = (uint32_t)a.ecols * 2u;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_stage_bytes = a.a_plane_bytes * planes;
+    const uint32_t w_stage_bytes = a.w_plane_bytes * planes;
+    const uint32_t e_slot_bytes = a.e_plane_bytes * planes;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_w = smem_base + a.off_w;
+    const uint32_t smem_e = smem_base + a.off_e;
+
+    uint32_t bp = smem_u32(&bars[0]);
+    const uint32_t bar_a_full = bp;            bp += 8 * kMaxA;
+    const uint32_t bar_a_empty = bp;           bp += 8 * kMaxA;
+    const uint32_t bar_w_full = bp;            bp += 8 * kMaxW;
+    const uint32_t bar_w_empty = bp;           bp += 8 * kMaxW;
+    const uint32_t bar_e_full = bp;            bp += 8 * kMaxE;
+    const uint32_t bar_e_empty = bp;           bp += 8 * kMaxE;
+    const uint32_t bar_acc_full = bp;          bp += 16;
+    const uint32_t bar_acc_empty = bp;         bp += 16;
+    const uint32_t bar_wres = bp;
+
+    for (int i = threadIdx.x; i < a.N; i += kThreads2) bias_s[i] = a.bias[i];
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_y_hi);
+        if (a.has_res) prefetch_tmap(&map_r_hi);
+        if (planes > 1) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); prefetch_tmap(&map_y_lo); if (a.has_res) prefetch_tmap(&map_r_lo); }
+    }
+    if (warp == 2 && lane == 0) {
+        for (int i = 0; i < a.n_a; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
+        for (int i = 0; i < a.n_w; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
+        for (int i = 0; i < a.n_e; ++i) { mbar_init(bar_e_full + 8 * i, 1); mbar_init(bar_e_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4); }
+        mbar_init(bar_wres, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(&tmem_base_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int acc_cols = a.mt * a.N;   // columns of one accumulator buffer
+
+    if (warp == 0) {
+        // ===== A / W producer =====
+        if (lane == 0) {
+            if (a.w_resident) {
+                mbar_expect_tx(bar_wres, (uint32_t)(a.nchunks * a.taps * planes) * (uint32_t)a.N * row_bytes);
+                for (int c = 0; c < a.nchunks; ++c)
+                    for (int j = 0; j < a.taps; ++j)
+                        for (int pl = 0; pl < planes; ++pl)
+                            tma_load_2d(smem_w + (uint32_t)(c * a.taps + j) * w_stage_bytes + pl * a.w_plane_bytes,
+                                        pl ? &map_w_lo : &map_w_hi, bar_wres, c * a.kc, j * a.N);
+            }
+            int sa = 0, sw = 0;
+            uint32_t pa = 0, pw = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_item;
+                const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
+                for (int c = 0; c < a.nchunks; ++c) {
+                    mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
+                    mbar_expect_tx(bar_a_full + 8 * sa, (uint32_t)a.rows_a * row_bytes * planes);
+                    for (int pl = 0; pl < planes; ++pl)
+                        for (int pc = 0; pc < a.a_pieces; ++pc)
+                            tma_load_3d(smem_a + sa * a_stage_bytes + pl * a.a_plane_bytes + pc * a.a_box_rows * row_bytes,
+                                        pl ? &map_a_lo : &map_a_hi, bar_a_full + 8 * sa, c * a.kc, m0 + a.lo + pc * a.a_box_rows, b);
+                    if (++sa == a.n_a) { sa = 0; pa ^= 1u; }
+                    if (!a.w_resident) {
+                        for (int j = 0; j < a.taps; ++j) {
+                            mbar_wait(bar_w_empty + 8 * sw, pw ^ 1u);
+                            mbar_expect_tx(bar_w_full + 8 * sw, (uint32_t)a.N * row_bytes * planes);
+                            for (int pl = 0; pl < planes; ++pl)
+                                tma_load_2d(smem_w + sw * w_stage_bytes + pl * a.w_plane_bytes, pl ? &map_w_lo : &map_w_hi,
+                                            bar_w_full + 8 * sw, c * a.kc, j * a.N);
+                            if (++sw == a.n_w) { sw = 0; pw ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
+            const int ksteps = a.kc / 16;
+            int sa = 0, sw = 0;
+            uint32_t pa = 0, pw = 0;
+            if (a.w_resident) mbar_wait(bar_wres, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(bar_acc_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols);
+                uint32_t first = 1;
+                for (int c = 0; c < a.nchunks; ++c) {
+                    mbar_wait(bar_a_full + 8 * sa, pa);
+                    for (int j = 0; j < a.taps; ++j) {
+                        uint32_t w_base;
+                        if (a.w_resident) {
+                            w_base = smem_w + (uint32_t)(c * a.taps + j) * w_stage_bytes;
+                        } else {
+                            mbar_wait(bar_w_full + 8 * sw, pw);
+                            w_base = smem_w + sw * w_stage_bytes;
+                        }
+                        tc_fence_after();
+                        const int shift = a.tap_off0 + j * a.tap_step - a.lo;
+                        for (int ps = 0; ps < a.npass; ++ps) {
+                            const int apl = ps == 1 ? 1 : 0;   // (hi,hi) (lo,hi) (hi,lo)
+                            const int wpl = ps == 2 ? 1 : 0;
+                            const uint32_t a_addr0 = smem_a + sa * a_stage_bytes + apl * a.a_plane_bytes + (uint32_t)shift * row_bytes;
+                            const uint32_t w_addr = w_base + wpl * a.w_plane_bytes;
+                            for (int ms = 0; ms < a.mt; ++ms) {
+                                const uint32_t a_addr = a_addr0 + (uint32_t)ms * 128u * row_bytes;
+                                const uint32_t d = d0 + (uint32_t)(ms * a.N);
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_bf16(d, make_desc(a_addr + k * 32, row_bytes), make_desc(w_addr + k * 32, row_bytes), idesc,
+                                              (first && ps == 0 && k == 0) ? 0u : 1u);
+                            }
+                        }
+                        first = 0;
+                        if (!a.w_resident) {
+                            umma_commit(bar_w_empty + 8 * sw);
+                            if (++sw == a.n_w) { sw = 0; pw ^= 1u; }
+                        }
+                    }
+                    umma_commit(bar_a_empty + 8 * sa);
+                    if (++sa == a.n_a) { sa = 0; pa ^= 1u; }
+                }
+                umma_commit(bar_acc_full + 8 * buf);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===== residual producer: one [128 x ecols] box of the residual planes per epilogue step =====
+        if (lane == 0 && a.has_res) {
+            int se = 0;
+            uint32_t pe = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_item;
+                const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
+                for (int ms = 0; ms < a.mt; ++ms) {
+                    const int row0 = m0 + ms * 128;
+                    if (row0 >= a.L) break;
+                    for (int g = 0; g < a.groups; ++g) {
+                        mbar_wait(bar_e_empty + 8 * se, pe ^ 1u);
+                        mbar_expect_tx(bar_e_full + 8 * se, 128u * erow_bytes * planes);
+                        for (int pl = 0; pl < planes; ++pl)
+                            tma_load_3d(smem_e + se * e_slot_bytes + pl * a.e_plane_bytes, pl ? &map_r_lo : &map_r_hi,
+                                        bar_e_full + 8 * se, g * a.ecols, row0, b);
+                        if (++se == a.n_e) { se = 0; pe ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;               // row of the 128-row subtile this thread owns
+        const bool issuer = (warp == 4 && lane == 0);
+        // 16-byte chunk swizzle of this row inside a TMA box: 128-byte rows XOR (row & 7); 64-byte rows XOR ((row >> 1) & 3)
+        const uint32_t sw_xor = erow_bytes == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+        const uint32_t row_off = (uint32_t)row * erow_bytes;
+        const int halves = a.ecols / 32;
+        int se = 0;
+        uint32_t pe = 0;
+        int prev_slot = -1;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            const int b = tile / a.tiles_per_item;
+            const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
+            const int buf = it & 1;
+            mbar_wait(bar_acc_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
+            tc_fence_after();
+            for (int ms = 0; ms < a.mt; ++ms) {
+                const int row0 = m0 + ms * 128;
+                if (row0 >= a.L) break;
+                for (int g = 0; g < a.groups; ++g) {
+                    if (a.has_res) mbar_wait(bar_e_full + 8 * se, pe);
+                    else mbar_wait(bar_e_empty + 8 * se, pe ^ 1u);
+                    const uint32_t slot = smem_e + se * e_slot_bytes;
+                    for (int h = 0; h < halves; ++h) {
+                        uint32_t r[32];
+                        const int col = g * a.ecols + h * 32;
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + ms * a.N + col), r);
+                        tmem_wait_ld();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[col + i];
+                        uint32_t addr[4];
+#pragma unroll
+                        for (int cidx = 0; cidx < 4; ++cidx)
+                            addr[cidx] = slot + row_off + ((((uint32_t)(h * 4 + cidx)) ^ sw_xor) << 4);
+                        if (a.has_res) {
+#pragma unroll
+                            for (int cidx = 0; cidx < 4; ++cidx) {
+                                float f[8];
+                                unpack8(lds128(addr[cidx]), f);
+                                if (planes > 1) {
+                                    float fl[8];
+                                    unpack8(lds128(addr[cidx] + a.e_plane_bytes), fl);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) f[i] += fl[i];
+                                }
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[cidx * 8 + i] += inv_lrelu(f[i]);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+#pragma unroll
+                        for (int cidx = 0; cidx < 4; ++cidx) {
+                            uint4 hi;
+                            hi.x = pack_bf16(v[cidx * 8 + 0], v[cidx * 8 + 1]);
+                            hi.y = pack_bf16(v[cidx * 8 + 2], v[cidx * 8 + 3]);
+                            hi.z = pack_bf16(v[cidx * 8 + 4], v[cidx * 8 + 5]);
+                            hi.w = pack_bf16(v[cidx * 8 + 6], v[cidx * 8 + 7]);
+                            sts128(addr[cidx], hi);
+                            if (planes > 1) {
+                                float fh[8];
+                                unpack8(hi, fh);
+                                uint4 lo;
+                                lo.x = pack_bf16(v[cidx * 8 + 0] - fh[0], v[cidx * 8 + 1] - fh[1]);
+                                lo.y = pack_bf16(v[cidx * 8 + 2] - fh[2], v[cidx * 8 + 3] - fh[3]);
+                                lo.z = pack_bf16(v[cidx * 8 + 4] - fh[4], v[cidx * 8 + 5] - fh[5]);
+                                lo.w = pack_bf16(v[cidx * 8 + 6] - fh[6], v[cidx * 8 + 7] - fh[7]);
+                                sts128(addr[cidx] + a.e_plane_bytes, lo);
+                            }
+                        }
+                    }
+                    if (ms == a.mt - 1 || row0 + 128 >= a.L) {
+                        if (g == a.groups - 1) {   // last TMEM read of this accumulator buffer by this warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+                        }
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                    if (issuer) {
+                        for (int pl = 0; pl < planes; ++pl)
+                            tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes, g * a.ecols, row0, b);
+                        bulk_commit();
+                        if (prev_slot >= 0) {          // the store issued one step ago has finished reading its slot
+                            bulk_wait_read<1>();
+                            mbar_arrive(bar_e_empty + 8 * prev_slot);
+                        }
+                        prev_slot = se;
+                    }
+                    if (++se == a.n_e) { se = 0; pe ^= 1u; }
+                }
+            }
+        }
+        if (issuer) bulk_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+bool encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+            uint32_t inner_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t gdim[3], gstr[2];
+    cuuint32_t bx[3], es[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+    const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (umma2) failed (%d) rank %d dims %llu,%llu box %u,%u", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        set_error(buf);
+        return false;
+    }
+    return true;
+}
+
+int env_i(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+uint32_t rup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct Umma2Launch::Impl {
+    K2Args a;
+    alignas(64) CUtensorMap map_a[2], map_w[2], map_r[2], map_y[2];
+    int grid;
+    size_t smem;
+};
+
+bool umma2_supported(const UmmaConvParams& p) {
+    const ConvGeom& g = p.g;
+    if (env_i("HFG_UMMA_V", 2) < 2) return false;
+    if (g.ups_s != 1 || g.Np != g.Cout || g.Cout > 256 || g.Cout % 32 != 0 || g.Cin != g.Cout) return false;
+    if (p.cin_pad != g.Cin) return false;
+    if (p.y_raw || p.res || p.xs || !p.y_act) return false;   // planes-only dataflow
+    return true;
+}
+
+int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                    const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int sm_count) {
+    const ConvGeom& g = p.g;
+    out->impl.reset();
+    if (!umma2_supported(p)) return HFG_ERR_UNSUPPORTED;
+    std::shared_ptr<Umma2Launch::Impl> I(new Umma2Launch::Impl());
+    K2Args& a = I->a;
+    memset(&a, 0, sizeof a);
+    const int planes = p.npass > 1 ? 2 : 1;
+    const int N = g.Cout;
+    const uint32_t row_bytes = (uint32_t)p.kc * 2u;
+    a.B = g.B; a.L = g.Lin; a.N = N;
+    a.kc = p.kc; a.nchunks = p.cin_pad / p.kc; a.taps = g.taps; a.tap_off0 = g.tap_off0; a.tap_step = g.tap_step;
+    const int last_off = g.tap_off0 + (g.taps - 1) * g.tap_step;
+    a.lo = std::min(g.tap_off0, last_off);
+    const int span = std::max(g.tap_off0, last_off) - a.lo;
+    a.planes = planes; a.npass = p.npass;
+    a.has_res = (p.res_hi != nullptr);
+    a.ecols = std::min(64, N);
+    a.groups = N / a.ecols;
+    a.e_plane_bytes = 128u * (uint32_t)a.ecols * 2u;
+    a.bias = p.bias;
+    const uint32_t e_slot = a.e_plane_bytes * planes;
+    const uint32_t w_plane = rup((uint32_t)N * row_bytes, 1024);
+    const uint32_t w_tile = w_plane * planes;
+    const uint32_t w_all = (uint32_t)(a.nchunks * a.taps) * w_tile;
+    a.w_plane_bytes = w_plane;
+
+    const int mt_max = std::max(1, std::min({256 / N, 4, env_i("HFG_U2_MT", 4), (g.Lin + 127) / 128}));
+    const uint32_t budget = kSmemBudget - 1024;   // alignment slack
+    bool ok = false;
+    for (int mt = mt_max; mt >= 1 && !ok; --mt) {
+        const int rows_need = mt * 128 + span;
+        const int pieces = (rows_need + 255) / 256;
+        const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
+        const uint32_t a_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
+        const uint32_t a_stage = a_plane * planes;
+        const int boxes = mt * a.groups;
+        for (int resident = 1; resident >= 0 && !ok; --resident) {
+            if (resident && (w_all > 120u * 1024u || env_i("HFG_U2_RESIDENT", 1) == 0)) continue;
+            for (int n_w = resident ? 1 : std::min(kMaxW, env_i("HFG_U2_NW", 4)); n_w >= (resident ? 1 : 2) && !ok; --n_w) {
+                const uint32_t w_bytes = resident ? w_all : (uint32_t)n_w * w_tile;
+                for (int n_e = std::min({kMaxE, std::max(2, boxes), env_i("HFG_U2_NE", 8)}); n_e >= 2 && !ok; --n_e) {
+                    const uint32_t fixed = w_bytes + (uint32_t)n_e * e_slot;
+                    if (fixed + 2 * a_stage > budget) continue;
+                    int n_a = (int)std::min<uint32_t>((budget - fixed) / a_stage, (uint32_t)std::min(kMaxA, env_i("HFG_U2_NA", 4)));
+                    if (n_a < 2) continue;
+                    a.mt = mt; a.rows_a = pieces * box_rows; a.a_box_rows = box_rows; a.a_pieces = pieces;
+                    a.a_plane_bytes = a_plane; a.n_a = n_a; a.n_w = resident ? 1 : n_w; a.n_e = n_e; a.w_resident = resident;
+                    a.off_w = (uint32_t)n_a * a_stage;
+                    a.off_e = a.off_w + w_bytes;
+                    I->smem = std::max<size_t>((size_t)a.off_e + (size_t)n_e * e_slot + 1024, 120u * 1024u);   // > half an SM: one CTA (512 TMEM columns) per SM
+                    ok = true;
+                }
+            }
+        }
+    }
+    if (!ok) return HFG_ERR_UNSUPPORTED;
+    a.tiles_per_item = (g.Lin + a.mt * 128 - 1) / (a.mt * 128);
+    a.total_tiles = a.tiles_per_item * g.B;
+    I->grid = std::min(a.total_tiles, std::max(1, sm_count));
+
+    const uint64_t dims3[3] = {(uint64_t)g.Cin, (uint64_t)g.Lin, (uint64_t)g.B};
+    const uint64_t str3[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Lin * g.Cin * 2};
+    {
+        const uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)a.a_box_rows, 1};
+        if (!encode(&I->map_a[0], x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_a[1], planes > 1 ? x_lo : x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)p.cin_pad, (uint64_t)g.taps * N};
+        const uint64_t str[1] = {(uint64_t)p.cin_pad * 2};
+        const uint32_t box[2] = {(uint32_t)p.kc, (uint32_t)N};
+        if (!encode(&I->map_w[0], w_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_w[1], planes > 1 ? w_lo : w_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
+    }
+    {
+        const uint32_t box[3] = {(uint32_t)a.ecols, 128, 1};
+        const uint32_t eb = (uint32_t)a.ecols * 2u;
+        const void* r0 = a.has_res ? (const void*)p.res_hi : (const void*)p.y_act;
+        const void* r1 = (a.has_res && planes > 1) ? (const void*)p.res_lo : r0;
+        if (!encode(&I->map_r[0], r0, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_r[1], r1, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_y[0], p.y_act, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
+    }
+    out->impl = I;
+    out->mt = a.mt; out->n_a = a.n_a; out->n_w = a.n_w; out->n_e = a.n_e; out->w_resident = a.w_resident;
+    out->smem = I->smem; out->grid = I->grid;
+    return HFG_OK;
+}
+
+cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev % 64]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e != cudaSuccess) return e;
+        configured[dev % 64] = true;
+    }
+    const Umma2Launch::Impl& I = *L.impl;
+    conv_umma2_kernel<<<I.grid, kThreads2, I.smem, s>>>(I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1],
+                                                       I.map_y[0], I.map_y[1], I.a);
+    return cudaGetLastError();
+}
+
+}  // namespace hfg
