@@ -157,13 +157,18 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        // Warp-uniform loops; the elected lane issues.  Descriptors advance by one add per MMA.
+        {
+            const bool leader = elect_one();
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-            const int ksteps = a.kc / 16;
+            const uint32_t dhi = desc_hi(row_bytes);
+            const uint32_t sub_step = (128u * row_bytes) >> 4;
+            const uint32_t a_pl_step = a.a_plane_bytes >> 4, w_pl_step = a.w_plane_bytes >> 4;
+            const bool k4 = a.kc == 64;
             int sa = 0, sw = 0;
             uint32_t pa = 0, pw = 0;
-            uint32_t first = 1;
+            uint32_t acc = 0;
             for (int c = 0; c < a.nchunks; ++c) {
                 if (!a.a_per_tap) mbar_wait(bar_a_full + 8 * sa, pa);
                 for (int j = 0; j < a.g.taps; ++j) {
@@ -171,33 +176,35 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
                     mbar_wait(bar_w_full + 8 * sw, pw);
                     tc_fence_after();
                     const int shift = a.a_per_tap ? 0 : (a.g.tap_off0 + j * a.g.tap_step - a.lo);
+                    const uint32_t a_lo0 = desc_lo(smem_a + sa * a_stage_bytes) + (((uint32_t)shift * row_bytes) >> 4);
+                    const uint32_t w_lo0 = desc_lo(smem_w + sw * w_stage_bytes);
                     for (int ps = 0; ps < a.npass; ++ps) {
-                        const int apl = ps == 1 ? 1 : 0;   // (hi,hi) (lo,hi) (hi,lo)
-                        const int wpl = ps == 2 ? 1 : 0;
-                        const uint32_t a_addr0 = smem_a + sa * a_stage_bytes + apl * a.a_plane_bytes + (uint32_t)shift * row_bytes;
-                        const uint32_t w_addr = smem_w + sw * w_stage_bytes + wpl * a.w_plane_bytes;
+                        uint32_t a_lo = a_lo0 + (ps == 1 ? a_pl_step : 0u);   // (hi,hi) (lo,hi) (hi,lo)
+                        const uint32_t w_lo = w_lo0 + (ps == 2 ? w_pl_step : 0u);
+                        uint32_t d = tmem_base;
                         for (int ms = 0; ms < a.mt; ++ms) {
-                            const uint32_t a_addr = a_addr0 + (uint32_t)ms * 128u * row_bytes;
-                            const uint32_t d = tmem_base + (uint32_t)(ms * a.n_tile);
-                            for (int k = 0; k < ksteps; ++k)
-                                umma_bf16(d, make_desc(a_addr + k * 32, row_bytes), make_desc(w_addr + k * 32, row_bytes), idesc,
-                                          (first && ps == 0 && k == 0) ? 0u : 1u);
+                            if (leader) {
+                                if (k4) umma_ksteps<4>(d, a_lo, w_lo, dhi, idesc, acc);
+                                else umma_ksteps<2>(d, a_lo, w_lo, dhi, idesc, acc);
+                            }
+                            a_lo += sub_step;
+                            d += (uint32_t)a.n_tile;
                         }
+                        acc = 1;
                     }
-                    first = 0;
-                    umma_commit(bar_w_empty + 8 * sw);
+                    if (leader) umma_commit(bar_w_empty + 8 * sw);
                     if (++sw == a.n_w) { sw = 0; pw ^= 1u; }
                     if (a.a_per_tap) {
-                        umma_commit(bar_a_empty + 8 * sa);
+                        if (leader) umma_commit(bar_a_empty + 8 * sa);
                         if (++sa == a.n_a) { sa = 0; pa ^= 1u; }
                     }
                 }
                 if (!a.a_per_tap) {
-                    umma_commit(bar_a_empty + 8 * sa);
+                    if (leader) umma_commit(bar_a_empty + 8 * sa);
                     if (++sa == a.n_a) { sa = 0; pa ^= 1u; }
                 }
             }
-            umma_commit(bar_acc);
+            if (leader) umma_commit(bar_acc);
         }
         __syncwarp();
     } else if (warp >= 4) {

@@ -89,6 +89,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Descriptor low word (start address >> 4 | LBO) and the constant high word (SBO, version, swizzle): advancing the
+// operand by `bytes` (a multiple of 16) is  lo += bytes >> 4  -- one add per MMA in the issue loop.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t row_bytes) {
+    const uint32_t layout = row_bytes == 128 ? 2u : 4u;   // SWIZZLE_128B : SWIZZLE_64B
+    return ((row_bytes * 8u) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+        : "memory");
+}
+// KSTEPS consecutive K=16 slices of one (tap, pass, 128-row subtile): operands advance by 32 bytes per slice.
+template <int KSTEPS>
+__device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) umma_bf16_lh(d_tmem, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, k == 0 ? acc0 : 1u);
+}
 // tcgen05.commit implies tcgen05.fence::before_thread_sync
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--L", type=int, default=333)
     ap.add_argument("--modes", default="fp32,bf16x3,bf16")
     ap.add_argument("--cfgs", default="v1,v2,v3")
+    ap.add_argument("--no-apt", action="store_true", help="skip the HFG_UMMA_A_PER_TAP=1 variants")
     a = ap.parse_args()
     if a.one:
         sys.exit(run_one(a.one, a.cfg, a.B, a.L))
@@ -125,7 +126,7 @@ def main():
     for cfg in a.cfgs.split(","):
         for mode in a.modes.split(","):
             for env_extra in ({}, {"HFG_UMMA_A_PER_TAP": "1"}):
-                if env_extra and mode == "fp32":
+                if env_extra and (mode == "fp32" or a.no_apt):
                     continue
                 env = dict(os.environ, **env_extra)
                 tag = f"{cfg}/{mode}" + ("/a_per_tap" if env_extra else "")
