@@ -19,7 +19,8 @@
 // bf16x3 mode).  leaky_relu is a bijection, so the residual  x = xt + x  (:70) recovers x from the plane:
 // x = p > 0 ? p : p / slope.  No fp32 activation stream exists in the tensor-core modes.
 //
-// Warp roles: 0 = A/W TMA producer, 1 = MMA issuer (+ TMEM alloc), 2 = residual TMA producer, 4..7 = epilogue.
+// Warp roles: 0 = A/W TMA producer, 1 = residual TMA producer, 2 = TMEM allocator, 4..7 = epilogue, 8..11 = MMA issuers
+// (issuer w owns the 128-row subtile w of every tile: small-N MMAs are issue-bound from one thread).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -33,7 +34,7 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kThreads2 = 256;
+constexpr int kThreads2 = 384;   // 12 warps: 0 A/W producer, 1 residual producer, 2 TMEM alloc, 4-7 epilogue, 8-11 MMA issuers
 constexpr int kMaxA = 6, kMaxW = 6, kMaxE = 8;
 constexpr uint32_t kSmemBudget = 227u * 1024u - 4096u;   // dynamic smem; static barriers/bias live outside
 
@@ -45,6 +46,7 @@ struct K2Args {
     int rows_a, a_box_rows, a_pieces;
     int n_a, n_w, n_e, w_resident, has_res;
     int ecols, groups;
+    int dbg;   // HFG_U2_DBG (timing experiments only): 1 = epilogue does no work, 2 = MMA warp issues no MMAs
     uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
     uint32_t off_w, off_e;
     const float* bias;
@@ -69,7 +71,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxW + 2 * kMaxE + 5];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float bias_s[256];
+    __shared__ __align__(16) float bias_s[256];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -102,15 +104,16 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (a.has_res) prefetch_tmap(&map_r_hi);
         if (planes > 1) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); prefetch_tmap(&map_y_lo); if (a.has_res) prefetch_tmap(&map_r_lo); }
     }
-    if (warp == 2 && lane == 0) {
-        for (int i = 0; i < a.n_a; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
-        for (int i = 0; i < a.n_w; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
-        for (int i = 0; i < a.n_e; ++i) { mbar_init(bar_e_full + 8 * i, 1); mbar_init(bar_e_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4); }
+    if (warp == 3 && lane == 0) {
+        const uint32_t nmma = (uint32_t)a.mt;   // one issuing warp per 128-row subtile
+        for (int i = 0; i < a.n_a; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, nmma); }
+        for (int i = 0; i < a.n_w; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, nmma); }
+        for (int i = 0; i < a.n_e; ++i) { mbar_init(bar_e_full + 8 * i, 1); mbar_init(bar_e_empty + 8 * i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, nmma); mbar_init(bar_acc_empty + 8 * i, 4); }
         mbar_init(bar_wres, 1);
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == 2) {
         tmem_alloc(smem_u32(&tmem_base_slot), 512);
         tmem_relinquish();
     }
@@ -137,13 +140,15 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int b = tile / a.tiles_per_item;
                 const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
                 for (int c = 0; c < a.nchunks; ++c) {
-                    mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
-                    mbar_expect_tx(bar_a_full + 8 * sa, (uint32_t)a.rows_a * row_bytes * planes);
-                    for (int pl = 0; pl < planes; ++pl)
-                        for (int pc = 0; pc < a.a_pieces; ++pc)
-                            tma_load_3d(smem_a + sa * a_stage_bytes + pl * a.a_plane_bytes + pc * a.a_box_rows * row_bytes,
-                                        pl ? &map_a_lo : &map_a_hi, bar_a_full + 8 * sa, c * a.kc, m0 + a.lo + pc * a.a_box_rows, b);
-                    if (++sa == a.n_a) { sa = 0; pa ^= 1u; }
+                    if (a.dbg != 3) {
+                        mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
+                        mbar_expect_tx(bar_a_full + 8 * sa, (uint32_t)a.rows_a * row_bytes * planes);
+                        for (int pl = 0; pl < planes; ++pl)
+                            for (int pc = 0; pc < a.a_pieces; ++pc)
+                                tma_load_3d(smem_a + sa * a_stage_bytes + pl * a.a_plane_bytes + pc * a.a_box_rows * row_bytes,
+                                            pl ? &map_a_lo : &map_a_hi, bar_a_full + 8 * sa, c * a.kc, m0 + a.lo + pc * a.a_box_rows, b);
+                        if (++sa == a.n_a) { sa = 0; pa ^= 1u; }
+                    }
                     if (!a.w_resident) {
                         for (int j = 0; j < a.taps; ++j) {
                             mbar_wait(bar_w_empty + 8 * sw, pw ^ 1u);
@@ -158,11 +163,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        // The whole warp walks the loops (all values warp-uniform, so they live in uniform registers); only the
+    } else if (warp >= 8) {
+        // ===== MMA issuers =====
+        // Issuer warp w owns subtile ms = w of every tile.  The whole warp walks the loops (warp-uniform values); only the
         // elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors advance by one add per MMA.
-        {
+        const int my_ms = warp - 8;
+        if (my_ms < a.mt) {
             const bool leader = elect_one();
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t dhi = desc_hi(row_bytes);
@@ -177,11 +183,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int buf = it & 1;
                 mbar_wait(bar_acc_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols);
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols + my_ms * a.N);
                 uint32_t acc = 0;
                 for (int c = 0; c < a.nchunks; ++c) {
-                    mbar_wait(bar_a_full + 8 * sa, pa);
-                    const uint32_t a_stage_lo = desc_lo(smem_a + sa * a_stage_bytes);
+                    if (a.dbg != 3) mbar_wait(bar_a_full + 8 * sa, pa);
+                    const uint32_t a_stage_lo = desc_lo(smem_a + sa * a_stage_bytes) + (uint32_t)my_ms * sub_step;
                     for (int j = 0; j < a.taps; ++j) {
                         uint32_t w_lo0;
                         if (a.w_resident) {
@@ -193,16 +199,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         tc_fence_after();
                         const uint32_t a_lo0 = a_stage_lo + (((uint32_t)(a.tap_off0 + j * a.tap_step - a.lo) * row_bytes) >> 4);
                         for (int ps = 0; ps < a.npass; ++ps) {
-                            uint32_t a_lo = a_lo0 + (ps == 1 ? a_pl_step : 0u);   // (hi,hi) (lo,hi) (hi,lo)
+                            const uint32_t a_lo = a_lo0 + (ps == 1 ? a_pl_step : 0u);   // (hi,hi) (lo,hi) (hi,lo)
                             const uint32_t w_lo = w_lo0 + (ps == 2 ? w_pl_step : 0u);
-                            uint32_t d = d0;
-                            for (int ms = 0; ms < a.mt; ++ms) {
-                                if (leader) {
-                                    if (k4) umma_ksteps<4>(d, a_lo, w_lo, dhi, idesc, acc);
-                                    else umma_ksteps<2>(d, a_lo, w_lo, dhi, idesc, acc);
-                                }
-                                a_lo += sub_step;
-                                d += (uint32_t)a.N;
+                            if (leader && a.dbg != 2) {
+                                if (k4) umma_ksteps<4>(d0, a_lo, w_lo, dhi, idesc, acc);
+                                else umma_ksteps<2>(d0, a_lo, w_lo, dhi, idesc, acc);
                             }
                             acc = 1;
                         }
@@ -218,9 +219,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 __syncwarp();
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == 1) {
         // ===== residual producer: one [128 x ecols] box of the residual planes per epilogue step =====
-        if (lane == 0 && a.has_res) {
+        if (lane == 0 && a.has_res && a.dbg != 1 && a.dbg != 3) {
             int se = 0;
             uint32_t pe = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -243,16 +244,19 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue =====
+        // Each warp owns 32 rows (its TMEM lane quarter) of every 128-row subtile and runs independently of the other
+        // three: its rows of the staging box are combined in place and leave through its own 32-row TMA store.
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;               // row of the 128-row subtile this thread owns
-        const bool issuer = (warp == 4 && lane == 0);
         // 16-byte chunk swizzle of this row inside a TMA box: 128-byte rows XOR (row & 7); 64-byte rows XOR ((row >> 1) & 3)
         const uint32_t sw_xor = erow_bytes == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
         const uint32_t row_off = (uint32_t)row * erow_bytes;
+        const uint32_t warp_off = (uint32_t)(q * 32) * erow_bytes;
         const int halves = a.ecols / 32;
+        const int depth = a.n_e >= 4 ? 2 : 1;        // stores in flight before a slot is handed back
         int se = 0;
         uint32_t pe = 0;
-        int prev_slot = -1;
+        int hist[2] = {-1, -1};                      // slots of the last `depth` stores (lane 0)
         int it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             const int b = tile / a.tiles_per_item;
@@ -260,6 +264,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const int buf = it & 1;
             mbar_wait(bar_acc_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
+            if (a.dbg == 1 || a.dbg == 3) {   // timing experiment: drain nothing
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+                continue;
+            }
             for (int ms = 0; ms < a.mt; ++ms) {
                 const int row0 = m0 + ms * 128;
                 if (row0 >= a.L) break;
@@ -271,14 +281,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         uint32_t r[32];
                         const int col = g * a.ecols + h * 32;
                         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + ms * a.N + col), r);
-                        tmem_wait_ld();
-                        float v[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias_s[col + i];
                         uint32_t addr[4];
 #pragma unroll
                         for (int cidx = 0; cidx < 4; ++cidx)
                             addr[cidx] = slot + row_off + ((((uint32_t)(h * 4 + cidx)) ^ sw_xor) << 4);
+                        float res[32];
                         if (a.has_res) {
 #pragma unroll
                             for (int cidx = 0; cidx < 4; ++cidx) {
@@ -291,8 +298,22 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                                     for (int i = 0; i < 8; ++i) f[i] += fl[i];
                                 }
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) v[cidx * 8 + i] += inv_lrelu(f[i]);
+                                for (int i = 0; i < 8; ++i) res[cidx * 8 + i] = inv_lrelu(f[i]);
                             }
+                        }
+                        tmem_wait_ld();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 bv = *reinterpret_cast<const float4*>(&bias_s[col + 4 * i]);
+                            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bv.x;
+                            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv.y;
+                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv.z;
+                            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv.w;
+                        }
+                        if (a.has_res) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += res[i];
                         }
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
@@ -316,35 +337,36 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             }
                         }
                     }
-                    if (ms == a.mt - 1 || row0 + 128 >= a.L) {
-                        if (g == a.groups - 1) {   // last TMEM read of this accumulator buffer by this warp
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
-                        }
+                    if ((ms == a.mt - 1 || row0 + 128 >= a.L) && g == a.groups - 1) {
+                        tc_fence_before();   // last TMEM read of this accumulator buffer by this warp
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
                     }
                     fence_proxy_async();
-                    named_bar_sync(1, 128);
-                    if (issuer) {
+                    __syncwarp();
+                    if (lane == 0) {
                         for (int pl = 0; pl < planes; ++pl)
-                            tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes, g * a.ecols, row0, b);
+                            tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, g * a.ecols, row0 + q * 32, b);
                         bulk_commit();
-                        if (prev_slot >= 0) {          // the store issued one step ago has finished reading its slot
-                            bulk_wait_read<1>();
-                            mbar_arrive(bar_e_empty + 8 * prev_slot);
+                        // hand back the slot whose store was issued `depth` steps ago: its shared-memory reads are done
+                        if (depth == 2) {
+                            if (hist[1] >= 0) { bulk_wait_read<2>(); mbar_arrive(bar_e_empty + 8 * hist[1]); }
+                            hist[1] = hist[0]; hist[0] = se;
+                        } else {
+                            if (hist[0] >= 0) { bulk_wait_read<1>(); mbar_arrive(bar_e_empty + 8 * hist[0]); }
+                            hist[0] = se;
                         }
-                        prev_slot = se;
                     }
                     if (++se == a.n_e) { se = 0; pe ^= 1u; }
                 }
             }
         }
-        if (issuer) bulk_wait_read<0>();
+        if (lane == 0) bulk_wait_read<0>();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------
@@ -434,6 +456,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     a.groups = N / a.ecols;
     a.e_plane_bytes = 128u * (uint32_t)a.ecols * 2u;
     a.bias = p.bias;
+    a.dbg = env_i("HFG_U2_DBG", 0);
     const uint32_t e_slot = a.e_plane_bytes * planes;
     const uint32_t w_plane = rup((uint32_t)N * row_bytes, 1024);
     const uint32_t w_tile = w_plane * planes;
@@ -454,7 +477,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
             if (resident && (w_all > 120u * 1024u || env_i("HFG_U2_RESIDENT", 1) == 0)) continue;
             for (int n_w = resident ? 1 : std::min(kMaxW, env_i("HFG_U2_NW", 4)); n_w >= (resident ? 1 : 2) && !ok; --n_w) {
                 const uint32_t w_bytes = resident ? w_all : (uint32_t)n_w * w_tile;
-                for (int n_e = std::min({kMaxE, std::max(2, boxes), env_i("HFG_U2_NE", 8)}); n_e >= 2 && !ok; --n_e) {
+                for (int n_e = std::min({kMaxE, std::max(2, 2 * boxes), env_i("HFG_U2_NE", 8)}); n_e >= 2 && !ok; --n_e) {
                     const uint32_t fixed = w_bytes + (uint32_t)n_e * e_slot;
                     if (fixed + 2 * a_stage > budget) continue;
                     int n_a = (int)std::min<uint32_t>((budget - fixed) / a_stage, (uint32_t)std::min(kMaxA, env_i("HFG_U2_NA", 4)));
@@ -495,8 +518,9 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
         const void* r1 = (a.has_res && planes > 1) ? (const void*)p.res_lo : r0;
         if (!encode(&I->map_r[0], r0, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
         if (!encode(&I->map_r[1], r1, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
-        if (!encode(&I->map_y[0], p.y_act, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
-        if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
+        const uint32_t ybox[3] = {(uint32_t)a.ecols, 32, 1};   // one epilogue warp's rows
+        if (!encode(&I->map_y[0], p.y_act, 3, dims3, str3, ybox, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 3, dims3, str3, ybox, eb)) return HFG_ERR_CUDA;
     }
     out->impl = I;
     out->mt = a.mt; out->n_a = a.n_a; out->n_w = a.n_w; out->n_e = a.n_e; out->w_resident = a.w_resident;
