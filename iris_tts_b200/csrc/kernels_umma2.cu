@@ -22,6 +22,7 @@
 // Warp roles: 0 = A/W TMA producer, 1 = residual TMA producer, 2 = TMEM allocator, 4..7 = epilogue, 8..11 = MMA issuers
 // (issuer w owns the 128-row subtile w of every tile: small-N MMAs are issue-bound from one thread).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -46,6 +47,7 @@ struct K2Args {
     int rows_a, a_box_rows, a_pieces;
     int n_a, n_w, n_e, w_resident, has_res;
     int ecols, groups;
+    int paired;   // C = 32: residual / output boxes address two 64-byte time rows as one 128-byte row (full-line TMA requests)
     int dbg;   // HFG_U2_DBG (timing experiments only): 1 = epilogue does no work, 2 = MMA warp issues no MMAs
     uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
     uint32_t off_w, off_e;
@@ -63,6 +65,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     }
 }
 
+template <int kPlanes, bool kHasRes>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -75,9 +78,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int planes = a.planes;
+    constexpr int planes = kPlanes;          // 1: bf16 ; 2: bf16x3 (hi + lo operand planes, three MMA passes)
+    constexpr int npass = kPlanes == 2 ? 3 : 1;
     const uint32_t row_bytes = (uint32_t)a.kc * 2u;
-    const uint32_t erow_bytes = (uint32_t)a.ecols * 2u;
+    const uint32_t erow_bytes = a.paired ? 128u : (uint32_t)a.ecols * 2u;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_stage_bytes = a.a_plane_bytes * planes;
@@ -101,8 +105,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     for (int i = threadIdx.x; i < a.N; i += kThreads2) bias_s[i] = a.bias[i];
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_y_hi);
-        if (a.has_res) prefetch_tmap(&map_r_hi);
-        if (planes > 1) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); prefetch_tmap(&map_y_lo); if (a.has_res) prefetch_tmap(&map_r_lo); }
+        if (kHasRes) prefetch_tmap(&map_r_hi);
+        if (planes > 1) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); prefetch_tmap(&map_y_lo); if (kHasRes) prefetch_tmap(&map_r_lo); }
     }
     if (warp == 3 && lane == 0) {
         const uint32_t nmma = (uint32_t)a.mt;   // one issuing warp per 128-row subtile
@@ -198,7 +202,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         }
                         tc_fence_after();
                         const uint32_t a_lo0 = a_stage_lo + (((uint32_t)(a.tap_off0 + j * a.tap_step - a.lo) * row_bytes) >> 4);
-                        for (int ps = 0; ps < a.npass; ++ps) {
+                        for (int ps = 0; ps < npass; ++ps) {
                             const uint32_t a_lo = a_lo0 + (ps == 1 ? a_pl_step : 0u);   // (hi,hi) (lo,hi) (hi,lo)
                             const uint32_t w_lo = w_lo0 + (ps == 2 ? w_pl_step : 0u);
                             if (leader && a.dbg != 2) {
@@ -221,7 +225,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         }
     } else if (warp == 1) {
         // ===== residual producer: one [128 x ecols] box of the residual planes per epilogue step =====
-        if (lane == 0 && a.has_res && a.dbg != 1 && a.dbg != 3) {
+        if (lane == 0 && kHasRes && a.dbg != 1 && a.dbg != 3) {
             int se = 0;
             uint32_t pe = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -232,10 +236,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (row0 >= a.L) break;
                     for (int g = 0; g < a.groups; ++g) {
                         mbar_wait(bar_e_empty + 8 * se, pe ^ 1u);
-                        mbar_expect_tx(bar_e_full + 8 * se, 128u * erow_bytes * planes);
+                        mbar_expect_tx(bar_e_full + 8 * se, a.e_plane_bytes * planes);
                         for (int pl = 0; pl < planes; ++pl)
                             tma_load_3d(smem_e + se * e_slot_bytes + pl * a.e_plane_bytes, pl ? &map_r_lo : &map_r_hi,
-                                        bar_e_full + 8 * se, g * a.ecols, row0, b);
+                                        bar_e_full + 8 * se, g * a.ecols, a.paired ? row0 >> 1 : row0, b);
                         if (++se == a.n_e) { se = 0; pe ^= 1u; }
                     }
                 }
@@ -249,9 +253,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;               // row of the 128-row subtile this thread owns
         // 16-byte chunk swizzle of this row inside a TMA box: 128-byte rows XOR (row & 7); 64-byte rows XOR ((row >> 1) & 3)
-        const uint32_t sw_xor = erow_bytes == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
-        const uint32_t row_off = (uint32_t)row * erow_bytes;
-        const uint32_t warp_off = (uint32_t)(q * 32) * erow_bytes;
+        // (paired: row r is the (r & 1) half of 128-byte row r >> 1)
+        const uint32_t sw_xor = a.paired ? (uint32_t)((row >> 1) & 7) : (erow_bytes == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3));
+        const uint32_t row_off = a.paired ? (uint32_t)(row >> 1) * 128u : (uint32_t)row * erow_bytes;
+        const uint32_t chunk0 = a.paired ? (uint32_t)(row & 1) * 4u : 0u;
+        const uint32_t warp_off = (uint32_t)(q * 32) * (uint32_t)a.ecols * 2u;
+        const int rshift = a.paired ? 1 : 0;
         const int halves = a.ecols / 32;
         const int depth = a.n_e >= 4 ? 2 : 1;        // stores in flight before a slot is handed back
         int se = 0;
@@ -274,19 +281,19 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int row0 = m0 + ms * 128;
                 if (row0 >= a.L) break;
                 for (int g = 0; g < a.groups; ++g) {
-                    if (a.has_res) mbar_wait(bar_e_full + 8 * se, pe);
+                    if (kHasRes) mbar_wait(bar_e_full + 8 * se, pe);
                     else mbar_wait(bar_e_empty + 8 * se, pe ^ 1u);
                     const uint32_t slot = smem_e + se * e_slot_bytes;
-                    for (int h = 0; h < halves; ++h) {
+                    for (int h = 0; h < (a.dbg == 5 ? 0 : halves); ++h) {
                         uint32_t r[32];
                         const int col = g * a.ecols + h * 32;
                         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + ms * a.N + col), r);
                         uint32_t addr[4];
 #pragma unroll
                         for (int cidx = 0; cidx < 4; ++cidx)
-                            addr[cidx] = slot + row_off + ((((uint32_t)(h * 4 + cidx)) ^ sw_xor) << 4);
+                            addr[cidx] = slot + row_off + (((chunk0 + (uint32_t)(h * 4 + cidx)) ^ sw_xor) << 4);
                         float res[32];
-                        if (a.has_res) {
+                        if (kHasRes) {
 #pragma unroll
                             for (int cidx = 0; cidx < 4; ++cidx) {
                                 float f[8];
@@ -311,7 +318,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv.z;
                             v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv.w;
                         }
-                        if (a.has_res) {
+                        if (kHasRes) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] += res[i];
                         }
@@ -344,9 +351,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lane == 0 && a.dbg == 4) {
+                        mbar_arrive(bar_e_empty + 8 * se);
+                    } else if (lane == 0) {
                         for (int pl = 0; pl < planes; ++pl)
-                            tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, g * a.ecols, row0 + q * 32, b);
+                            tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, g * a.ecols, (row0 + q * 32) >> rshift, b);
                         bulk_commit();
                         // hand back the slot whose store was issued `depth` steps ago: its shared-memory reads are done
                         if (depth == 2) {
@@ -453,6 +462,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     a.planes = planes; a.npass = p.npass;
     a.has_res = (p.res_hi != nullptr);
     a.ecols = std::min(64, N);
+    a.paired = (N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
     a.groups = N / a.ecols;
     a.e_plane_bytes = 128u * (uint32_t)a.ecols * 2u;
     a.bias = p.bias;
@@ -463,35 +473,66 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     const uint32_t w_all = (uint32_t)(a.nchunks * a.taps) * w_tile;
     a.w_plane_bytes = w_plane;
 
+    // Choose (MT, resident W, ring depths) by a small cost model: cycles per output row = tile interval / rows, where the
+    // interval is the larger of the tensor time (measured MMA floors: max(128*N/256, (4096 + 32*N)/128) cycles per K=16 MMA)
+    // and the HBM time of the tile, inflated when a ring is too shallow to cover its fetch latency.
     const int mt_max = std::max(1, std::min({256 / N, 4, env_i("HFG_U2_MT", 4), (g.Lin + 127) / 128}));
     const uint32_t budget = kSmemBudget - 1024;   // alignment slack
+    const double mma_clk = std::max(128.0 * N / 256.0, (4096.0 + 32.0 * N) / 128.0);
+    const double lat_hbm = 3000.0, lat_l2 = 1600.0, sm_bw = 20.0;   // cycles, cycles, bytes per cycle per SM
+    const int ksteps = p.kc / 16;
+    const int force_na = env_i("HFG_U2_NA", 0), force_nw = env_i("HFG_U2_NW", 0), force_ne = env_i("HFG_U2_NE", 0);
+    const int force_res = env_i("HFG_U2_RESIDENT", -1);
     bool ok = false;
-    for (int mt = mt_max; mt >= 1 && !ok; --mt) {
+    double best = 1e30;
+    for (int mt = mt_max; mt >= 1; --mt) {
         const int rows_need = mt * 128 + span;
         const int pieces = (rows_need + 255) / 256;
         const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
         const uint32_t a_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
         const uint32_t a_stage = a_plane * planes;
         const int boxes = mt * a.groups;
-        for (int resident = 1; resident >= 0 && !ok; --resident) {
-            if (resident && (w_all > 120u * 1024u || env_i("HFG_U2_RESIDENT", 1) == 0)) continue;
-            for (int n_w = resident ? 1 : std::min(kMaxW, env_i("HFG_U2_NW", 4)); n_w >= (resident ? 1 : 2) && !ok; --n_w) {
+        const double t_tile = (double)mt * a.nchunks * a.taps * p.npass * ksteps * mma_clk;
+        const double bytes = (double)pieces * box_rows * a.nchunks * row_bytes * planes + (a.has_res ? 2.0 : 1.0) * mt * 128.0 * N * 2.0 * planes;
+        for (int resident = 1; resident >= 0; --resident) {
+            if (resident && w_all > 140u * 1024u) continue;
+            if (force_res >= 0 && resident != force_res) continue;
+            const double w_bytes_tile = resident ? 0.0 : (double)w_all;
+            const double t_int = std::max({t_tile, bytes / sm_bw, w_bytes_tile / 40.0}) + 1200.0;
+            for (int n_w = resident ? 1 : kMaxW; n_w >= (resident ? 1 : 2); --n_w) {
+                if (!resident && force_nw && n_w != force_nw) continue;
                 const uint32_t w_bytes = resident ? w_all : (uint32_t)n_w * w_tile;
-                for (int n_e = std::min({kMaxE, std::max(2, 2 * boxes), env_i("HFG_U2_NE", 8)}); n_e >= 2 && !ok; --n_e) {
+                for (int n_e = kMaxE; n_e >= 2; --n_e) {
+                    if (force_ne && n_e != force_ne) continue;
                     const uint32_t fixed = w_bytes + (uint32_t)n_e * e_slot;
                     if (fixed + 2 * a_stage > budget) continue;
-                    int n_a = (int)std::min<uint32_t>((budget - fixed) / a_stage, (uint32_t)std::min(kMaxA, env_i("HFG_U2_NA", 4)));
-                    if (n_a < 2) continue;
-                    a.mt = mt; a.rows_a = pieces * box_rows; a.a_box_rows = box_rows; a.a_pieces = pieces;
-                    a.a_plane_bytes = a_plane; a.n_a = n_a; a.n_w = resident ? 1 : n_w; a.n_e = n_e; a.w_resident = resident;
-                    a.off_w = (uint32_t)n_a * a_stage;
-                    a.off_e = a.off_w + w_bytes;
-                    I->smem = std::max<size_t>((size_t)a.off_e + (size_t)n_e * e_slot + 1024, 120u * 1024u);   // > half an SM: one CTA (512 TMEM columns) per SM
-                    ok = true;
+                    const int n_a_max = (int)std::min<uint32_t>((budget - fixed) / a_stage, (uint32_t)kMaxA);
+                    for (int n_a = n_a_max; n_a >= 2; --n_a) {
+                        if (force_na && n_a != force_na) continue;
+                        const double f_a = std::min(1.0, (n_a - 1) * (t_int / a.nchunks) / lat_hbm);
+                        const double f_w = resident ? 1.0 : std::min(1.0, (n_w - 1) * (t_int / (a.nchunks * a.taps)) / lat_l2);
+                        const int pend = n_e >= 4 ? 2 : 1;
+                        const double f_e = a.has_res ? std::min(1.0, std::max(0.25, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm)
+                                                     : (n_e - pend >= 1 ? 1.0 : 0.5);
+                        const double cost = t_int / std::min({f_a, f_w, f_e}) / (mt * 128.0);
+                        if (cost < best - 1e-9) {
+                            best = cost;
+                            a.mt = mt; a.rows_a = pieces * box_rows; a.a_box_rows = box_rows; a.a_pieces = pieces;
+                            a.a_plane_bytes = a_plane; a.n_a = n_a; a.n_w = resident ? 1 : n_w; a.n_e = n_e; a.w_resident = resident;
+                            a.off_w = (uint32_t)n_a * a_stage;
+                            a.off_e = a.off_w + w_bytes;
+                            // > half an SM, so exactly one CTA (512 TMEM columns) lives on an SM
+                            I->smem = std::max<size_t>((size_t)a.off_e + (size_t)n_e * e_slot + 1024, 120u * 1024u);
+                            ok = true;
+                        }
+                    }
                 }
             }
         }
     }
+    if (env_i("HFG_U2_VERBOSE", 0) && ok)
+        fprintf(stderr, "umma2 plan N=%d taps=%d planes=%d res=%d: mt=%d resident=%d n_a=%d n_w=%d n_e=%d smem=%zu cost=%.2f\n", N, a.taps,
+                planes, a.has_res, a.mt, a.w_resident, a.n_a, a.n_w, a.n_e, I->smem, best);
     if (!ok) return HFG_ERR_UNSUPPORTED;
     a.tiles_per_item = (g.Lin + a.mt * 128 - 1) / (a.mt * 128);
     a.total_tiles = a.tiles_per_item * g.B;
@@ -512,15 +553,19 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
         if (!encode(&I->map_w[1], planes > 1 ? w_lo : w_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
     }
     {
-        const uint32_t box[3] = {(uint32_t)a.ecols, 128, 1};
-        const uint32_t eb = (uint32_t)a.ecols * 2u;
+        // residual boxes: 128 time rows; output boxes: one epilogue warp's 32 rows.  Paired (C = 32): [B][L/2][64] view.
+        const int pr = a.paired ? 2 : 1;
+        const uint64_t edims[3] = {(uint64_t)g.Cin * pr, (uint64_t)g.Lin / pr, (uint64_t)g.B};
+        const uint64_t estr[2] = {(uint64_t)g.Cin * pr * 2, (uint64_t)g.Lin * g.Cin * 2};
+        const uint32_t box[3] = {(uint32_t)a.ecols * pr, (uint32_t)(128 / pr), 1};
+        const uint32_t ybox[3] = {(uint32_t)a.ecols * pr, (uint32_t)(32 / pr), 1};
+        const uint32_t eb = (uint32_t)a.ecols * pr * 2u;
         const void* r0 = a.has_res ? (const void*)p.res_hi : (const void*)p.y_act;
         const void* r1 = (a.has_res && planes > 1) ? (const void*)p.res_lo : r0;
-        if (!encode(&I->map_r[0], r0, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
-        if (!encode(&I->map_r[1], r1, 3, dims3, str3, box, eb)) return HFG_ERR_CUDA;
-        const uint32_t ybox[3] = {(uint32_t)a.ecols, 32, 1};   // one epilogue warp's rows
-        if (!encode(&I->map_y[0], p.y_act, 3, dims3, str3, ybox, eb)) return HFG_ERR_CUDA;
-        if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 3, dims3, str3, ybox, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_r[0], r0, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_r[1], r1, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_y[0], p.y_act, 3, edims, estr, ybox, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 3, edims, estr, ybox, eb)) return HFG_ERR_CUDA;
     }
     out->impl = I;
     out->mt = a.mt; out->n_a = a.n_a; out->n_w = a.n_w; out->n_e = a.n_e; out->w_resident = a.w_resident;
@@ -533,13 +578,20 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev % 64]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
         if (e != cudaSuccess) return e;
         configured[dev % 64] = true;
     }
     const Umma2Launch::Impl& I = *L.impl;
-    conv_umma2_kernel<<<I.grid, kThreads2, I.smem, s>>>(I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1],
-                                                       I.map_y[0], I.map_y[1], I.a);
+#define HFG_U2_LAUNCH(P, R)                                                                                                   \
+    conv_umma2_kernel<P, R><<<I.grid, kThreads2, I.smem, s>>>(I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1], \
+                                                             I.map_y[0], I.map_y[1], I.a)
+    if (I.a.planes == 2) { if (I.a.has_res) HFG_U2_LAUNCH(2, true); else HFG_U2_LAUNCH(2, false); }
+    else { if (I.a.has_res) HFG_U2_LAUNCH(1, true); else HFG_U2_LAUNCH(1, false); }
+#undef HFG_U2_LAUNCH
     return cudaGetLastError();
 }
 
