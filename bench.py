@@ -180,7 +180,8 @@ def time_device_steps(eng, stream, mel_dev, out_dev, B, T, precision, steps, war
     return ms, eng.launch_count - l0, recs
 
 
-def roofline_from_records(recs, peaks, kernel="conv_umma"):
+def roofline_from_records(recs, peaks, kernel="conv_umma2"):
+    """Dominant kernel = conv_umma2_kernel (the persistent tcgen05 conv: 72 of the 77 conv launches of a V1 forward)."""
     sel = [r for r in recs if r["kernel"] == kernel]
     if not sel:
         return None

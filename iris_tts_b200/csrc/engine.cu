@@ -62,7 +62,7 @@ struct Layer {
     __nv_bfloat16* d_wb_lo = nullptr;
 };
 
-enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_POST32, S_POSTBF, S_ACCUM, S_SPLIT, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_TAP };
+enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_POST32, S_POSTBF, S_ACCUM, S_SPLIT, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP };
 
 struct Step {
     StepKind kind;
@@ -500,7 +500,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                 snprintf(nm, sizeof nm, "resblocks.%d", n);
                 tap_planes(nm, r_p[j], ch, L);
             }
-            {   // xs = sum_j r_j ; x = xs / nk  (:133-137)
+            const bool fuse_post = last_stage && !keep_taps;   // the MRF mean of the last stage is computed inside conv_post
+            if (!fuse_post) {   // xs = sum_j r_j ; x = xs / nk  (:133-137)
                 Step s{}; s.kind = S_MRF; s.n = ne;
                 memset(&s.mrf, 0, sizeof s.mrf);
                 for (int j = 0; j < nk; ++j) { s.mrf.hi[j] = r_p[j].hi; s.mrf.lo[j] = x3 ? r_p[j].lo : nullptr; }
@@ -549,7 +550,16 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         Step s{};
         s.w = post.d_w32; s.bias = post.d_bias; s.f_out = pass ? wave_dev : post_tap;
         s.B = B; s.L = L; s.C = post.cin; s.k = post.k; s.flag0 = 1; s.flag1 = pass;
-        if (post_planes) { s.kind = S_POSTBF; s.b_in = xp.hi; s.b_in_lo = x3 ? xp.lo : nullptr; } else { s.kind = S_POST32; s.f_in = x_raw; }
+        if (post_planes) {
+            // One kernel for both plans (identical arithmetic order): the production plan hands it the nk branch outputs and
+            // it forms the MRF mean itself; the tap plan hands it the already combined stage planes (nk = 1).
+            s.kind = S_POSTMRF;
+            memset(&s.mrf, 0, sizeof s.mrf);
+            if (keep_taps) { s.mrf.hi[0] = xp.hi; s.mrf.lo[0] = x3 ? xp.lo : nullptr; s.mrf.nk = 1; }
+            else { for (int j = 0; j < nk; ++j) { s.mrf.hi[j] = r_p[j].hi; s.mrf.lo[j] = x3 ? r_p[j].lo : nullptr; } s.mrf.nk = nk; }
+        } else {
+            s.kind = S_POST32; s.f_in = x_raw;
+        }
         work(s, post, L, post_planes ? 2 : 4);
         push(std::move(s));
         if (!pass) tap("conv_post", post_tap, 1, L);
@@ -578,6 +588,7 @@ const char* kind_label(StepKind k) {
         case S_UMMA2: return "conv_umma2";
         case S_P2RAW: return "planes_to_raw";
         case S_MRF: return "mrf_combine";
+        case S_POSTMRF: return "conv_post_mrf";
         case S_POST32: case S_POSTBF: return "conv_post";
         case S_ACCUM: return "accum";
         case S_SPLIT: return "act_split";
@@ -607,6 +618,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_UMMA2: CK(launch_conv_umma2(s.u2, st)); break;
             case S_P2RAW: CK(launch_planes_to_raw(s.b_in, s.b_in_lo, s.f_out, s.n, st)); break;
             case S_MRF: CK(launch_mrf_combine(s.mrf, s.n, st)); break;
+            case S_POSTMRF: CK(launch_conv_post_mrf(s.mrf, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
             case S_POST32: CK(launch_conv_post_fp32(s.f_in, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag0, s.flag1, st)); break;
             case S_POSTBF: CK(launch_conv_post_bf16(s.b_in, s.b_in_lo, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
             case S_ACCUM: CK(launch_accum_fp32(s.f_out, s.f_in, s.n, s.flag0, s.fval, st)); break;

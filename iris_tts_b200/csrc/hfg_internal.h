@@ -144,6 +144,10 @@ struct MrfArgs {
     float* out_raw;
 };
 cudaError_t launch_mrf_combine(const MrfArgs& a, size_t n, cudaStream_t s);
+// MRF combine of the LAST stage fused into conv_post: wave = tanh(Conv1d(lrelu(mean_j x_j)))  (:133-141); the mean is rounded
+// through the operand-plane format exactly as launch_mrf_combine would store it, so both plans give identical bits.
+cudaError_t launch_conv_post_mrf(const MrfArgs& a, const float* w /*[k][C]*/, const float* bias, float* wave, int B, int L, int C,
+                                 int k, int apply_tanh, cudaStream_t s);
 
 void set_error(const std::string& msg);
 

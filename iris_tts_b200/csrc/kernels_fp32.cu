@@ -383,6 +383,70 @@ __global__ void mrf_combine_kernel(const MrfArgs a, size_t n8) {
     }
 }
 
+// conv_post on the nk branch-output planes of the last stage: stage tile = lrelu(mean_j inverse-lrelu(plane_j)) in fp32
+// shared memory (row stride C + 4 floats: conflict-free float4 reads by consecutive rows), one output sample per thread.
+constexpr int kPostMrfTile = 256;
+__global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfArgs a, const float* __restrict__ w, const float* __restrict__ bias,
+                                                                    float* __restrict__ wave, int L, int C, int k, int apply_tanh) {
+    extern __shared__ __align__(16) float smem[];
+    const int pad = (k - 1) / 2;
+    const int rows = kPostMrfTile + k - 1;
+    const int stride = C + 4;
+    float* in_s = smem;                    // [rows][stride]
+    float* w_s = in_s + rows * stride;     // [k][C]
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * kPostMrfTile;
+    const int b = blockIdx.y;
+    const int c8n = C / 8;
+    const size_t base8 = (size_t)b * L * c8n;
+    const float d = (float)a.nk;
+    for (int idx = tid; idx < rows * c8n; idx += kPostMrfTile) {
+        const int r = idx / c8n, c8 = idx - r * c8n;
+        const int t = t0 - pad + r;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < L) {
+            const size_t i8 = base8 + (size_t)t * c8n + c8;
+            load8(a.hi[0], a.lo[0], i8, v);
+            if (a.nk > 1) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = inv_lrelu(v[q]);
+                for (int j = 1; j < a.nk; ++j) {
+                    float f[8];
+                    load8(a.hi[j], a.lo[j], i8, f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = v[q] + inv_lrelu(f[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float x = lrelu(__fdiv_rn(v[q], d));
+                    const float h = __bfloat162float(__float2bfloat16_rn(x));   // what the operand plane(s) would hold
+                    v[q] = a.lo[0] ? h + __bfloat162float(__float2bfloat16_rn(x - h)) : h;
+                }
+            }
+        }
+        float* dst = in_s + r * stride + c8 * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    for (int idx = tid; idx < k * C; idx += kPostMrfTile) w_s[idx] = __ldg(w + idx);
+    __syncthreads();
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) {
+        const float* xr = in_s + (tid + j) * stride;
+        const float* wr = w_s + j * C;
+        for (int c = 0; c < C; c += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xr + c);
+            const float4 ww = *reinterpret_cast<const float4*>(wr + c);
+            s = fmaf(x.x, ww.x, s); s = fmaf(x.y, ww.y, s); s = fmaf(x.z, ww.z, s); s = fmaf(x.w, ww.w, s);
+        }
+    }
+    const int t = t0 + tid;
+    if (t < L) {
+        s += __ldg(bias);
+        wave[(size_t)b * L + t] = apply_tanh ? tanhf(s) : s;
+    }
+}
+
 cudaError_t launch_transpose(const float* in, float* out, int B, int R, int Cc, cudaStream_t s) {
     dim3 grid((Cc + 31) / 32, (R + 31) / 32, B);
     dim3 block(32, 8);
@@ -464,6 +528,23 @@ cudaError_t launch_mrf_combine(const MrfArgs& a, size_t n, cudaStream_t s) {
     const size_t n8 = n / 8;
     const int blocks = (int)std::min<size_t>((n8 + 255) / 256, 148 * 16);
     mrf_combine_kernel<<<blocks, 256, 0, s>>>(a, n8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post_mrf(const MrfArgs& a, const float* w, const float* bias, float* wave, int B, int L, int C, int k,
+                                 int apply_tanh, cudaStream_t s) {
+    if (C % 8 != 0 || a.nk < 1 || a.nk > HFG_MAX_KERNELS) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)((kPostMrfTile + k - 1) * (C + 4) + k * C) * sizeof(float);
+    static size_t configured[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && smem > configured[dev % kMaxDevices]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_post_mrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev % kMaxDevices] = smem;
+    }
+    dim3 grid((L + kPostMrfTile - 1) / kPostMrfTile, B);
+    conv_post_mrf_kernel<<<grid, kPostMrfTile, smem, s>>>(a, w, bias, wave, L, C, k, apply_tanh);
     return cudaGetLastError();
 }
 

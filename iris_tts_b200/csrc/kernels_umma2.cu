@@ -453,86 +453,97 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     memset(&a, 0, sizeof a);
     const int planes = p.npass > 1 ? 2 : 1;
     const int N = g.Cout;
-    const uint32_t row_bytes = (uint32_t)p.kc * 2u;
     a.B = g.B; a.L = g.Lin; a.N = N;
-    a.kc = p.kc; a.nchunks = p.cin_pad / p.kc; a.taps = g.taps; a.tap_off0 = g.tap_off0; a.tap_step = g.tap_step;
+    a.taps = g.taps; a.tap_off0 = g.tap_off0; a.tap_step = g.tap_step;
     const int last_off = g.tap_off0 + (g.taps - 1) * g.tap_step;
     a.lo = std::min(g.tap_off0, last_off);
     const int span = std::max(g.tap_off0, last_off) - a.lo;
     a.planes = planes; a.npass = p.npass;
     a.has_res = (p.res_hi != nullptr);
-    a.ecols = std::min(64, N);
     a.paired = (N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
-    a.groups = N / a.ecols;
-    a.e_plane_bytes = 128u * (uint32_t)a.ecols * 2u;
     a.bias = p.bias;
     a.dbg = env_i("HFG_U2_DBG", 0);
-    const uint32_t e_slot = a.e_plane_bytes * planes;
-    const uint32_t w_plane = rup((uint32_t)N * row_bytes, 1024);
-    const uint32_t w_tile = w_plane * planes;
-    const uint32_t w_all = (uint32_t)(a.nchunks * a.taps) * w_tile;
-    a.w_plane_bytes = w_plane;
 
-    // Choose (MT, resident W, ring depths) by a small cost model: cycles per output row = tile interval / rows, where the
-    // interval is the larger of the tensor time (measured MMA floors: max(128*N/256, (4096 + 32*N)/128) cycles per K=16 MMA)
-    // and the HBM time of the tile, inflated when a ring is too shallow to cover its fetch latency.
+    // Choose (K-chunk width, epilogue box width, MT, resident W, ring depths) by a small cost model: cycles per output
+    // row = tile interval / rows, where the interval is the largest of the tensor time (measured MMA floors:
+    // max(128*N/256, (4096 + 32*N)/128) cycles per K=16 MMA), the HBM time of the tile and the L2 time of the streamed
+    // weights, inflated when a ring is too shallow to cover its fetch latency.  Narrow K-chunks / boxes (32 channels)
+    // halve the stage sizes, which is what lets the two-plane (bf16x3) mode keep MT >= 2 and real pipelining.
     const int mt_max = std::max(1, std::min({256 / N, 4, env_i("HFG_U2_MT", 4), (g.Lin + 127) / 128}));
     const uint32_t budget = kSmemBudget - 1024;   // alignment slack
     const double mma_clk = std::max(128.0 * N / 256.0, (4096.0 + 32.0 * N) / 128.0);
-    const double lat_hbm = 3000.0, lat_l2 = 1600.0, sm_bw = 20.0;   // cycles, cycles, bytes per cycle per SM
-    const int ksteps = p.kc / 16;
+    const double lat_hbm = 3000.0, lat_l2 = 1600.0, sm_bw = 20.0, l2_bw = 36.0;   // cycles, cycles, bytes/cycle/SM
     const int force_na = env_i("HFG_U2_NA", 0), force_nw = env_i("HFG_U2_NW", 0), force_ne = env_i("HFG_U2_NE", 0);
-    const int force_res = env_i("HFG_U2_RESIDENT", -1);
+    const int force_res = env_i("HFG_U2_RESIDENT", -1), force_kc = env_i("HFG_U2_KC", 0), force_ec = env_i("HFG_U2_ECOLS", 0);
     bool ok = false;
     double best = 1e30;
-    for (int mt = mt_max; mt >= 1; --mt) {
-        const int rows_need = mt * 128 + span;
-        const int pieces = (rows_need + 255) / 256;
-        const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
-        const uint32_t a_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
-        const uint32_t a_stage = a_plane * planes;
-        const int boxes = mt * a.groups;
-        const double t_tile = (double)mt * a.nchunks * a.taps * p.npass * ksteps * mma_clk;
-        const double bytes = (double)pieces * box_rows * a.nchunks * row_bytes * planes + (a.has_res ? 2.0 : 1.0) * mt * 128.0 * N * 2.0 * planes;
-        for (int resident = 1; resident >= 0; --resident) {
-            if (resident && w_all > 140u * 1024u) continue;
-            if (force_res >= 0 && resident != force_res) continue;
-            const double w_bytes_tile = resident ? 0.0 : (double)w_all;
-            const double t_int = std::max({t_tile, bytes / sm_bw, w_bytes_tile / 40.0}) + 1200.0;
-            for (int n_w = resident ? 1 : kMaxW; n_w >= (resident ? 1 : 2); --n_w) {
-                if (!resident && force_nw && n_w != force_nw) continue;
-                const uint32_t w_bytes = resident ? w_all : (uint32_t)n_w * w_tile;
-                for (int n_e = kMaxE; n_e >= 2; --n_e) {
-                    if (force_ne && n_e != force_ne) continue;
-                    const uint32_t fixed = w_bytes + (uint32_t)n_e * e_slot;
-                    if (fixed + 2 * a_stage > budget) continue;
-                    const int n_a_max = (int)std::min<uint32_t>((budget - fixed) / a_stage, (uint32_t)kMaxA);
-                    for (int n_a = n_a_max; n_a >= 2; --n_a) {
-                        if (force_na && n_a != force_na) continue;
-                        const double f_a = std::min(1.0, (n_a - 1) * (t_int / a.nchunks) / lat_hbm);
-                        const double f_w = resident ? 1.0 : std::min(1.0, (n_w - 1) * (t_int / (a.nchunks * a.taps)) / lat_l2);
-                        const int pend = n_e >= 4 ? 2 : 1;
-                        const double f_e = a.has_res ? std::min(1.0, std::max(0.25, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm)
-                                                     : (n_e - pend >= 1 ? 1.0 : 0.5);
-                        const double cost = t_int / std::min({f_a, f_w, f_e}) / (mt * 128.0);
-                        if (cost < best - 1e-9) {
-                            best = cost;
-                            a.mt = mt; a.rows_a = pieces * box_rows; a.a_box_rows = box_rows; a.a_pieces = pieces;
-                            a.a_plane_bytes = a_plane; a.n_a = n_a; a.n_w = resident ? 1 : n_w; a.n_e = n_e; a.w_resident = resident;
-                            a.off_w = (uint32_t)n_a * a_stage;
-                            a.off_e = a.off_w + w_bytes;
-                            // > half an SM, so exactly one CTA (512 TMEM columns) lives on an SM
-                            I->smem = std::max<size_t>((size_t)a.off_e + (size_t)n_e * e_slot + 1024, 120u * 1024u);
-                            ok = true;
+    for (int kc = p.kc; kc >= 32; kc -= 32) {
+      if (force_kc && kc != force_kc && p.kc != 32) continue;
+      const uint32_t row_bytes = (uint32_t)kc * 2u;
+      const int nchunks = p.cin_pad / kc, ksteps = kc / 16;
+      const uint32_t w_plane = rup((uint32_t)N * row_bytes, 1024);
+      const uint32_t w_tile = w_plane * planes;
+      const uint32_t w_all = (uint32_t)(nchunks * a.taps) * w_tile;
+      for (int ecols = std::min(64, N); ecols >= 32; ecols -= 32) {
+        if (force_ec && ecols != force_ec && N > 32) continue;
+        const int groups = N / ecols;
+        const uint32_t e_plane = 128u * (uint32_t)ecols * 2u;
+        const uint32_t e_slot = e_plane * planes;
+        for (int mt = mt_max; mt >= 1; --mt) {
+            const int rows_need = mt * 128 + span;
+            const int pieces = (rows_need + 255) / 256;
+            const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
+            const uint32_t a_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
+            const uint32_t a_stage = a_plane * planes;
+            const int boxes = mt * groups;
+            const double t_tile = (double)mt * nchunks * a.taps * p.npass * ksteps * mma_clk;
+            const double bytes = (double)pieces * box_rows * nchunks * row_bytes * planes + (a.has_res ? 2.0 : 1.0) * mt * 128.0 * N * 2.0 * planes;
+            // epilogue: ~(250 + 120 per residual plane) issue cycles per 32-column step and warp, 4 warps in parallel
+            const double t_epi = (double)mt * (N / 32) * (260.0 + (a.has_res ? 110.0 : 0.0) * planes + (planes > 1 ? 120.0 : 0.0)) + boxes * 150.0;
+            for (int resident = 1; resident >= 0; --resident) {
+                if (resident && w_all > 140u * 1024u) continue;
+                if (force_res >= 0 && resident != force_res) continue;
+                const double w_bytes_tile = resident ? 0.0 : (double)w_all;
+                const double t_int = std::max({t_tile, bytes / sm_bw, w_bytes_tile / l2_bw, t_epi}) + 1200.0;
+                for (int n_w = resident ? 1 : kMaxW; n_w >= (resident ? 1 : 2); --n_w) {
+                    if (!resident && force_nw && n_w != force_nw) continue;
+                    const uint32_t w_bytes = resident ? w_all : (uint32_t)n_w * w_tile;
+                    for (int n_e = kMaxE; n_e >= 2; --n_e) {
+                        if (force_ne && n_e != force_ne) continue;
+                        const uint32_t fixed = w_bytes + (uint32_t)n_e * e_slot;
+                        if (fixed + 2 * a_stage > budget) continue;
+                        const int n_a_max = (int)std::min<uint32_t>((budget - fixed) / a_stage, (uint32_t)kMaxA);
+                        for (int n_a = n_a_max; n_a >= 2; --n_a) {
+                            if (force_na && n_a != force_na) continue;
+                            const double f_a = std::min(1.0, (n_a - 1) * (t_int / nchunks) / lat_hbm);
+                            const double f_w = resident ? 1.0 : std::min(1.0, (n_w - 1) * (t_int / (nchunks * a.taps)) / lat_l2);
+                            const int pend = n_e >= 4 ? 2 : 1;
+                            const double f_e = a.has_res ? std::min(1.0, std::max(0.25, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm)
+                                                         : (n_e - pend >= 1 ? 1.0 : 0.5);
+                            const double cost = t_int / std::min({f_a, f_w, f_e}) / (mt * 128.0);
+                            if (cost < best - 1e-9) {
+                                best = cost;
+                                a.kc = kc; a.nchunks = nchunks; a.ecols = ecols; a.groups = groups;
+                                a.e_plane_bytes = e_plane; a.w_plane_bytes = w_plane;
+                                a.mt = mt; a.rows_a = pieces * box_rows; a.a_box_rows = box_rows; a.a_pieces = pieces;
+                                a.a_plane_bytes = a_plane; a.n_a = n_a; a.n_w = resident ? 1 : n_w; a.n_e = n_e; a.w_resident = resident;
+                                a.off_w = (uint32_t)n_a * a_stage;
+                                a.off_e = a.off_w + w_bytes;
+                                // > half an SM, so exactly one CTA (512 TMEM columns) lives on an SM
+                                I->smem = std::max<size_t>((size_t)a.off_e + (size_t)n_e * e_slot + 1024, 120u * 1024u);
+                                ok = true;
+                            }
                         }
                     }
                 }
             }
         }
+      }
     }
     if (env_i("HFG_U2_VERBOSE", 0) && ok)
-        fprintf(stderr, "umma2 plan N=%d taps=%d planes=%d res=%d: mt=%d resident=%d n_a=%d n_w=%d n_e=%d smem=%zu cost=%.2f\n", N, a.taps,
-                planes, a.has_res, a.mt, a.w_resident, a.n_a, a.n_w, a.n_e, I->smem, best);
+        fprintf(stderr, "umma2 plan N=%d taps=%d planes=%d res=%d: kc=%d ecols=%d mt=%d resident=%d n_a=%d n_w=%d n_e=%d smem=%zu cost=%.2f\n",
+                N, a.taps, planes, a.has_res, a.kc, a.ecols, a.mt, a.w_resident, a.n_a, a.n_w, a.n_e, I->smem, best);
+    const uint32_t row_bytes = (uint32_t)a.kc * 2u;
     if (!ok) return HFG_ERR_UNSUPPORTED;
     a.tiles_per_item = (g.Lin + a.mt * 128 - 1) / (a.mt * 128);
     a.total_tiles = a.tiles_per_item * g.B;
@@ -541,14 +552,14 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     const uint64_t dims3[3] = {(uint64_t)g.Cin, (uint64_t)g.Lin, (uint64_t)g.B};
     const uint64_t str3[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Lin * g.Cin * 2};
     {
-        const uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)a.a_box_rows, 1};
+        const uint32_t box[3] = {(uint32_t)a.kc, (uint32_t)a.a_box_rows, 1};
         if (!encode(&I->map_a[0], x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
         if (!encode(&I->map_a[1], planes > 1 ? x_lo : x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
     }
     {
         const uint64_t dims[2] = {(uint64_t)p.cin_pad, (uint64_t)g.taps * N};
         const uint64_t str[1] = {(uint64_t)p.cin_pad * 2};
-        const uint32_t box[2] = {(uint32_t)p.kc, (uint32_t)N};
+        const uint32_t box[2] = {(uint32_t)a.kc, (uint32_t)N};
         if (!encode(&I->map_w[0], w_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
         if (!encode(&I->map_w[1], planes > 1 ? w_lo : w_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
     }
