@@ -47,6 +47,8 @@ struct K2Args {
     int rows_a, a_box_rows, a_pieces;
     int n_a, n_w, n_e, w_resident, has_res;
     int ecols, groups;
+    int concat;   // bf16x3, 2N <= 128: pass 1 = A_hi x [W_hi ; W_lo] (one MMA of width 2N), pass 2 = A_lo x W_hi; the epilogue adds the halves
+    int acc_n;    // TMEM columns of one 128-row subtile accumulator (N, or 2N when concat)
     int paired;   // C = 32: residual / output boxes address two 64-byte time rows as one 128-byte row (full-line TMA requests)
     int dbg;   // HFG_U2_DBG (timing experiments only): 1 = epilogue does no work, 2 = MMA warp issues no MMAs
     uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
@@ -125,7 +127,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    const int acc_cols = a.mt * a.N;   // columns of one accumulator buffer
+    const int acc_cols = a.mt * a.acc_n;   // columns of one accumulator buffer
 
     if (warp == 0) {
         // ===== A / W producer =====
@@ -175,6 +177,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (my_ms < a.mt) {
             const bool leader = elect_one();
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * a.N) >> 3) << 17) | ((128u >> 4) << 24);
+            const int np = a.concat ? 2 : npass;
             const uint32_t dhi = desc_hi(row_bytes);
             const uint32_t sub_step = (128u * row_bytes) >> 4;          // descriptor step between 128-row subtiles
             const uint32_t a_pl_step = a.a_plane_bytes >> 4, w_pl_step = a.w_plane_bytes >> 4;
@@ -187,7 +191,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int buf = it & 1;
                 mbar_wait(bar_acc_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols + my_ms * a.N);
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols + my_ms * a.acc_n);
                 uint32_t acc = 0;
                 for (int c = 0; c < a.nchunks; ++c) {
                     if (a.dbg != 3) mbar_wait(bar_a_full + 8 * sa, pa);
@@ -202,12 +206,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         }
                         tc_fence_after();
                         const uint32_t a_lo0 = a_stage_lo + (((uint32_t)(a.tap_off0 + j * a.tap_step - a.lo) * row_bytes) >> 4);
-                        for (int ps = 0; ps < npass; ++ps) {
-                            const uint32_t a_lo = a_lo0 + (ps == 1 ? a_pl_step : 0u);   // (hi,hi) (lo,hi) (hi,lo)
-                            const uint32_t w_lo = w_lo0 + (ps == 2 ? w_pl_step : 0u);
+                        for (int ps = 0; ps < np; ++ps) {
+                            const uint32_t a_lo = a_lo0 + (ps == 1 ? a_pl_step : 0u);   // (hi,hi) (lo,hi) (hi,lo) | concat: (hi,[hi;lo]) (lo,hi)
+                            const uint32_t w_lo = w_lo0 + ((ps == 2) ? w_pl_step : 0u);
+                            const uint32_t id = (a.concat && ps == 0) ? idesc2 : idesc;
                             if (leader && a.dbg != 2) {
-                                if (k4) umma_ksteps<4>(d0, a_lo, w_lo, dhi, idesc, acc);
-                                else umma_ksteps<2>(d0, a_lo, w_lo, dhi, idesc, acc);
+                                if (k4) umma_ksteps<4>(d0, a_lo, w_lo, dhi, id, acc);
+                                else umma_ksteps<2>(d0, a_lo, w_lo, dhi, id, acc);
                             }
                             acc = 1;
                         }
@@ -287,7 +292,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     for (int h = 0; h < (a.dbg == 5 ? 0 : halves); ++h) {
                         uint32_t r[32];
                         const int col = g * a.ecols + h * 32;
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + ms * a.N + col), r);
+                        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + ms * a.acc_n + col);
+                        tmem_ld32(tcol, r);
                         uint32_t addr[4];
 #pragma unroll
                         for (int cidx = 0; cidx < 4; ++cidx)
@@ -317,6 +323,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv.y;
                             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv.z;
                             v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv.w;
+                        }
+                        if (kPlanes == 2 && a.concat) {   // second half of the concatenated accumulator: A_hi x W_lo
+                            tmem_ld32(tcol + (uint32_t)a.N, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
                         }
                         if (kHasRes) {
 #pragma unroll
@@ -463,15 +475,19 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     a.paired = (N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
     a.bias = p.bias;
     a.dbg = env_i("HFG_U2_DBG", 0);
+    a.concat = (planes == 2 && N <= 64 && env_i("HFG_U2_CONCAT", 1)) ? 1 : 0;
+    a.acc_n = a.concat ? 2 * N : N;
 
     // Choose (K-chunk width, epilogue box width, MT, resident W, ring depths) by a small cost model: cycles per output
     // row = tile interval / rows, where the interval is the largest of the tensor time (measured MMA floors:
     // max(128*N/256, (4096 + 32*N)/128) cycles per K=16 MMA), the HBM time of the tile and the L2 time of the streamed
     // weights, inflated when a ring is too shallow to cover its fetch latency.  Narrow K-chunks / boxes (32 channels)
     // halve the stage sizes, which is what lets the two-plane (bf16x3) mode keep MT >= 2 and real pipelining.
-    const int mt_max = std::max(1, std::min({256 / N, 4, env_i("HFG_U2_MT", 4), (g.Lin + 127) / 128}));
+    const int mt_max = std::max(1, std::min({256 / a.acc_n, 4, env_i("HFG_U2_MT", 4), (g.Lin + 127) / 128}));
     const uint32_t budget = kSmemBudget - 1024;   // alignment slack
-    const double mma_clk = std::max(128.0 * N / 256.0, (4096.0 + 32.0 * N) / 128.0);
+    auto floor_clk = [](double n) { return std::max(128.0 * n / 256.0, (4096.0 + 32.0 * n) / 128.0); };
+    // tensor cycles per K=16 step of one 128-row subtile, all passes
+    const double step_clk = a.concat ? floor_clk(2.0 * N) + floor_clk(N) : p.npass * floor_clk(N);
     const double lat_hbm = 3000.0, lat_l2 = 1600.0, sm_bw = 20.0, l2_bw = 36.0;   // cycles, cycles, bytes/cycle/SM
     const int force_na = env_i("HFG_U2_NA", 0), force_nw = env_i("HFG_U2_NW", 0), force_ne = env_i("HFG_U2_NE", 0);
     const int force_res = env_i("HFG_U2_RESIDENT", -1), force_kc = env_i("HFG_U2_KC", 0), force_ec = env_i("HFG_U2_ECOLS", 0);
@@ -482,6 +498,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
       const uint32_t row_bytes = (uint32_t)kc * 2u;
       const int nchunks = p.cin_pad / kc, ksteps = kc / 16;
       const uint32_t w_plane = rup((uint32_t)N * row_bytes, 1024);
+      if (a.concat && w_plane != (uint32_t)N * row_bytes) continue;   // [W_hi ; W_lo] must be contiguous rows
       const uint32_t w_tile = w_plane * planes;
       const uint32_t w_all = (uint32_t)(nchunks * a.taps) * w_tile;
       for (int ecols = std::min(64, N); ecols >= 32; ecols -= 32) {
@@ -496,7 +513,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
             const uint32_t a_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
             const uint32_t a_stage = a_plane * planes;
             const int boxes = mt * groups;
-            const double t_tile = (double)mt * nchunks * a.taps * p.npass * ksteps * mma_clk;
+            const double t_tile = (double)mt * nchunks * a.taps * ksteps * step_clk;
             const double bytes = (double)pieces * box_rows * nchunks * row_bytes * planes + (a.has_res ? 2.0 : 1.0) * mt * 128.0 * N * 2.0 * planes;
             // epilogue: ~(250 + 120 per residual plane) issue cycles per 32-column step and warp, 4 warps in parallel
             const double t_epi = (double)mt * (N / 32) * (260.0 + (a.has_res ? 110.0 : 0.0) * planes + (planes > 1 ? 120.0 : 0.0)) + boxes * 150.0;

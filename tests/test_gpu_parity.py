@@ -118,7 +118,11 @@ def test_layer_edges_one_row_and_tile_boundaries(mode):
     cfg, ocfg = _cfgs("v1")
     w = O.folded_weights(sd)
     geo = {n: (kind, cin, cout, k, dil) for n, kind, cin, cout, k, dil, _, _ in O.conv_layers(ocfg)}
-    for name, lengths in (("resblocks.2.convs1.2", (1, 7, 127, 128, 129, 513)), ("ups.0", (1, 2, 129)), ("ups.3", (1, 255, 257))):
+    # C = 256 / 128 / 64 / 32 resblock convs (the persistent planes kernel: tile heights 128..512, odd lengths make the
+    # C = 32 layer fall back from paired 128-byte boxes to 64-byte rows) and the polyphase upsamplers
+    for name, lengths in (("resblocks.2.convs1.2", (1, 7, 127, 128, 129, 513)), ("resblocks.4.convs1.1", (1, 255, 256, 257, 771)),
+                          ("resblocks.7.convs2.0", (3, 511, 512, 513, 1031)), ("resblocks.11.convs1.2", (1, 2, 511, 512, 1025, 1030)),
+                          ("ups.0", (1, 2, 129)), ("ups.3", (1, 255, 257))):
         for L in lengths:
             torch.manual_seed(L)
             x = torch.randn(1, geo[name][1], L)
@@ -173,9 +177,21 @@ def test_golden_intermediate_activations(case, mode):
     assert checked >= 10
 
 
+def test_batched_layer_matches_single_items():
+    """Tiles never mix batch items (3-D tensor maps): a B = 5 layer call equals five B = 1 calls bitwise."""
+    eng, _ = _engine("v1")
+    torch.manual_seed(3)
+    for name, cin, L in (("resblocks.10.convs2.1", 32, 700), ("resblocks.5.convs1.2", 128, 300)):
+        x = torch.randn(5, cin, L).numpy()
+        for mode in ("bf16x3", "bf16"):
+            y = eng.run_layer(name, x, pre_lrelu=True, precision=mode)
+            for b in (0, 4):
+                np.testing.assert_array_equal(y[b], eng.run_layer(name, x[b:b + 1], pre_lrelu=True, precision=mode)[0])
+
+
 def test_fused_plan_equals_tapped_plan_bitwise():
-    """The production plan fuses the MRF sum / divide into conv epilogues; the KEEP_TAPS plan runs them as separate
-    kernels.  Same arithmetic in the same order -> identical bits."""
+    """The production plan forms the MRF mean of the last stage inside conv_post; the KEEP_TAPS plan materialises every
+    intermediate.  Same kernels and arithmetic order on the data path -> identical bits."""
     eng, _ = _engine("v1")
     mel = O.synthetic_mel(2, 40, seed=3)
     for mode in ("fp32", "bf16x3"):
