@@ -54,10 +54,13 @@ struct Layer {
     std::vector<float> bias;
     // GEMM form
     int taps = 0, tap_off0 = 0, tap_step = 0, Np = 0, ups_s = 1, ups_p = 0;
-    int cin_pad = 0, kc = 64;
+    int cin_pad = 0, kc = 64;   // tensor-core family: channels of the input planes (>= 32, multiple of kc)
+    int cout_tc = 0, Np_tc = 0;  // tensor-core family: output channels padded to >= 32 (zero weights / bias), GEMM N
     // device packs
     float* d_w32 = nullptr;            // [taps][Cin][Np]  (conv_post: [k][C])
     float* d_bias = nullptr;           // [Cout]
+    float* d_bias_tc = nullptr;        // [cout_tc], zero padded
+    float* d_w32_tc = nullptr;         // conv_post only: [k][cin_pad], zero padded
     __nv_bfloat16* d_wb_hi = nullptr;  // [taps*Np][cin_pad]
     __nv_bfloat16* d_wb_lo = nullptr;
 };
@@ -172,8 +175,12 @@ void add_layer(hfg_engine* e, Layer L) {
         L.taps = (L.k + L.stride - 1) / L.stride; L.tap_off0 = 0; L.tap_step = -1;
         L.Np = L.stride * L.cout; L.ups_s = L.stride; L.ups_p = L.pad;
     }
+    // Tensor-core family: stages narrower than 32 channels (V2's tail) are carried with 32 channels; the extra channels have
+    // zero weights and zero bias, so they hold lrelu(0) = 0 everywhere and change nothing.
     L.kc = (L.cin % 64 == 0 || L.cin > 64) ? 64 : 32;
-    L.cin_pad = (L.cin + L.kc - 1) / L.kc * L.kc;
+    L.cin_pad = std::max(32, (L.cin + L.kc - 1) / L.kc * L.kc);
+    L.cout_tc = L.is_post ? 1 : std::max(32, L.cout);
+    L.Np_tc = L.transposed ? L.stride * L.cout_tc : L.cout_tc;
     e->index[L.name] = (int)e->layers.size();
     e->layers.push_back(std::move(L));
 }
@@ -224,8 +231,8 @@ Layer* find_layer(hfg_engine* e, const char* name) {
 }
 
 void free_layer_dev(Layer& L) {
-    cudaFree(L.d_w32); cudaFree(L.d_bias); cudaFree(L.d_wb_hi); cudaFree(L.d_wb_lo);
-    L.d_w32 = L.d_bias = nullptr; L.d_wb_hi = L.d_wb_lo = nullptr;
+    cudaFree(L.d_w32); cudaFree(L.d_bias); cudaFree(L.d_wb_hi); cudaFree(L.d_wb_lo); cudaFree(L.d_bias_tc); cudaFree(L.d_w32_tc);
+    L.d_w32 = L.d_bias = L.d_bias_tc = L.d_w32_tc = nullptr; L.d_wb_hi = L.d_wb_lo = nullptr;
 }
 
 inline uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat16_rn
@@ -241,7 +248,18 @@ int upload_layer(Layer& L) {
     const int Cin = L.cin, Cout = L.cout, k = L.k;
     CK(cudaMalloc(&L.d_bias, sizeof(float) * Cout));
     CK(cudaMemcpy(L.d_bias, L.bias.data(), sizeof(float) * Cout, cudaMemcpyHostToDevice));
+    {
+        std::vector<float> bt((size_t)L.cout_tc, 0.f);
+        std::copy(L.bias.begin(), L.bias.end(), bt.begin());
+        CK(cudaMalloc(&L.d_bias_tc, bt.size() * sizeof(float)));
+        CK(cudaMemcpy(L.d_bias_tc, bt.data(), bt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     if (L.is_post) {
+        std::vector<float> pt((size_t)k * L.cin_pad, 0.f);
+        for (int j = 0; j < k; ++j)
+            for (int ci = 0; ci < Cin; ++ci) pt[(size_t)j * L.cin_pad + ci] = L.w[(size_t)ci * k + j];
+        CK(cudaMalloc(&L.d_w32_tc, pt.size() * sizeof(float)));
+        CK(cudaMemcpy(L.d_w32_tc, pt.data(), pt.size() * sizeof(float), cudaMemcpyHostToDevice));
         std::vector<float> p((size_t)k * Cin);
         for (int j = 0; j < k; ++j)
             for (int ci = 0; ci < Cin; ++ci) p[(size_t)j * Cin + ci] = L.w[(size_t)ci * k + j];   // w[0][ci][j]
@@ -266,14 +284,16 @@ int upload_layer(Layer& L) {
     }
     CK(cudaMalloc(&L.d_w32, p.size() * sizeof(float)));
     CK(cudaMemcpy(L.d_w32, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
-    // tensor-core pack: [taps*Np][cin_pad] bf16 hi/lo, K-major
-    std::vector<uint16_t> hi((size_t)L.taps * L.Np * L.cin_pad, 0), lo(hi.size(), 0);
+    // tensor-core pack: [taps*Np_tc][cin_pad] bf16 hi/lo, K-major (rows of padded output channels and columns of padded
+    // input channels stay zero)
+    std::vector<uint16_t> hi((size_t)L.taps * L.Np_tc * L.cin_pad, 0), lo(hi.size(), 0);
     for (int j = 0; j < L.taps; ++j)
         for (int ci = 0; ci < Cin; ++ci)
             for (int n = 0; n < L.Np; ++n) {
                 const float v = p[((size_t)j * Cin + ci) * L.Np + n];
                 const uint16_t h = f2bf(v);
-                const size_t o = ((size_t)j * L.Np + n) * L.cin_pad + ci;
+                const int n_tc = (n / Cout) * L.cout_tc + (n % Cout);   // (phase, co) -> padded column
+                const size_t o = ((size_t)j * L.Np_tc + n_tc) * L.cin_pad + ci;
                 hi[o] = h;
                 lo[o] = f2bf(v - bf2f(h));
             }
@@ -291,6 +311,13 @@ ConvGeom geom_of(const Layer& L, int B, int Lin) {
     g.Mrows = L.transposed ? Lin + L.taps - 1 : Lin;
     g.Np = L.Np; g.taps = L.taps; g.tap_off0 = L.tap_off0; g.tap_step = L.tap_step;
     g.ups_s = L.ups_s; g.ups_p = L.ups_p;
+    return g;
+}
+
+// Geometry of the same layer on the tensor-core family's (channel-padded) planes.
+ConvGeom geom_tc(const Layer& L, int B, int Lin) {
+    ConvGeom g = geom_of(L, B, Lin);
+    g.Cin = L.cin_pad; g.Cout = L.cout_tc; g.Np = L.Np_tc;
     return g;
 }
 
@@ -320,12 +347,12 @@ struct Bump {
     }
 };
 
-size_t stage_elems_max(const hfg_engine* e, int B, int T) {
+size_t stage_elems_max(const hfg_engine* e, int B, int T, int min_ch = 1) {
     size_t mx = 0;
     size_t L = (size_t)T;
     for (int i = 0; i < e->cfg.num_upsamples; ++i) {
         L *= e->cfg.upsample_rates[i];
-        mx = std::max(mx, (size_t)B * L * (e->cfg.upsample_initial_channel >> (i + 1)));
+        mx = std::max(mx, (size_t)B * L * std::max(min_ch, e->cfg.upsample_initial_channel >> (i + 1)));
     }
     return mx;
 }
@@ -353,16 +380,15 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     const int NU = c.num_upsamples;
     const int nk = c.num_kernels;
     // number of leading stages (after conv_pre) that run on tensor cores; -1: conv_pre is fp32 too
+    // (every stage: narrow stages are carried with 32 channels, see add_layer)
     int n_tc = -1;
-    if (prec != HFG_PREC_FP32 && c0 % 32 == 0) {
-        n_tc = 0;
-        while (n_tc < NU && (c0 >> (n_tc + 1)) % 32 == 0) ++n_tc;
-    }
+    if (prec != HFG_PREC_FP32 && c0 % 32 == 0) n_tc = NU;
     const bool any_tc = n_tc >= 0;
     const bool any_32 = n_tc < NU;   // some stage (or everything) runs on the fp32 family
 
     Bump bump{base};
     const size_t smax = stage_elems_max(e, B, T);
+    const size_t smax_tc = stage_elems_max(e, B, T, 32);   // planes of the tensor-core family
     const size_t n_pre = (size_t)B * T * c0;
     const Layer& pre = e->layers[e->index["conv_pre"]];
     const Layer& post = e->layers[e->index["conv_post"]];
@@ -400,9 +426,9 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         mel_p = take_planes((size_t)B * T * pre.cin_pad);
         x0_p = take_planes(n_pre);
         if (n_tc > 0) {
-            u_p = take_planes(smax); xt_p = take_planes(smax); pp[0] = take_planes(smax); pp[1] = take_planes(smax);
-            s_p = take_planes(smax);
-            for (int j = 0; j < nk; ++j) r_p[j] = take_planes(smax);
+            u_p = take_planes(smax_tc); xt_p = take_planes(smax_tc); pp[0] = take_planes(smax_tc); pp[1] = take_planes(smax_tc);
+            s_p = take_planes(smax_tc);
+            for (int j = 0; j < nk; ++j) r_p[j] = take_planes(smax_tc);
         }
     }
 
@@ -419,9 +445,9 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         Step s{};
         UmmaConvParams p;
         memset(&p, 0, sizeof p);
-        p.g = geom_of(L, B, Lin);
+        p.g = geom_tc(L, B, Lin);
         p.cin_pad = L.cin_pad; p.kc = L.kc; p.npass = npass;
-        p.bias = L.d_bias; p.res_hi = res.hi; p.res_lo = x3 ? res.lo : nullptr;
+        p.bias = L.d_bias_tc; p.res_hi = res.hi; p.res_lo = x3 ? res.lo : nullptr;
         p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
         p.a_per_tap = a_per_tap;
         work(s, L, Lin, 2);
@@ -444,13 +470,13 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.fval = j == nk - 1 ? (float)nk : 0.f;
         push(std::move(s));
     };
-    auto to_raw = [&](Planes p, float* raw, size_t ne) {
-        Step s{}; s.kind = S_P2RAW; s.b_in = p.hi; s.b_in_lo = x3 ? p.lo : nullptr; s.f_out = raw; s.n = ne;
+    auto to_raw = [&](Planes p, float* raw, size_t rows, int C_tc, int C) {   // [rows][C_tc] planes -> [rows][C] fp32
+        Step s{}; s.kind = S_P2RAW; s.b_in = p.hi; s.b_in_lo = x3 ? p.lo : nullptr; s.f_out = raw; s.n = rows; s.cpad = C_tc; s.C = C;
         push(std::move(s));
     };
     auto tap_planes = [&](const char* name, Planes p, int C, int L) {
         if (!keep_taps) return;
-        to_raw(p, tap_tmp, (size_t)B * L * C);
+        to_raw(p, tap_tmp, (size_t)B * L, std::max(32, C), C);
         tap(name, tap_tmp, C, L);
     };
 
@@ -476,8 +502,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         const int ch = up.cout;
         const int Lin = L;
         L *= up.stride;
-        const size_t ne = (size_t)B * L * ch;
         const bool tc_stage = i < n_tc;
+        const size_t ne = (size_t)B * L * (tc_stage ? up.cout_tc : ch);
         if (tc_stage) {
             const bool last_stage = i == NU - 1;
             const bool next_tc = i + 1 < n_tc;
@@ -508,8 +534,11 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                 s.mrf.nk = nk;
                 s.mrf.out_hi = want_planes ? s_p.hi : nullptr;
                 s.mrf.out_lo = (want_planes && x3) ? s_p.lo : nullptr;
-                s.mrf.out_raw = want_raw ? xs : nullptr;
+                s.mrf.out_raw = (want_raw && up.cout_tc == ch) ? xs : nullptr;
+                s.mrf.out_hi = (want_planes || up.cout_tc != ch) ? s_p.hi : nullptr;
+                s.mrf.out_lo = ((want_planes || up.cout_tc != ch) && x3) ? s_p.lo : nullptr;
                 push(std::move(s));
+                if (want_raw && up.cout_tc != ch) to_raw(s_p, xs, (size_t)B * L, up.cout_tc, ch);
             }
             snprintf(nm, sizeof nm, "stage.%d", i);
             tap(nm, xs, ch, L);
@@ -551,6 +580,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.w = post.d_w32; s.bias = post.d_bias; s.f_out = pass ? wave_dev : post_tap;
         s.B = B; s.L = L; s.C = post.cin; s.k = post.k; s.flag0 = 1; s.flag1 = pass;
         if (post_planes) {
+            s.w = post.d_w32_tc; s.C = post.cin_pad;
             // One kernel for both plans (identical arithmetic order): the production plan hands it the nk branch outputs and
             // it forms the MRF mean itself; the tap plan hands it the already combined stage planes (nk = 1).
             s.kind = S_POSTMRF;
@@ -616,7 +646,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_CONV32: CK(launch_conv_fp32(s.cp, st)); break;
             case S_UMMA: CK(launch_conv_umma(s.ul, st)); break;
             case S_UMMA2: CK(launch_conv_umma2(s.u2, st)); break;
-            case S_P2RAW: CK(launch_planes_to_raw(s.b_in, s.b_in_lo, s.f_out, s.n, st)); break;
+            case S_P2RAW: CK(launch_planes_to_raw(s.b_in, s.b_in_lo, s.f_out, s.n, s.cpad, s.C, st)); break;
             case S_MRF: CK(launch_mrf_combine(s.mrf, s.n, st)); break;
             case S_POSTMRF: CK(launch_conv_post_mrf(s.mrf, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
             case S_POST32: CK(launch_conv_post_fp32(s.f_in, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag0, s.flag1, st)); break;
@@ -624,7 +654,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_ACCUM: CK(launch_accum_fp32(s.f_out, s.f_in, s.n, s.flag0, s.fval, st)); break;
             case S_SPLIT: CK(launch_act_split(s.f_in, s.b_out, s.b_out_lo, s.n, s.flag0, st)); break;
             case S_MEL_CL32: CK(launch_transpose_cf_to_cl(s.f_in, s.f_out, s.B, s.C, s.L, st)); break;
-            case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, st)); break;
+            case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, 0, st)); break;
             case S_TAP: RET(store_tap(e, s)); break;   // a copy, not one of our kernels
         }
         if (ncu) cudaProfilerStop();
@@ -876,8 +906,8 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
     CK(cudaSetDevice(e->device));
     const ConvGeom g = geom_of(*lay, B, L);
     const size_t n_in = (size_t)B * lay->cin * L, n_out = (size_t)B * lay->cout * g.Lout;
-    const size_t n_in_pad = (size_t)B * lay->cin_pad * L;
-    const size_t need = (2 * n_in + 2 * n_out) * sizeof(float) + 4 * n_in_pad * 2 + 4 * n_out * 2 + 16 * 256;
+    const size_t n_in_pad = (size_t)B * lay->cin_pad * L, n_out_pad = (size_t)B * lay->cout_tc * g.Lout;
+    const size_t need = (2 * n_in + 2 * n_out) * sizeof(float) + 4 * n_in_pad * 2 + 4 * n_out_pad * 2 + 16 * 256;
     if (need > e->scratch_bytes) {
         CK(cudaStreamSynchronize(e->stream));
         cudaFree(e->scratch);
@@ -892,8 +922,8 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
     float* y_cf = bump.take<float>(n_out);
     __nv_bfloat16* a_hi = bump.take<__nv_bfloat16>(n_in_pad);
     __nv_bfloat16* a_lo = bump.take<__nv_bfloat16>(n_in_pad);
-    __nv_bfloat16* y_hi = bump.take<__nv_bfloat16>(n_out);
-    __nv_bfloat16* y_lo = bump.take<__nv_bfloat16>(n_out);
+    __nv_bfloat16* y_hi = bump.take<__nv_bfloat16>(n_out_pad);
+    __nv_bfloat16* y_lo = bump.take<__nv_bfloat16>(n_out_pad);
     cudaStream_t st = e->stream;
     CK(cudaMemcpyAsync(x_cf, x, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
     if (lay->is_post) {
@@ -907,37 +937,26 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
         CK(launch_transpose_cl_to_cf(y_cl, y_cf, B, lay->cout, g.Lout, st));
         e->launches += 3;
     } else {
+        // The forward's production path for this layer: activated operand planes in (channel-padded like the plan's),
+        // activated planes out, inverted back to the raw conv output for the caller.
         const bool x3 = precision == HFG_PREC_BF16X3;
-        if (lay->cin_pad != lay->cin) {
-            CK(cudaMemsetAsync(a_hi, 0, n_in_pad * 2, st));
-            CK(cudaMemsetAsync(a_lo, 0, n_in_pad * 2, st));
-            CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, lay->cin, L, lay->cin_pad, st));
-            if (pre_lrelu) return fail(HFG_ERR_UNSUPPORTED, "hfg_run_layer: pre_lrelu on a channel-padded layer");
-        } else {
-            CK(launch_transpose_cf_to_cl(x_cf, x_cl, B, lay->cin, L, st));
-            CK(launch_act_split(x_cl, a_hi, x3 ? a_lo : nullptr, n_in, pre_lrelu, st));
-            ++e->launches;
-        }
+        CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, lay->cin, L, lay->cin_pad, pre_lrelu, st));
         UmmaConvParams p;
         memset(&p, 0, sizeof p);
-        p.g = g; p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1;
-        p.bias = lay->d_bias; p.a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
-        // The forward's production path for this layer: the persistent planes kernel where it applies (its output is the
-        // ACTIVATED plane, inverted back to the raw conv output here), the v1 kernel with an fp32 output otherwise.
+        p.g = geom_tc(*lay, B, L); p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1;
+        p.bias = lay->d_bias_tc; p.a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
         p.y_act = y_hi; p.y_act_lo = x3 ? y_lo : nullptr;
         Umma2Launch u2;
         if (umma2_supported(p) && plan_conv_umma2(&u2, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo, e->sm_count) == HFG_OK) {
             CK(launch_conv_umma2(u2, st));
-            CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, n_out, st));
-            ++e->launches;
         } else {
-            p.y_act = nullptr; p.y_act_lo = nullptr; p.y_raw = y_cl;
             UmmaLaunch ul;
             RET(plan_conv_umma(&ul, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo));
             CK(launch_conv_umma(ul, st));
         }
+        CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, (size_t)B * g.Lout, lay->cout_tc, lay->cout, st));
         CK(launch_transpose_cl_to_cf(y_cl, y_cf, B, lay->cout, g.Lout, st));
-        e->launches += 3;
+        e->launches += 4;
     }
     CK(cudaMemcpyAsync(y, y_cf, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -69,9 +69,9 @@ cudaError_t launch_conv_post_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16
 // [B][C][L] <-> [B][L][C] fp32
 cudaError_t launch_transpose_cf_to_cl(const float* in, float* out, int B, int C, int L, cudaStream_t s);
 cudaError_t launch_transpose_cl_to_cf(const float* in, float* out, int B, int C, int L, cudaStream_t s);
-// mel [B][C][L] fp32 -> channels-last bf16 [B][L][Cpad] (zero padded channels), hi (+ lo) planes
+// [B][C][L] fp32 -> channels-last bf16 [B][L][Cpad] (zero padded channels), hi (+ lo) planes, optional lrelu
 cudaError_t launch_mel_to_cl_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int L, int Cpad,
-                                  cudaStream_t s);
+                                  int apply_lrelu, cudaStream_t s);
 // xs = (first ? r : xs + r) ; if div > 0: xs /= div   (MRF sum, hifigan_pretrained.py:133-137)
 cudaError_t launch_accum_fp32(float* xs, const float* r, size_t n, int first, float div, cudaStream_t s);
 // act planes from an fp32 tensor: hi = bf16(lrelu(x)), lo = bf16(lrelu(x) - hi)
@@ -131,8 +131,9 @@ int plan_conv_umma2(Umma2Launch* L, const UmmaConvParams& p, const __nv_bfloat16
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int sm_count);
 cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s);
 
-// raw fp32 = inverse-lrelu(hi (+ lo))   (taps, and the hand-over to an fp32-family stage)
-cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t n, cudaStream_t s);
+// raw fp32 [rows][C] = inverse-lrelu(hi (+ lo)) of planes [rows][C_tc], C <= C_tc   (taps; drops padding channels)
+cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t rows, int C_tc, int C,
+                                 cudaStream_t s);
 // MRF combine (hifigan_pretrained.py:133-137) on planes: v = ((x0 + x1) + x2 ...) / nk with x_j = inverse-lrelu(plane j);
 // writes planes of lrelu(v) and/or raw fp32 v.
 struct MrfArgs {

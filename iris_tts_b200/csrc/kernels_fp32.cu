@@ -269,7 +269,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 // mel [B][C][L] fp32 -> [B][L][Cpad] bf16 hi (+ lo) planes, channels >= C zero.
 __global__ void mel_to_cl_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                      __nv_bfloat16* __restrict__ lo, int C, int L, int Cpad) {
+                                      __nv_bfloat16* __restrict__ lo, int C, int L, int Cpad, int apply_lrelu) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
@@ -282,7 +282,8 @@ __global__ void mel_to_cl_bf16_kernel(const float* __restrict__ in, __nv_bfloat1
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int l = l0 + i, c = c0 + threadIdx.x;
         if (l < L && c < Cpad) {
-            const float v = tile[threadIdx.x][i];
+            float v = tile[threadIdx.x][i];
+            if (apply_lrelu) v = lrelu(v);
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const size_t o = ((size_t)b * L + l) * Cpad + c;
             hi[o] = h;
@@ -331,11 +332,15 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat
     }
 }
 
+// [rows][C_tc] planes -> [rows][C] fp32 (C <= C_tc: drops the zero padding channels of narrow stages)
 __global__ void planes_to_raw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ raw,
-                                     size_t n8) {
+                                     size_t rows, int c8_tc, int c8) {
+    const size_t n8 = rows * (size_t)c8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / c8;
+        const int c = (int)(i - r * c8);
         float f[8];
-        load8(hi, lo, i, f);
+        load8(hi, lo, r * c8_tc + c, f);
         float4 a = make_float4(inv_lrelu(f[0]), inv_lrelu(f[1]), inv_lrelu(f[2]), inv_lrelu(f[3]));
         float4 b = make_float4(inv_lrelu(f[4]), inv_lrelu(f[5]), inv_lrelu(f[6]), inv_lrelu(f[7]));
         reinterpret_cast<float4*>(raw)[2 * i] = a;
@@ -430,20 +435,34 @@ __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfAr
     }
     for (int idx = tid; idx < k * C; idx += kPostMrfTile) w_s[idx] = __ldg(w + idx);
     __syncthreads();
-    float s = 0.f;
-    for (int j = 0; j < k; ++j) {
-        const float* xr = in_s + (tid + j) * stride;
-        const float* wr = w_s + j * C;
-        for (int c = 0; c < C; c += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xr + c);
-            const float4 ww = *reinterpret_cast<const float4*>(wr + c);
-            s = fmaf(x.x, ww.x, s); s = fmaf(x.y, ww.y, s); s = fmaf(x.z, ww.z, s); s = fmaf(x.w, ww.w, s);
+    // Thread = (group of 4 consecutive outputs) x (quarter of the channels): a sliding window over k + 3 staged rows feeds
+    // 4 accumulators, so one shared-memory row read serves up to 4 outputs; the 4 channel quarters meet in two shuffles.
+    const int q = tid & 3, og = tid >> 2;
+    const int cq = C / 4;                      // channels per quarter (multiple of 2; 8 for C = 32)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < cq; c += 2) {
+        const int ch = q * cq + c;
+        float2 win[4];                         // rows o .. o+3 of the window for this channel pair
+#pragma unroll
+        for (int i = 0; i < 3; ++i) win[i + 1] = *reinterpret_cast<const float2*>(in_s + (og * 4 + i) * stride + ch);
+        for (int j = 0; j < k; ++j) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) win[i] = win[i + 1];
+            win[3] = *reinterpret_cast<const float2*>(in_s + (og * 4 + j + 3) * stride + ch);
+            const float2 ww = *reinterpret_cast<const float2*>(w_s + j * C + ch);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(win[i].y, ww.y, fmaf(win[i].x, ww.x, acc[i]));
         }
     }
-    const int t = t0 + tid;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+    }
+    const int t = t0 + og * 4 + q;             // lane q of the group writes output q: a warp stores 32 consecutive samples
     if (t < L) {
-        s += __ldg(bias);
-        wave[(size_t)b * L + t] = apply_tanh ? tanhf(s) : s;
+        const float sres = (q == 0 ? acc[0] : q == 1 ? acc[1] : q == 2 ? acc[2] : acc[3]) + __ldg(bias);
+        wave[(size_t)b * L + t] = apply_tanh ? tanhf(sres) : sres;
     }
 }
 
@@ -500,10 +519,10 @@ cudaError_t launch_transpose_cl_to_cf(const float* in, float* out, int B, int C,
 }
 
 cudaError_t launch_mel_to_cl_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int L, int Cpad,
-                                  cudaStream_t s) {
+                                  int apply_lrelu, cudaStream_t s) {
     dim3 grid((L + 31) / 32, (Cpad + 31) / 32, B);
     dim3 block(32, 8);
-    mel_to_cl_bf16_kernel<<<grid, block, 0, s>>>(in, hi, lo, C, L, Cpad);
+    mel_to_cl_bf16_kernel<<<grid, block, 0, s>>>(in, hi, lo, C, L, Cpad, apply_lrelu);
     return cudaGetLastError();
 }
 
@@ -515,11 +534,12 @@ cudaError_t launch_accum_fp32(float* xs, const float* r, size_t n, int first, fl
     return cudaGetLastError();
 }
 
-cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t n, cudaStream_t s) {
-    if (n % 8 != 0) return cudaErrorInvalidValue;
-    const size_t n8 = n / 8;
+cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t rows, int C_tc, int C,
+                                 cudaStream_t s) {
+    if (C % 8 != 0 || C_tc % 8 != 0 || C > C_tc) return cudaErrorInvalidValue;
+    const size_t n8 = rows * (size_t)(C / 8);
     const int blocks = (int)std::min<size_t>((n8 + 255) / 256, 148 * 16);
-    planes_to_raw_kernel<<<blocks, 256, 0, s>>>(hi, lo, raw, n8);
+    planes_to_raw_kernel<<<blocks, 256, 0, s>>>(hi, lo, raw, rows, C_tc / 8, C / 8);
     return cudaGetLastError();
 }
 
