@@ -360,9 +360,10 @@ __global__ void mrf_combine_kernel(const MrfArgs a, size_t n8) {
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[t] = v[t] + inv_lrelu(f[t]);
         }
-        const float d = (float)a.nk;
+        // mean: multiply by 1/nk (the tensor-core modes are not bit-faithful to fp32 anyway; conv_post_mrf uses the same form)
+        const float rinv = 1.0f / (float)a.nk;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = __fdiv_rn(v[t], d);
+        for (int t = 0; t < 8; ++t) v[t] = v[t] * rinv;
         if (a.out_raw) {
             reinterpret_cast<float4*>(a.out_raw)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
             reinterpret_cast<float4*>(a.out_raw)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfAr
     const int b = blockIdx.y;
     const int c8n = C / 8;
     const size_t base8 = (size_t)b * L * c8n;
-    const float d = (float)a.nk;
+    const float rinv = 1.0f / (float)a.nk;
     for (int idx = tid; idx < rows * c8n; idx += kPostMrfTile) {
         const int r = idx / c8n, c8 = idx - r * c8n;
         const int t = t0 - pad + r;
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfAr
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float x = lrelu(__fdiv_rn(v[q], d));
+                    const float x = lrelu(v[q] * rinv);
                     const float h = __bfloat162float(__float2bfloat16_rn(x));   // what the operand plane(s) would hold
                     v[q] = a.lo[0] ? h + __bfloat162float(__float2bfloat16_rn(x - h)) : h;
                 }

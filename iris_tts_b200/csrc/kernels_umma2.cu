@@ -128,6 +128,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     const int acc_cols = a.mt * a.acc_n;   // columns of one accumulator buffer
+    // Programmatic dependent launch: the next kernel of the plan may start its own prologue on SMs this grid has left;
+    // nothing above reads or writes an activation.  Weights are static, so the resident-W loads below precede the wait.
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===== A / W producer =====
@@ -142,6 +145,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
             int sa = 0, sw = 0;
             uint32_t pa = 0, pw = 0;
+            pdl_wait();   // activations of the previous kernel are complete and visible from here on
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int b = tile / a.tiles_per_item;
                 const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
@@ -233,6 +237,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (lane == 0 && kHasRes && a.dbg != 1 && a.dbg != 3) {
             int se = 0;
             uint32_t pe = 0;
+            pdl_wait();
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int b = tile / a.tiles_per_item;
                 const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
@@ -266,6 +271,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int rshift = a.paired ? 1 : 0;
         const int halves = a.ecols / 32;
         const int depth = a.n_e >= 4 ? 2 : 1;        // stores in flight before a slot is handed back
+        pdl_wait();                                  // before the first global write (WAR against the previous kernel's reads)
         int se = 0;
         uint32_t pe = 0;
         int hist[2] = {-1, -1};                      // slots of the last `depth` stores (lane 0)
@@ -537,7 +543,11 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
                             const int pend = n_e >= 4 ? 2 : 1;
                             const double f_e = a.has_res ? std::min(1.0, std::max(0.25, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm)
                                                          : (n_e - pend >= 1 ? 1.0 : 0.5);
-                            const double cost = t_int / std::min({f_a, f_w, f_e}) / (mt * 128.0);
+                            // small problems: a partly filled last wave of the persistent grid idles SMs (favours smaller tiles)
+                            const long tiles = (long)((g.Lin + mt * 128 - 1) / (mt * 128)) * g.B;
+                            const long waves = (tiles + sm_count - 1) / std::max(1, sm_count);
+                            const double fill = (double)tiles / (double)(waves * std::max(1, sm_count));
+                            const double cost = t_int / std::min({f_a, f_w, f_e}) / (mt * 128.0) / fill;
                             if (cost < best - 1e-9) {
                                 best = cost;
                                 a.kc = kc; a.nchunks = nchunks; a.ecols = ecols; a.groups = groups;
@@ -614,11 +624,21 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
         configured[dev % 64] = true;
     }
     const Umma2Launch::Impl& I = *L.impl;
-#define HFG_U2_LAUNCH(P, R)                                                                                                   \
-    conv_umma2_kernel<P, R><<<I.grid, kThreads2, I.smem, s>>>(I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1], \
-                                                             I.map_y[0], I.map_y[1], I.a)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(I.grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = I.smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const int use_pdl = env_i("HFG_PDL", 1);
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+#define HFG_U2_LAUNCH(P, R)                                                                                              \
+    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<P, R>, I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1], \
+                           I.map_y[0], I.map_y[1], I.a)
+    cudaError_t e;
     if (I.a.planes == 2) { if (I.a.has_res) HFG_U2_LAUNCH(2, true); else HFG_U2_LAUNCH(2, false); }
     else { if (I.a.has_res) HFG_U2_LAUNCH(1, true); else HFG_U2_LAUNCH(1, false); }
+    if (e != cudaSuccess) return e;
 #undef HFG_U2_LAUNCH
     return cudaGetLastError();
 }

@@ -149,6 +149,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 
+// ---- programmatic dependent launch: the prologue (barriers, TMEM, weights) of kernel N+1 overlaps the tail of kernel N ----
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA stores / bulk groups ---------------------------------------------
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"

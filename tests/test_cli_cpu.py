@@ -1,0 +1,88 @@
+"""The synthesis CLI's vocoder hook: ``--vocoder_entry module:function`` with the documented
+``function(mel, sample_rate, hop_length) -> [samples]`` contract (reference HIFIGAN_SETUP.md:61-75), checked without a GPU
+through a stand-in entry."""
+import importlib.util
+import os
+import sys
+import types
+import wave
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("synthesize_cli", os.path.join(ROOT, "scripts", "synthesize.py"))
+cli = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(cli)
+
+
+@pytest.fixture
+def fake_entry():
+    calls = []
+    mod = types.ModuleType("fake_vocoder_mod")
+
+    def entry(mel, sample_rate, hop_length, checkpoint_path=None):
+        calls.append((mel.shape, sample_rate, hop_length, checkpoint_path))
+        t = mel.shape[-1] * hop_length
+        wav = 0.5 * np.sin(np.arange(t) * 2 * np.pi * 440.0 / sample_rate).astype(np.float32)
+        return wav if mel.ndim == 2 else np.stack([wav] * mel.shape[0])
+
+    mod.entry = entry
+    mod.not_callable = 3
+    sys.modules["fake_vocoder_mod"] = mod
+    yield calls
+    del sys.modules["fake_vocoder_mod"]
+
+
+def test_default_entry_is_the_documented_one():
+    args = cli.build_parser().parse_args(["--synthetic_frames", "4"])
+    assert args.vocoder == "hifigan" and args.vocoder_entry == "iris.hifigan_pretrained:infer_hifigan"
+    fn = cli.resolve_entry(args.vocoder_entry)
+    import iris.hifigan_pretrained as hp
+    assert fn is hp.infer_hifigan
+
+
+def test_entry_resolution_errors(fake_entry):
+    with pytest.raises(ValueError, match="module:function"):
+        cli.resolve_entry("iris.hifigan_pretrained.infer_hifigan")
+    with pytest.raises(ValueError, match="not a callable"):
+        cli.resolve_entry("fake_vocoder_mod:not_callable")
+    with pytest.raises(ModuleNotFoundError):
+        cli.resolve_entry("no_such_module_xyz:fn")
+
+
+def test_cli_runs_the_entry_and_writes_a_wav(tmp_path, fake_entry):
+    mel = np.random.default_rng(0).standard_normal((80, 10)).astype(np.float32)
+    np.save(tmp_path / "mel.npy", mel)
+    out = tmp_path / "sub" / "o.wav"
+    rc = cli.main(["--mel", str(tmp_path / "mel.npy"), "--output_wav", str(out), "--vocoder_entry", "fake_vocoder_mod:entry",
+                   "--checkpoint", "some.ckpt"])
+    assert rc == 0
+    assert fake_entry == [((80, 10), 22050, 256, "some.ckpt")]          # contract: (mel, sample_rate, hop_length)
+    with wave.open(str(out)) as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 22050, 2560)
+    # batches are written item by item
+    np.save(tmp_path / "melb.npy", np.stack([mel, mel]))
+    cli.main(["--mel", str(tmp_path / "melb.npy"), "--output_wav", str(tmp_path / "b.wav"), "--vocoder_entry", "fake_vocoder_mod:entry"])
+    assert (tmp_path / "b_0.wav").exists() and (tmp_path / "b_1.wav").exists()
+    with pytest.raises(ValueError):
+        np.save(tmp_path / "bad.npy", np.zeros((79, 4), np.float32))
+        cli.main(["--mel", str(tmp_path / "bad.npy"), "--vocoder_entry", "fake_vocoder_mod:entry"])
+
+
+def test_griffin_lim_restatement_runs_on_cpu():
+    from iris_tts_b200.griffin_lim import griffin_lim_from_log_mel, mel_filterbank
+    fb = mel_filterbank()
+    assert fb.shape == (80, 513) and (fb >= 0).all() and (fb.sum(axis=1) > 0).all()
+    # a pure tone's log-mel comes back as a waveform with its energy at that tone
+    sr, hop, T = 22050, 256, 40
+    t = np.arange(hop * (T - 1)) / sr
+    import torch
+    x = torch.from_numpy(np.sin(2 * np.pi * 1000.0 * t).astype(np.float32))
+    S = torch.stft(x, 1024, hop_length=hop, win_length=1024, window=torch.hann_window(1024), return_complex=True).abs().numpy()
+    logmel = np.log(np.clip(fb @ S, 1e-5, None))
+    y = griffin_lim_from_log_mel(logmel, n_iter=8)
+    assert y.dtype == np.float32 and abs(y.size - x.numel()) <= hop
+    spec = np.abs(np.fft.rfft(y))
+    peak_hz = np.argmax(spec) * sr / y.size
+    assert abs(peak_hz - 1000.0) < 60.0
