@@ -499,8 +499,10 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     const int force_res = env_i("HFG_U2_RESIDENT", -1), force_kc = env_i("HFG_U2_KC", 0), force_ec = env_i("HFG_U2_ECOLS", 0);
     bool ok = false;
     double best = 1e30;
-    for (int kc = p.kc; kc >= 32; kc -= 32) {
-      if (force_kc && kc != force_kc && p.kc != 32) continue;
+    // The K-chunk width fixes the order in which partial products enter the fp32 accumulator, so it depends on the mode and
+    // layer only -- never on B or L: a batch shard must reproduce the bits of the whole batch (tests: batch independence).
+    const int kc_fixed = force_kc ? std::min(force_kc, p.kc) : (planes == 2 ? 32 : p.kc);
+    for (int kc = kc_fixed; kc == kc_fixed; kc = 0) {
       const uint32_t row_bytes = (uint32_t)kc * 2u;
       const int nchunks = p.cin_pad / kc, ksteps = kc / 16;
       const uint32_t w_plane = rup((uint32_t)N * row_bytes, 1024);
