@@ -376,6 +376,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     const bool x3 = prec == HFG_PREC_BF16X3;
     const int npass = x3 ? 3 : 1;
     const int a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
+    const int snake = env_flag("HFG_SNAKE", 1);   // alternate the tile direction of consecutive convs (L2 reuse)
+    int n_umma2 = 0;
     const int c0 = c.upsample_initial_channel;
     const int NU = c.num_upsamples;
     const int nk = c.num_kernels;
@@ -450,6 +452,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.bias = L.d_bias_tc; p.res_hi = res.hi; p.res_lo = x3 ? res.lo : nullptr;
         p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
         p.a_per_tap = a_per_tap;
+        p.reverse = snake ? (n_umma2++ & 1) : 0;
         work(s, L, Lin, 2);
         if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, L.d_wb_hi, L.d_wb_lo, e->sm_count) == HFG_OK) {
             s.kind = S_UMMA2;

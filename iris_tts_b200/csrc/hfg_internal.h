@@ -97,6 +97,7 @@ struct UmmaConvParams {
     float* xs;            // MRF accumulator or nullptr
     int xs_read, xs_write;
     float out_div;
+    int reverse;          // conv_umma2: walk tiles last-to-first (L2 reuse between consecutive kernels)
     int a_per_tap;        // debug/A-B: reload the A tile per tap instead of shifting descriptors
 };
 

@@ -36,7 +36,7 @@ namespace {
 using namespace ptx;
 
 constexpr int kThreads2 = 384;   // 12 warps: 0 A/W producer, 1 residual producer, 2 TMEM alloc, 4-7 epilogue, 8-11 MMA issuers
-constexpr int kMaxA = 6, kMaxW = 6, kMaxE = 8;
+constexpr int kMaxA = 6, kMaxW = 12, kMaxE = 8;
 constexpr uint32_t kSmemBudget = 227u * 1024u - 4096u;   // dynamic smem; static barriers/bias live outside
 
 struct K2Args {
@@ -47,6 +47,8 @@ struct K2Args {
     int rows_a, a_box_rows, a_pieces;
     int n_a, n_w, n_e, w_resident, has_res;
     int ecols, groups;
+    int reverse;  // walk the tiles last-to-first: consecutive kernels alternate, so the part of the input the previous kernel wrote
+                  // last (still in the 126 MB L2) is the part this kernel reads first
     int concat;   // bf16x3, 2N <= 128: pass 1 = A_hi x [W_hi ; W_lo] (one MMA of width 2N), pass 2 = A_lo x W_hi; the epilogue adds the halves
     int acc_n;    // TMEM columns of one 128-row subtile accumulator (N, or 2N when concat)
     int paired;   // C = 32: residual / output boxes address two 64-byte time rows as one 128-byte row (full-line TMA requests)
@@ -147,8 +149,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t pa = 0, pw = 0;
             pdl_wait();   // activations of the previous kernel are complete and visible from here on
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int b = tile / a.tiles_per_item;
-                const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
+                const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+                const int b = tl / a.tiles_per_item;
+                const int m0 = (tl - b * a.tiles_per_item) * a.mt * 128;
                 for (int c = 0; c < a.nchunks; ++c) {
                     if (a.dbg != 3) {
                         mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
@@ -239,8 +242,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t pe = 0;
             pdl_wait();
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int b = tile / a.tiles_per_item;
-                const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
+                const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+                const int b = tl / a.tiles_per_item;
+                const int m0 = (tl - b * a.tiles_per_item) * a.mt * 128;
                 for (int ms = 0; ms < a.mt; ++ms) {
                     const int row0 = m0 + ms * 128;
                     if (row0 >= a.L) break;
@@ -277,8 +281,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         int hist[2] = {-1, -1};                      // slots of the last `depth` stores (lane 0)
         int it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-            const int b = tile / a.tiles_per_item;
-            const int m0 = (tile - b * a.tiles_per_item) * a.mt * 128;
+            const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+            const int b = tl / a.tiles_per_item;
+            const int m0 = (tl - b * a.tiles_per_item) * a.mt * 128;
             const int buf = it & 1;
             mbar_wait(bar_acc_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
@@ -481,7 +486,8 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     a.paired = (N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
     a.bias = p.bias;
     a.dbg = env_i("HFG_U2_DBG", 0);
-    a.concat = (planes == 2 && N <= 64 && env_i("HFG_U2_CONCAT", 1)) ? 1 : 0;
+    a.reverse = p.reverse;
+    a.concat = (planes == 2 && N <= env_i("HFG_U2_CONCAT_MAXN", 32)) ? 1 : 0;   // wider layers stream W: halving MT would double that traffic
     a.acc_n = a.concat ? 2 * N : N;
 
     // Choose (K-chunk width, epilogue box width, MT, resident W, ring depths) by a small cost model: cycles per output
@@ -494,7 +500,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     auto floor_clk = [](double n) { return std::max(128.0 * n / 256.0, (4096.0 + 32.0 * n) / 128.0); };
     // tensor cycles per K=16 step of one 128-row subtile, all passes
     const double step_clk = a.concat ? floor_clk(2.0 * N) + floor_clk(N) : p.npass * floor_clk(N);
-    const double lat_hbm = 3000.0, lat_l2 = 1600.0, sm_bw = 20.0, l2_bw = 36.0;   // cycles, cycles, bytes/cycle/SM
+    const double lat_hbm = 3500.0, lat_l2 = 3000.0, sm_bw = 20.0, l2_bw = 24.0;   // cycles, cycles, bytes/cycle/SM
     const int force_na = env_i("HFG_U2_NA", 0), force_nw = env_i("HFG_U2_NW", 0), force_ne = env_i("HFG_U2_NE", 0);
     const int force_res = env_i("HFG_U2_RESIDENT", -1), force_kc = env_i("HFG_U2_KC", 0), force_ec = env_i("HFG_U2_ECOLS", 0);
     bool ok = false;
@@ -543,7 +549,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
                             const double f_a = std::min(1.0, (n_a - 1) * (t_int / nchunks) / lat_hbm);
                             const double f_w = resident ? 1.0 : std::min(1.0, (n_w - 1) * (t_int / (nchunks * a.taps)) / lat_l2);
                             const int pend = n_e >= 4 ? 2 : 1;
-                            const double f_e = a.has_res ? std::min(1.0, std::max(0.25, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm)
+                            const double f_e = a.has_res ? std::max(0.6, std::min(1.0, std::max(0.5, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm))
                                                          : (n_e - pend >= 1 ? 1.0 : 0.5);
                             // small problems: a partly filled last wave of the persistent grid idles SMs (favours smaller tiles)
                             const long tiles = (long)((g.Lin + mt * 128 - 1) / (mt * 128)) * g.B;
