@@ -35,7 +35,9 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kThreads2 = 384;   // 12 warps: 0 A/W producer, 1 residual producer, 2 TMEM alloc, 4-7 epilogue, 8-11 MMA issuers
+// warps: 0 A/W producer, 1 residual producer, 2 TMEM alloc, 4-7 epilogue group 0, 8-11 MMA issuers, 12-15 epilogue group 1
+// (single-plane mode only: the two-plane epilogue needs more than the 128 registers a 512-thread CTA leaves per thread)
+constexpr int threads_for(int planes) { return planes == 1 ? 512 : 384; }
 constexpr int kMaxA = 6, kMaxW = 12, kMaxE = 8;
 constexpr uint32_t kSmemBudget = 227u * 1024u - 4096u;   // dynamic smem; static barriers/bias live outside
 
@@ -70,7 +72,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 template <int kPlanes, bool kHasRes>
-__global__ void __launch_bounds__(kThreads2, 1)
+__global__ void __launch_bounds__(threads_for(kPlanes), 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                   const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
@@ -84,6 +86,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int lane = threadIdx.x & 31;
     constexpr int planes = kPlanes;          // 1: bf16 ; 2: bf16x3 (hi + lo operand planes, three MMA passes)
     constexpr int npass = kPlanes == 2 ? 3 : 1;
+    constexpr int kEpiGroups = kPlanes == 1 ? 2 : 1;   // epilogue warp groups; steps alternate between them
     const uint32_t row_bytes = (uint32_t)a.kc * 2u;
     const uint32_t erow_bytes = a.paired ? 128u : (uint32_t)a.ecols * 2u;
 
@@ -106,7 +109,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const uint32_t bar_acc_empty = bp;         bp += 16;
     const uint32_t bar_wres = bp;
 
-    for (int i = threadIdx.x; i < a.N; i += kThreads2) bias_s[i] = a.bias[i];
+    for (int i = threadIdx.x; i < a.N; i += blockDim.x) bias_s[i] = a.bias[i];
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_y_hi);
         if (kHasRes) prefetch_tmap(&map_r_hi);
@@ -117,7 +120,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         for (int i = 0; i < a.n_a; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, nmma); }
         for (int i = 0; i < a.n_w; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, nmma); }
         for (int i = 0; i < a.n_e; ++i) { mbar_init(bar_e_full + 8 * i, 1); mbar_init(bar_e_empty + 8 * i, 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, nmma); mbar_init(bar_acc_empty + 8 * i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, nmma); mbar_init(bar_acc_empty + 8 * i, 4 * kEpiGroups); }
         mbar_init(bar_wres, 1);
         fence_barrier_init();
     }
@@ -176,7 +179,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // ===== MMA issuers =====
         // Issuer warp w owns subtile ms = w of every tile.  The whole warp walks the loops (warp-uniform values); only the
         // elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors advance by one add per MMA.
@@ -274,11 +277,17 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const uint32_t warp_off = (uint32_t)(q * 32) * (uint32_t)a.ecols * 2u;
         const int rshift = a.paired ? 1 : 0;
         const int halves = a.ecols / 32;
-        const int depth = a.n_e >= 4 ? 2 : 1;        // stores in flight before a slot is handed back
+        // A slot is handed back `depth` of this warp's own steps after its store was issued; it must be back before the warp
+        // meets the slot again, i.e. depth <= (own steps between two uses of a slot) - 1.
+        // With two groups a warp meets only every other step, and step s may reuse the slot of step s - n_e only if that
+        // slot's owner has handed it back: 2 * depth < n_e global steps (one group: depth < n_e).
+        const int depth = min(2, kEpiGroups == 2 ? (a.n_e - 1) / 2 : a.n_e - 1);
         pdl_wait();                                  // before the first global write (WAR against the previous kernel's reads)
         int se = 0;
         uint32_t pe = 0;
         int hist[2] = {-1, -1};                      // slots of the last `depth` stores (lane 0)
+        const int grp = warp >= 12 ? 1 : 0;          // epilogue group of this warp
+        int step = 0;                                // (tile, subtile, column group) steps alternate between the groups
         int it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
@@ -297,6 +306,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int row0 = m0 + ms * 128;
                 if (row0 >= a.L) break;
                 for (int g = 0; g < a.groups; ++g) {
+                    if (kEpiGroups > 1 && ((step++ & 1) != grp)) {   // the other group's step: only track the ring position
+                        if (++se == a.n_e) { se = 0; pe ^= 1u; }
+                        continue;
+                    }
                     if (kHasRes) mbar_wait(bar_e_full + 8 * se, pe);
                     else mbar_wait(bar_e_empty + 8 * se, pe ^ 1u);
                     const uint32_t slot = smem_e + se * e_slot_bytes;
@@ -367,11 +380,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             }
                         }
                     }
-                    if ((ms == a.mt - 1 || row0 + 128 >= a.L) && g == a.groups - 1) {
-                        tc_fence_before();   // last TMEM read of this accumulator buffer by this warp
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
-                    }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0 && a.dbg == 4) {
@@ -392,6 +400,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (++se == a.n_e) { se = 0; pe ^= 1u; }
                 }
             }
+            tc_fence_before();   // this warp has read the last of this accumulator buffer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
         }
         if (lane == 0) bulk_wait_read<0>();
     }
@@ -535,12 +546,14 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
                 if (resident && w_all > 140u * 1024u) continue;
                 if (force_res >= 0 && resident != force_res) continue;
                 const double w_bytes_tile = resident ? 0.0 : (double)w_all;
-                const double t_int = std::max({t_tile, bytes / sm_bw, w_bytes_tile / l2_bw, t_epi}) + 1200.0;
+                // streamed weights also cost one barrier round trip per (chunk, tap) in every issuer
+                const double t_int = std::max({t_tile, bytes / sm_bw, w_bytes_tile / l2_bw, t_epi}) + 1200.0 + (resident ? 0.0 : nchunks * a.taps * 80.0);
                 for (int n_w = resident ? 1 : kMaxW; n_w >= (resident ? 1 : 2); --n_w) {
                     if (!resident && force_nw && n_w != force_nw) continue;
                     const uint32_t w_bytes = resident ? w_all : (uint32_t)n_w * w_tile;
                     for (int n_e = kMaxE; n_e >= 2; --n_e) {
                         if (force_ne && n_e != force_ne) continue;
+                        if (planes == 1 && n_e == 2) continue;   // two epilogue groups alternate steps: a slot must outlive one own step
                         const uint32_t fixed = w_bytes + (uint32_t)n_e * e_slot;
                         if (fixed + 2 * a_stage > budget) continue;
                         const int n_a_max = (int)std::min<uint32_t>((budget - fixed) / a_stage, (uint32_t)kMaxA);
@@ -548,7 +561,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
                             if (force_na && n_a != force_na) continue;
                             const double f_a = std::min(1.0, (n_a - 1) * (t_int / nchunks) / lat_hbm);
                             const double f_w = resident ? 1.0 : std::min(1.0, (n_w - 1) * (t_int / (nchunks * a.taps)) / lat_l2);
-                            const int pend = n_e >= 4 ? 2 : 1;
+                            const int pend = planes == 1 ? 2 * std::min(2, (n_e - 1) / 2) : std::min(2, n_e - 1);   // slots held by stores in flight
                             const double f_e = a.has_res ? std::max(0.6, std::min(1.0, std::max(0.5, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm))
                                                          : (n_e - pend >= 1 ? 1.0 : 0.5);
                             // small problems: a partly filled last wave of the persistent grid idles SMs (favours smaller tiles)
@@ -634,7 +647,7 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
     const Umma2Launch::Impl& I = *L.impl;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(I.grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = I.smem; cfg.stream = s;
+    cfg.gridDim = dim3(I.grid); cfg.blockDim = dim3(threads_for(I.a.planes)); cfg.dynamicSmemBytes = I.smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
