@@ -65,7 +65,7 @@ struct Layer {
     __nv_bfloat16* d_wb_lo = nullptr;
 };
 
-enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_POST32, S_POSTBF, S_ACCUM, S_SPLIT, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP };
+enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_POST32, S_ACCUM, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP };
 
 struct Step {
     StepKind kind;
@@ -622,9 +622,8 @@ const char* kind_label(StepKind k) {
         case S_P2RAW: return "planes_to_raw";
         case S_MRF: return "mrf_combine";
         case S_POSTMRF: return "conv_post_mrf";
-        case S_POST32: case S_POSTBF: return "conv_post";
+        case S_POST32: return "conv_post";
         case S_ACCUM: return "accum";
-        case S_SPLIT: return "act_split";
         case S_MEL_CL32: return "transpose";
         case S_MEL_CLBF: return "mel_to_cl_bf16";
         default: return "copy";
@@ -653,9 +652,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_MRF: CK(launch_mrf_combine(s.mrf, s.n, st)); break;
             case S_POSTMRF: CK(launch_conv_post_mrf(s.mrf, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
             case S_POST32: CK(launch_conv_post_fp32(s.f_in, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag0, s.flag1, st)); break;
-            case S_POSTBF: CK(launch_conv_post_bf16(s.b_in, s.b_in_lo, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
             case S_ACCUM: CK(launch_accum_fp32(s.f_out, s.f_in, s.n, s.flag0, s.fval, st)); break;
-            case S_SPLIT: CK(launch_act_split(s.f_in, s.b_out, s.b_out_lo, s.n, s.flag0, st)); break;
             case S_MEL_CL32: CK(launch_transpose_cf_to_cl(s.f_in, s.f_out, s.B, s.C, s.L, st)); break;
             case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, 0, st)); break;
             case S_TAP: RET(store_tap(e, s)); break;   // a copy, not one of our kernels
