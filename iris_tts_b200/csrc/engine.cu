@@ -876,6 +876,10 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     const auto key = std::make_tuple((int)B, (int)T, (int)precision, keep ? 1 : 0);
     auto it = e->plans.find(key);
     if (it == e->plans.end()) {
+        if (e->plans.size() >= 64) {   // variable-length traffic: bound the cache (plans are cheap to rebuild)
+            CK(cudaStreamSynchronize(e->stream));
+            e->plans.clear();
+        }
         size_t bytes = 0;
         RET(build_plan(e, B, T, precision, keep, nullptr, nullptr, &bytes));
         RET(ensure_arena(e, bytes));
