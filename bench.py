@@ -180,7 +180,18 @@ def time_device_steps(eng, stream, mel_dev, out_dev, B, T, precision, steps, war
     return ms, eng.launch_count - l0, recs
 
 
-def roofline_from_records(recs, peaks, kernel="conv_umma2"):
+def ncu_traffic(precision, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/traffic_<mode>.json), or None."""
+    p = os.path.join(ROOT, "profiles", f"traffic_{precision}.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["kernels"][kernel + "_kernel"]["traffic_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def roofline_from_records(recs, peaks, kernel="conv_umma2", precision=None):
     """Dominant kernel = conv_umma2_kernel (the persistent tcgen05 conv: 72 of the 77 conv launches of a V1 forward)."""
     sel = [r for r in recs if r["kernel"] == kernel]
     if not sel:
@@ -190,7 +201,8 @@ def roofline_from_records(recs, peaks, kernel="conv_umma2"):
     total_ms = sum(r["ms"] for r in recs)
     achieved = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": kernel + "_kernel", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops"], "traffic": None, "launches": len(sel), "avg_launch_ms": ms / len(sel),
+            "frac": achieved / peaks["tflops"], "traffic": ncu_traffic(precision, kernel) if precision else None,
+            "algorithmic_bytes_per_launch": sum(r["bytes"] for r in sel) / len(sel), "launches": len(sel), "avg_launch_ms": ms / len(sel),
             "share_of_step": ms / total_ms if total_ms else None, "peak_source": peaks["source"],
             "algorithmic_flops_per_launch": flops / len(sel)}
 
@@ -283,7 +295,7 @@ def run_ours(args):
         rl2 = work.layer_roofline_seconds(voc.model.config, B, T, 2, peaks["tflops"] * 1e12, peaks["gbs"] * 1e9)
         secondary = {"dtype": "bf16", "value": samples_per_step * args.steps / (ms2 * 1e-3), "unit": "samples/s",
                      "ms_per_step": ms2 / args.steps, "layer_roofline_ms": rl2 * 1e3, "layer_roofline_frac": rl2 * 1e3 / (ms2 / args.steps),
-                     "roofline": roofline_from_records(recs2, peaks),
+                     "roofline": roofline_from_records(recs2, peaks, precision="bf16"),
                      "tolerance": "max-abs 1.5e-1 vs oracle on loud weights (tests/test_gpu_parity.py); 1e-3 at default init"}
 
     if rank != 0:
@@ -317,7 +329,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(B * 80 * T * 4),
                 "d2h_bytes_per_step": int(B * T * hop * 4), "api": "iris.hifigan_pretrained.HiFiGANGenerator.__call__(np.ndarray)"},
         "gpu_launches": int(launches),
-        "roofline": roofline_from_records(recs, peaks),
+        "roofline": roofline_from_records(recs, peaks, precision=args.precision),
         "layer_roofline": {"ms": rl * 1e3, "frac": rl * 1e3 / ms_step,
                            "definition": "sum_l max(F_l/P, Q_l/BW) (SURVEY 8d): " + ("bf16 peak, 2-byte activations" if args.precision == "bf16" else
                                          "fp32-class mode: P = bf16 peak / 2 (TF32-class), 4-byte activations"),

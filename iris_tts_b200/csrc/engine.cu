@@ -642,7 +642,8 @@ int run_plan(hfg_engine* e, Plan* plan) {
         CK(cudaEventRecord(e->prof_events[nev++], st));
     }
     for (const Step& s : plan->steps) {
-        const bool ncu = !e->ncu_layers.empty() && std::find(e->ncu_layers.begin(), e->ncu_layers.end(), s.label) != e->ncu_layers.end();
+        const bool ncu = !e->ncu_layers.empty() && s.kind != S_TAP &&
+                         (e->ncu_layers[0] == "*" || std::find(e->ncu_layers.begin(), e->ncu_layers.end(), s.label) != e->ncu_layers.end());
         if (ncu) cudaProfilerStart();
         switch (s.kind) {
             case S_CONV32: CK(launch_conv_fp32(s.cp, st)); break;

@@ -26,4 +26,9 @@ for MODE in ${NCU_MODES:-bf16x3 bf16}; do
     rm -f $OUT/${TAG}_prof_${MODE}.ncu-rep
   fi
 done
+# DRAM traffic of EVERY launch of one forward (metrics-only pass), per mode -> roofline.traffic in bench.py
+for MODE in ${NCU_MODES:-bf16x3 bf16}; do
+  PROF="python tools/layer_times.py --mode $MODE --B 16 --T 862 --reps 1 --warm 1"
+  HFG_NCU_LAYERS='*' timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/${TAG}_traffic_${MODE}.csv $PROF > $OUT/${TAG}_ncu_traffic_${MODE}.log 2>&1
+done
 tail -3 $OUT/${TAG}_pytest_gpu.log; tail -4 $OUT/${TAG}_smoke.log; head -1 $OUT/${TAG}_layer_times_bf16.txt; head -1 $OUT/${TAG}_layer_times_bf16x3.txt; tail -2 $OUT/${TAG}_ncu_full_bf16.log; ls -la $OUT
