@@ -453,7 +453,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
         p.a_per_tap = a_per_tap;
         p.reverse = snake ? (n_umma2++ & 1) : 0;
-        work(s, L, Lin, 2);
+        work(s, L, Lin, x3 ? 4 : 2);   // two bf16 planes carry what an fp32 activation would
         if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, L.d_wb_hi, L.d_wb_lo, e->sm_count) == HFG_OK) {
             s.kind = S_UMMA2;
         } else {
@@ -593,7 +593,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         } else {
             s.kind = S_POST32; s.f_in = x_raw;
         }
-        work(s, post, L, post_planes ? 2 : 4);
+        work(s, post, L, post_planes ? (x3 ? 4 : 2) : 4);
         push(std::move(s));
         if (!pass) tap("conv_post", post_tap, 1, L);
     }
