@@ -204,6 +204,9 @@ def roofline_from_records(recs, peaks, kernel="conv_umma2", precision=None):
             "frac": achieved / peaks["tflops"], "traffic": ncu_traffic(precision, kernel) if precision else None,
             "algorithmic_bytes_per_launch": sum(r["bytes"] for r in sel) / len(sel), "launches": len(sel), "avg_launch_ms": ms / len(sel),
             "share_of_step": ms / total_ms if total_ms else None, "peak_source": peaks["source"],
+            # bf16x3 executes three bf16 MMAs per algorithmic one (hi*hi, lo*hi, hi*lo): the tensor pipe's own rate
+            "executed_flop_factor": 3 if precision == "bf16x3" else 1,
+            "executed_frac": (3 if precision == "bf16x3" else 1) * achieved / peaks["tflops"],
             "algorithmic_flops_per_launch": flops / len(sel)}
 
 

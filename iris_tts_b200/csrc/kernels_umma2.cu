@@ -49,6 +49,9 @@ struct K2Args {
     int rows_a, a_box_rows, a_pieces;
     int n_a, n_w, n_e, w_resident, has_res;
     int ecols, groups;
+    int ups;      // polyphase ConvTranspose1d (k = 2s, N = s*C_out <= 256): GEMM row m, column half h lands on output half-row
+                  // 2m - 1 + h of [B][2*L_in][N/2]; the two column groups ARE the halves, stored through a 4-D tensor map
+    int cout;     // bias index = column % cout
     int reverse;  // walk the tiles last-to-first: consecutive kernels alternate, so the part of the input the previous kernel wrote
                   // last (still in the 126 MB L2) is the part this kernel reads first
     int concat;   // bf16x3, 2N <= 128: pass 1 = A_hi x [W_hi ; W_lo] (one MMA of width 2N), pass 2 = A_lo x W_hi; the epilogue adds the halves
@@ -109,7 +112,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const uint32_t bar_acc_empty = bp;         bp += 16;
     const uint32_t bar_wres = bp;
 
-    for (int i = threadIdx.x; i < a.N; i += blockDim.x) bias_s[i] = a.bias[i];
+    for (int i = threadIdx.x; i < a.N; i += blockDim.x) bias_s[i] = a.bias[i % a.cout];
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_y_hi);
         if (kHasRes) prefetch_tmap(&map_r_hi);
@@ -385,8 +388,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (lane == 0 && a.dbg == 4) {
                         mbar_arrive(bar_e_empty + 8 * se);
                     } else if (lane == 0) {
-                        for (int pl = 0; pl < planes; ++pl)
-                            tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, g * a.ecols, (row0 + q * 32) >> rshift, b);
+                        for (int pl = 0; pl < planes; ++pl) {
+                            if (a.ups)   // half g of GEMM rows m..m+31 -> (r, q) = (1, m - 1) for g = 0, (0, m) for g = 1
+                                tma_store_4d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, 0, 1 - g, row0 + q * 32 - 1 + g, b);
+                            else
+                                tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, g * a.ecols, (row0 + q * 32) >> rshift, b);
+                        }
                         bulk_commit();
                         // hand back the slot whose store was issued `depth` steps ago: its shared-memory reads are done
                         if (depth == 2) {
@@ -436,8 +443,8 @@ bool encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, co
             uint32_t inner_bytes) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
-    cuuint64_t gdim[3], gstr[2];
-    cuuint32_t bx[3], es[3] = {1, 1, 1};
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
     const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -471,9 +478,15 @@ struct Umma2Launch::Impl {
 bool umma2_supported(const UmmaConvParams& p) {
     const ConvGeom& g = p.g;
     if (env_i("HFG_UMMA_V", 2) < 2) return false;
-    if (g.ups_s != 1 || g.Np != g.Cout || g.Cout > 256 || g.Cout % 32 != 0 || g.Cin != g.Cout) return false;
     if (p.cin_pad != g.Cin) return false;
     if (p.y_raw || p.res || p.xs || !p.y_act) return false;   // planes-only dataflow
+    if (g.ups_s == 1) {
+        if (g.Np != g.Cout || g.Cout > 256 || g.Cout % 32 != 0 || g.Cin != g.Cout) return false;
+    } else {   // polyphase upsampler with k = 2s (two taps, pad = s/2) whose whole N = s*C_out fits one tile
+        if (env_i("HFG_U2_UPS", 1) == 0) return false;
+        if (g.taps != 2 || g.tap_off0 != 0 || g.tap_step != -1 || g.ups_s % 2 != 0 || g.ups_p * 2 != g.ups_s) return false;
+        if (g.Np != g.ups_s * g.Cout || g.Np > 128 || g.Np % 64 != 0 || p.res_hi) return false;   // halves of <= 64 columns
+    }
     return true;
 }
 
@@ -486,15 +499,17 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     K2Args& a = I->a;
     memset(&a, 0, sizeof a);
     const int planes = p.npass > 1 ? 2 : 1;
-    const int N = g.Cout;
-    a.B = g.B; a.L = g.Lin; a.N = N;
+    const bool ups = g.ups_s > 1;
+    const int N = g.Np;                 // C_out, or s * C_out for the polyphase upsampler
+    a.B = g.B; a.L = g.Mrows; a.N = N;   // GEMM rows per item (L_in + 1 for the upsampler: the last row only feeds its first half)
+    a.ups = ups ? 1 : 0; a.cout = g.Cout;
     a.taps = g.taps; a.tap_off0 = g.tap_off0; a.tap_step = g.tap_step;
     const int last_off = g.tap_off0 + (g.taps - 1) * g.tap_step;
     a.lo = std::min(g.tap_off0, last_off);
     const int span = std::max(g.tap_off0, last_off) - a.lo;
     a.planes = planes; a.npass = p.npass;
     a.has_res = (p.res_hi != nullptr);
-    a.paired = (N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
+    a.paired = (!ups && N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
     a.bias = p.bias;
     a.dbg = env_i("HFG_U2_DBG", 0);
     a.reverse = p.reverse;
@@ -506,7 +521,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     // max(128*N/256, (4096 + 32*N)/128) cycles per K=16 MMA), the HBM time of the tile and the L2 time of the streamed
     // weights, inflated when a ring is too shallow to cover its fetch latency.  Narrow K-chunks / boxes (32 channels)
     // halve the stage sizes, which is what lets the two-plane (bf16x3) mode keep MT >= 2 and real pipelining.
-    const int mt_max = std::max(1, std::min({256 / a.acc_n, 4, env_i("HFG_U2_MT", 4), (g.Lin + 127) / 128}));
+    const int mt_max = std::max(1, std::min({256 / a.acc_n, 4, env_i("HFG_U2_MT", 4), (g.Mrows + 127) / 128}));
     const uint32_t budget = kSmemBudget - 1024;   // alignment slack
     auto floor_clk = [](double n) { return std::max(128.0 * n / 256.0, (4096.0 + 32.0 * n) / 128.0); };
     // tensor cycles per K=16 step of one 128-row subtile, all passes
@@ -528,6 +543,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
       const uint32_t w_all = (uint32_t)(nchunks * a.taps) * w_tile;
       for (int ecols = std::min(64, N); ecols >= 32; ecols -= 32) {
         if (force_ec && ecols != force_ec && N > 32) continue;
+        if (ups && ecols != N / 2) continue;   // the two column groups are the two output half-rows
         const int groups = N / ecols;
         const uint32_t e_plane = 128u * (uint32_t)ecols * 2u;
         const uint32_t e_slot = e_plane * planes;
@@ -565,7 +581,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
                             const double f_e = a.has_res ? std::max(0.6, std::min(1.0, std::max(0.5, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm))
                                                          : (n_e - pend >= 1 ? 1.0 : 0.5);
                             // small problems: a partly filled last wave of the persistent grid idles SMs (favours smaller tiles)
-                            const long tiles = (long)((g.Lin + mt * 128 - 1) / (mt * 128)) * g.B;
+                            const long tiles = (long)((g.Mrows + mt * 128 - 1) / (mt * 128)) * g.B;
                             const long waves = (tiles + sm_count - 1) / std::max(1, sm_count);
                             const double fill = (double)tiles / (double)(waves * std::max(1, sm_count));
                             const double cost = t_int / std::min({f_a, f_w, f_e}) / (mt * 128.0) / fill;
@@ -593,7 +609,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
                 N, a.taps, planes, a.has_res, a.kc, a.ecols, a.mt, a.w_resident, a.n_a, a.n_w, a.n_e, I->smem, best);
     const uint32_t row_bytes = (uint32_t)a.kc * 2u;
     if (!ok) return HFG_ERR_UNSUPPORTED;
-    a.tiles_per_item = (g.Lin + a.mt * 128 - 1) / (a.mt * 128);
+    a.tiles_per_item = (g.Mrows + a.mt * 128 - 1) / (a.mt * 128);
     a.total_tiles = a.tiles_per_item * g.B;
     I->grid = std::min(a.total_tiles, std::max(1, sm_count));
 
@@ -623,8 +639,16 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
         const void* r1 = (a.has_res && planes > 1) ? (const void*)p.res_lo : r0;
         if (!encode(&I->map_r[0], r0, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
         if (!encode(&I->map_r[1], r1, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
-        if (!encode(&I->map_y[0], p.y_act, 3, edims, estr, ybox, eb)) return HFG_ERR_CUDA;
-        if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 3, edims, estr, ybox, eb)) return HFG_ERR_CUDA;
+        if (ups) {   // output [B][L_in * s][C_out] viewed as [B][L_in][2][N/2]: (half-row parity r, q = half-row / 2)
+            const uint64_t ud[4] = {(uint64_t)N / 2, 2, (uint64_t)g.Lin, (uint64_t)g.B};
+            const uint64_t us[3] = {(uint64_t)N, (uint64_t)N * 2, (uint64_t)g.Lin * N * 2};
+            const uint32_t ub[4] = {(uint32_t)N / 2, 1, 32, 1};
+            if (!encode(&I->map_y[0], p.y_act, 4, ud, us, ub, eb)) return HFG_ERR_CUDA;
+            if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 4, ud, us, ub, eb)) return HFG_ERR_CUDA;
+        } else {
+            if (!encode(&I->map_y[0], p.y_act, 3, edims, estr, ybox, eb)) return HFG_ERR_CUDA;
+            if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 3, edims, estr, ybox, eb)) return HFG_ERR_CUDA;
+        }
     }
     out->impl = I;
     out->mt = a.mt; out->n_a = a.n_a; out->n_w = a.n_w; out->n_e = a.n_e; out->w_resident = a.w_resident;
