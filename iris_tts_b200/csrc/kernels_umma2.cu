@@ -61,6 +61,8 @@ struct K2Args {
     uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
     uint32_t off_w, off_e;
     const float* bias;
+    __nv_bfloat16* y_hi;   // raw output planes (upsampler: the one box that starts before the sequence is stored directly)
+    __nv_bfloat16* y_lo;
 };
 
 __device__ __forceinline__ float inv_lrelu(float p) { return p > 0.f ? p : p * (1.0f / kLreluSlope); }
@@ -371,6 +373,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             hi.z = pack_bf16(v[cidx * 8 + 4], v[cidx * 8 + 5]);
                             hi.w = pack_bf16(v[cidx * 8 + 6], v[cidx * 8 + 7]);
                             sts128(addr[cidx], hi);
+                            const bool direct = a.ups && g == 0 && row0 + q * 32 == 0;   // box would start at q = -1: TMA stores fault there
+                            const size_t doff = direct && row >= 1
+                                ? ((((size_t)b * (a.L - 1) + (size_t)(row - 1)) * 2 + 1) * (size_t)(a.N / 2) + (size_t)(h * 32 + cidx * 8)) : 0;
+                            if (direct && row >= 1) *reinterpret_cast<uint4*>(a.y_hi + doff) = hi;
                             if (planes > 1) {
                                 float fh[8];
                                 unpack8(hi, fh);
@@ -380,6 +386,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                                 lo.z = pack_bf16(v[cidx * 8 + 4] - fh[4], v[cidx * 8 + 5] - fh[5]);
                                 lo.w = pack_bf16(v[cidx * 8 + 6] - fh[6], v[cidx * 8 + 7] - fh[7]);
                                 sts128(addr[cidx] + a.e_plane_bytes, lo);
+                                if (direct && row >= 1) *reinterpret_cast<uint4*>(a.y_lo + doff) = lo;
                             }
                         }
                     }
@@ -389,7 +396,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         mbar_arrive(bar_e_empty + 8 * se);
                     } else if (lane == 0) {
                         for (int pl = 0; pl < planes; ++pl) {
-                            if (a.ups)   // half g of GEMM rows m..m+31 -> (r, q) = (1, m - 1) for g = 0, (0, m) for g = 1
+                            // half g of GEMM rows m..m+31 -> (r, q) = (1, m - 1) for g = 0, (0, m) for g = 1.  TMA stores fault on a
+                            // negative start coordinate (measured), so the one box per item that starts at q = -1 was written
+                            // with plain stores above (31 rows; GEMM row 0's first half lies before the sequence).
+                            if (a.ups && row0 + q * 32 - 1 + g < 0)
+                                continue;
+                            else if (a.ups)
                                 tma_store_4d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, 0, 1 - g, row0 + q * 32 - 1 + g, b);
                             else
                                 tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, g * a.ecols, (row0 + q * 32) >> rshift, b);
@@ -511,6 +523,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     a.has_res = (p.res_hi != nullptr);
     a.paired = (!ups && N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
     a.bias = p.bias;
+    a.y_hi = p.y_act; a.y_lo = p.y_act_lo;
     a.dbg = env_i("HFG_U2_DBG", 0);
     a.reverse = p.reverse;
     a.concat = (planes == 2 && N <= env_i("HFG_U2_CONCAT_MAXN", 32)) ? 1 : 0;   // wider layers stream W: halving MT would double that traffic
