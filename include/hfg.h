@@ -134,6 +134,13 @@ int hfg_profile_get(hfg_engine* e, int i, char* layer, size_t layer_len, char* k
 int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, int32_t L,
                   int32_t pre_lrelu, float* y, int32_t precision);
 
+/* One ResBlock step in isolation (src/iris/hifigan_pretrained.py:66-70), host pointers, reference layout:
+ * y = x + convs2[m](lrelu(convs1[m](lrelu(x)))) for ResBlock n; x, y [B][C][L].  Tensor-core precisions only.
+ * Runs the fused pair kernel where the forward's plan would (C <= 64), the two single-conv launches otherwise;
+ * *fused (optional) reports which. */
+int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int32_t B, int32_t L, float* y,
+                 int32_t precision, int32_t* fused);
+
 /* After hfg_forward(..., HFG_KEEP_TAPS): copy an intermediate activation to
  * host as fp32 [B][C][L] (reference layout).  Names: "conv_pre", "ups.<i>",
  * "resblocks.<3i>" (first ResBlock of each stage), "stage.<i>", "conv_post".

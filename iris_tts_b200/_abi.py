@@ -53,6 +53,7 @@ SIGNATURES = {
     "hfg_profile_get": (c_int, [c_void_p, c_int, c_char_p, c_size_t, c_char_p, c_size_t, POINTER(c_float),
                                 POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "hfg_run_layer": (c_int, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32]),
+    "hfg_run_pair": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "hfg_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_size_t)]),
 }
 

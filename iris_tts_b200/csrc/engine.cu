@@ -65,13 +65,14 @@ struct Layer {
     __nv_bfloat16* d_wb_lo = nullptr;
 };
 
-enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_POST32, S_ACCUM, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP };
+enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_PAIR, S_POST32, S_ACCUM, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP };
 
 struct Step {
     StepKind kind;
     ConvParams cp;
     UmmaLaunch ul;
     Umma2Launch u2;
+    PairLaunch pl;
     MrfArgs mrf;
     // misc operands
     const float* f_in = nullptr;
@@ -463,6 +464,29 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         plan->steps.push_back(std::move(s));
         return HFG_OK;
     };
+    // convs1[m] -> lrelu -> convs2[m] -> + x  (:66-70) as one launch where the fused kernel applies (C <= 64); false otherwise
+    auto pair = [&](const Layer& c1, const Layer& c2, int Lrows, Planes x, Planes y, char const* label) -> bool {
+        if (!real) return false;
+        if (c1.cin_pad != c1.cout_tc || c2.cin_pad != c1.cin_pad || c2.cout_tc != c1.cout_tc || c1.k != c2.k || c2.dil != 1) return false;
+        PairParams p;
+        memset(&p, 0, sizeof p);
+        p.B = B; p.L = Lrows; p.C = c1.cin_pad; p.k = c1.k; p.d = c1.dil; p.npass = npass;
+        p.bias1 = c1.d_bias_tc; p.bias2 = c2.d_bias_tc;
+        p.x_hi = x.hi; p.x_lo = x3 ? x.lo : nullptr;
+        p.w1_hi = c1.d_wb_hi; p.w1_lo = c1.d_wb_lo; p.w2_hi = c2.d_wb_hi; p.w2_lo = c2.d_wb_lo;
+        p.y_hi = y.hi; p.y_lo = x3 ? y.lo : nullptr;
+        p.reverse = snake ? (n_umma2 & 1) : 0;
+        if (!pair_supported(p)) return false;
+        Step s{};
+        if (plan_conv_pair(&s.pl, p, e->sm_count) != HFG_OK) return false;
+        ++n_umma2;
+        Step w2{};
+        work(s, c1, Lrows, x3 ? 4 : 2);
+        work(w2, c2, Lrows, x3 ? 4 : 2);
+        s.kind = S_PAIR; s.label = label; s.flops += w2.flops; s.bytes += w2.bytes;
+        plan->steps.push_back(std::move(s));
+        return true;
+    };
     auto c32 = [&](const Layer& L, int Lin, const float* x, float* y, const float* res, int pre_lrelu, int accumulate, float out_div) {
         Step s{}; s.kind = S_CONV32; s.cp = conv32(L, B, Lin, x, y, res, pre_lrelu, accumulate, out_div);
         work(s, L, Lin, 4);
@@ -520,10 +544,13 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                 const int nd = c.num_dilations[j];
                 for (int m = 0; m < nd; ++m) {
                     const Layer& c1 = layer("resblocks.%d.convs1.%d", n, m);
-                    RET(umma(c1, L, xin, Planes(), nullptr, xt_p));               // :66-67 (+ :68 in the epilogue)
                     const Layer& c2 = layer("resblocks.%d.convs2.%d", n, m);
                     Planes xout = m == nd - 1 ? r_p[j] : pp[m & 1];
-                    RET(umma(c2, L, xt_p, xin, nullptr, xout));                   // :69-70
+                    snprintf(nm, sizeof nm, "resblocks.%d.pair.%d", n, m);
+                    if (!pair(c1, c2, L, xin, xout, nm)) {
+                        RET(umma(c1, L, xin, Planes(), nullptr, xt_p));               // :66-67 (+ :68 in the epilogue)
+                        RET(umma(c2, L, xt_p, xin, nullptr, xout));                   // :69-70
+                    }
                     xin = xout;
                 }
                 snprintf(nm, sizeof nm, "resblocks.%d", n);
@@ -619,6 +646,7 @@ const char* kind_label(StepKind k) {
         case S_CONV32: return "conv_cl_fp32";
         case S_UMMA: return "conv_umma";
         case S_UMMA2: return "conv_umma2";
+        case S_PAIR: return "conv_pair";
         case S_P2RAW: return "planes_to_raw";
         case S_MRF: return "mrf_combine";
         case S_POSTMRF: return "conv_post_mrf";
@@ -649,6 +677,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_CONV32: CK(launch_conv_fp32(s.cp, st)); break;
             case S_UMMA: CK(launch_conv_umma(s.ul, st)); break;
             case S_UMMA2: CK(launch_conv_umma2(s.u2, st)); break;
+            case S_PAIR: CK(launch_conv_pair(s.pl, st)); break;
             case S_P2RAW: CK(launch_planes_to_raw(s.b_in, s.b_in_lo, s.f_out, s.n, s.cpad, s.C, st)); break;
             case S_MRF: CK(launch_mrf_combine(s.mrf, s.n, st)); break;
             case S_POSTMRF: CK(launch_conv_post_mrf(s.mrf, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
@@ -964,6 +993,87 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
         e->launches += 4;
     }
     CK(cudaMemcpyAsync(y, y_cf, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return HFG_OK;
+}
+
+int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int32_t B, int32_t L, float* y, int32_t precision,
+                 int32_t* fused) {
+    if (!e || !x || !y) return fail(HFG_ERR_INVALID, "hfg_run_pair: null argument");
+    if (B <= 0 || L <= 0) return fail(HFG_ERR_INVALID, "hfg_run_pair: B and L must be positive");
+    RET(check_prec(precision));
+    if (precision == HFG_PREC_FP32) return fail(HFG_ERR_UNSUPPORTED, "hfg_run_pair: tensor-core precisions only");
+    if (!e->finalized) return fail(HFG_ERR_STATE, "hfg_run_pair: call hfg_finalize first");
+    char n1[64], n2[64];
+    snprintf(n1, sizeof n1, "resblocks.%d.convs1.%d", resblock, m);
+    snprintf(n2, sizeof n2, "resblocks.%d.convs2.%d", resblock, m);
+    Layer* c1 = find_layer(e, n1);
+    Layer* c2 = find_layer(e, n2);
+    if (!c1 || !c2) return fail(HFG_ERR_INVALID, std::string("unknown layer: ") + n1);
+    CK(cudaSetDevice(e->device));
+    const bool x3 = precision == HFG_PREC_BF16X3;
+    const int C = c1->cin, Cp = c1->cin_pad;
+    const size_t n_raw = (size_t)B * C * L, n_pad = (size_t)B * Cp * L;
+    const size_t need = 2 * n_raw * sizeof(float) + 6 * n_pad * 2 + 16 * 256;
+    if (need > e->scratch_bytes) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->scratch);
+        e->scratch = nullptr; e->scratch_bytes = 0;
+        CK(cudaMalloc(&e->scratch, need));
+        e->scratch_bytes = need;
+    }
+    Bump bump{e->scratch};
+    float* x_cf = bump.take<float>(n_raw);
+    float* y_cl = bump.take<float>(n_raw);
+    __nv_bfloat16* a_hi = bump.take<__nv_bfloat16>(n_pad);
+    __nv_bfloat16* a_lo = bump.take<__nv_bfloat16>(n_pad);
+    __nv_bfloat16* t_hi = bump.take<__nv_bfloat16>(n_pad);
+    __nv_bfloat16* t_lo = bump.take<__nv_bfloat16>(n_pad);
+    __nv_bfloat16* y_hi = bump.take<__nv_bfloat16>(n_pad);
+    __nv_bfloat16* y_lo = bump.take<__nv_bfloat16>(n_pad);
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(x_cf, x, n_raw * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, C, L, Cp, 1, st));
+    PairParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.B = B; pp.L = L; pp.C = Cp; pp.k = c1->k; pp.d = c1->dil; pp.npass = x3 ? 3 : 1;
+    pp.bias1 = c1->d_bias_tc; pp.bias2 = c2->d_bias_tc;
+    pp.x_hi = a_hi; pp.x_lo = x3 ? a_lo : nullptr;
+    pp.w1_hi = c1->d_wb_hi; pp.w1_lo = c1->d_wb_lo; pp.w2_hi = c2->d_wb_hi; pp.w2_lo = c2->d_wb_lo;
+    pp.y_hi = y_hi; pp.y_lo = x3 ? y_lo : nullptr;
+    PairLaunch pl;
+    const bool can_fuse = c1->cin_pad == c1->cout_tc && c1->k == c2->k && c2->dil == 1 && pair_supported(pp) &&
+                          plan_conv_pair(&pl, pp, e->sm_count) == HFG_OK;
+    if (fused) *fused = can_fuse ? 1 : 0;
+    if (can_fuse) {
+        CK(launch_conv_pair(pl, st));
+        e->launches += 1;
+    } else {
+        for (int which = 0; which < 2; ++which) {
+            const Layer* lay = which ? c2 : c1;
+            UmmaConvParams p;
+            memset(&p, 0, sizeof p);
+            p.g = geom_tc(*lay, B, L); p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1;
+            p.bias = lay->d_bias_tc;
+            if (which) { p.res_hi = a_hi; p.res_lo = x3 ? a_lo : nullptr; }
+            p.y_act = which ? y_hi : t_hi; p.y_act_lo = x3 ? (which ? y_lo : t_lo) : nullptr;
+            const __nv_bfloat16* in_hi = which ? t_hi : a_hi;
+            const __nv_bfloat16* in_lo = which ? t_lo : a_lo;
+            Umma2Launch u2;
+            if (umma2_supported(p) && plan_conv_umma2(&u2, p, in_hi, in_lo, lay->d_wb_hi, lay->d_wb_lo, e->sm_count) == HFG_OK) {
+                CK(launch_conv_umma2(u2, st));
+            } else {
+                UmmaLaunch ul;
+                RET(plan_conv_umma(&ul, p, in_hi, in_lo, lay->d_wb_hi, lay->d_wb_lo));
+                CK(launch_conv_umma(ul, st));
+            }
+        }
+        e->launches += 2;
+    }
+    CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, (size_t)B * L, Cp, C, st));
+    CK(launch_transpose_cl_to_cf(y_cl, x_cf, B, C, L, st));
+    e->launches += 3;
+    CK(cudaMemcpyAsync(y, x_cf, n_raw * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return HFG_OK;
 }

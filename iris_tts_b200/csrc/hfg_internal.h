@@ -132,6 +132,29 @@ int plan_conv_umma2(Umma2Launch* L, const UmmaConvParams& p, const __nv_bfloat16
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int sm_count);
 cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s);
 
+// ---- fused ResBlock pair (convs1[m] -> lrelu -> convs2[m] -> + x) for C = 32 / 64 on planes (kernels_pair.cu) ----
+// hifigan_pretrained.py:66-70 as one kernel: the intermediate stays in shared memory, the residual comes from the staged x tile.
+struct PairParams {
+    int B, L, C;          // planes are [B][L][C] bf16, C = 32 or 64 (already channel-padded)
+    int k, d;             // c1: k taps, dilation d ; c2: k taps, dilation 1 ; both 'same'-padded
+    int npass;            // 1: bf16 ; 3: bf16x3
+    int reverse;
+    const float* bias1;
+    const float* bias2;
+    const __nv_bfloat16 *x_hi, *x_lo;
+    const __nv_bfloat16 *w1_hi, *w1_lo, *w2_hi, *w2_lo;   // [k*C][C] K-major
+    __nv_bfloat16 *y_hi, *y_lo;
+};
+struct PairLaunch {
+    struct Impl;
+    std::shared_ptr<Impl> impl;
+    int mt = 0, n_x = 0, n_t = 0, n_o = 0, grid = 0;
+    size_t smem = 0;
+};
+bool pair_supported(const PairParams& p);
+int plan_conv_pair(PairLaunch* L, const PairParams& p, int sm_count);
+cudaError_t launch_conv_pair(const PairLaunch& L, cudaStream_t s);
+
 // raw fp32 [rows][C] = inverse-lrelu(hi (+ lo)) of planes [rows][C_tc], C <= C_tc   (taps; drops padding channels)
 cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t rows, int C_tc, int C,
                                  cudaStream_t s);

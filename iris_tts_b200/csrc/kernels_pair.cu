@@ -1,0 +1,634 @@
+// conv_pair: one ResBlock (convs1[m], convs2[m]) pair as ONE persistent tcgen05 kernel for the narrow stages (C <= 64).
+//
+//   xt = lrelu(x); xt = c1(xt); xt = lrelu(xt); xt = c2(xt); x = xt + x      src/iris/hifigan_pretrained.py:66-70
+//
+// The unfused plan (kernels_umma2.cu) moves five activation streams through HBM per pair (c1: read x, write t; c2: read t,
+// read x, write out) and the C <= 64 layers are bound by exactly that (and by the shared-memory operand fetch of small-N
+// MMAs), not by the tensor pipe.  Here the intermediate t never leaves the SM:
+//
+//   x halo tile (TMA, OOB rows = 0)  --c1 taps: row-shifted UMMA descriptors-->  acc1 (TMEM)
+//   acc1 --epilogue 1: + b1, lrelu, rows outside [0, L) := 0 (c2's zero padding), bf16 plane(s)-->  t tile (shared, swizzled K-major)
+//   t tile  --c2 taps-->  acc2 (TMEM)
+//   acc2 --epilogue 2: + b2 + inverse-lrelu(x rows of the SAME x tile), lrelu, bf16 plane(s)-->  staging -> TMA store
+//
+// Two streams (x in, out) instead of five.  A tile computes R = 128*MT conv rows of both convs; the last k-1 rows of c2 see
+// t rows this tile did not compute and are dropped: V = R - (k-1) valid output rows per tile (k <= 11: >= 92 % at MT = 1).
+//
+// c1 and c2 have separate issuer warps ordered only by barriers: c1 of tile i+1 (and i+2) runs while epilogue 1 of tile i+1
+// and epilogue 2 of tile i work on their own warps, so the tensor pipe stays busy.  acc1 / acc2 are double-buffered in TMEM (4 * MT * N <= 512 columns).
+//
+// Arithmetic is the unfused plan's: same bf16 (hi[, lo]) rounding of t, same fp32 accumulation per output row with a fixed
+// (tap, K-slice, pass) order that does not depend on the tile a row falls in, nor on B or L.
+//
+// Warps: 0 = TMA producer (resident weights of both convs, x ring), 2 = TMEM allocator, 3 = barrier init,
+//        4-7 = epilogue 1, 8..8+2*MT-1 = MMA issuers (one per conv and 128-row subtile), 12-15 = epilogue 2.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "hfg_internal.h"
+#include "umma_ptx.cuh"
+
+namespace hfg {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kThreads = 512;
+constexpr int kMaxX = 8;
+constexpr uint32_t kSmemMax = 227u * 1024u - 2048u;   // dynamic smem; barriers / bias (static, < 2 KB) live outside
+
+struct PairArgs {
+    int B, L, N;                 // N = C = 32 or 64 (operand rows of 64 / 128 bytes)
+    int k, d, h1, h2;            // c1: k taps, dilation d, halo h1 = d(k-1)/2 ; c2: k taps, dilation 1, halo h2 = (k-1)/2
+    int planes, mt, R, V;        // R = 128*mt conv rows per tile, V = R - (k-1) valid output rows
+    int tiles_per_item, total_tiles;
+    int x_rows, x_box_rows, x_pieces;
+    int n_x, n_t, n_o;
+    int concat, acc_n, paired, reverse;
+    int dbg;                     // HFG_PAIR_DBG (timing experiments only): 1 = epilogue 2 idle, 2 = no MMAs, 3 = epilogue 1 idle, 4 = no TMA stores
+    uint32_t x_plane_bytes, t_plane_bytes, w_plane_bytes, o_plane_bytes;
+    uint32_t off_w, off_t, off_o;
+    const float* bias1;
+    const float* bias2;
+};
+
+__device__ __forceinline__ float inv_lrelu(float p) { return p > 0.f ? p : p * (1.0f / kLreluSlope); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// hi (and lo = v - hi) planes of 8 consecutive channels -> 16-byte chunks
+template <int kPlanes>
+__device__ __forceinline__ void store_planes8(const float* v, uint32_t addr, uint32_t plane_bytes) {
+    uint4 hi;
+    hi.x = pack_bf16(v[0], v[1]); hi.y = pack_bf16(v[2], v[3]); hi.z = pack_bf16(v[4], v[5]); hi.w = pack_bf16(v[6], v[7]);
+    sts128(addr, hi);
+    if (kPlanes > 1) {
+        float fh[8];
+        unpack8(hi, fh);
+        uint4 lo;
+        lo.x = pack_bf16(v[0] - fh[0], v[1] - fh[1]); lo.y = pack_bf16(v[2] - fh[2], v[3] - fh[3]);
+        lo.z = pack_bf16(v[4] - fh[4], v[5] - fh[5]); lo.w = pack_bf16(v[6] - fh[6], v[7] - fh[7]);
+        sts128(addr + plane_bytes, lo);
+    }
+}
+
+// 16-byte chunk XOR of a row inside a swizzled tile whose base is 1024-byte aligned
+__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t row_bytes) { return row_bytes == 128 ? (row & 7u) : ((row >> 1) & 3u); }
+
+// All taps of one 128-row subtile of one conv.  The loop is warp-uniform (operands live in uniform registers); only the elected
+// lane issues.  KS = K=16 slices per tap, NP = MMA passes per tap: 1 bf16 | 3 bf16x3 (hi,hi)(lo,hi)(hi,lo) | 2 concat (hi,[hi;lo])(lo,hi).
+// Per tap the descriptors advance by one add each; everything else is loop-invariant (the generic loop spent ~19 instructions
+// and ~100 cycles per MMA on rebuilding them, twice the tensor pipe's own time for N <= 64).
+template <int KS, int NP>
+__device__ __forceinline__ void issue_taps(bool leader, int k, uint32_t d0, uint32_t a_lo, uint32_t w_lo, uint32_t a_tap, uint32_t w_tap,
+                                           uint32_t a_pl, uint32_t w_pl, uint32_t dhi, uint32_t id0, uint32_t id1) {
+#pragma unroll 1
+    for (int j = 0; j < k; ++j) {
+        if (leader) {
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+                const uint32_t aa = a_lo + (ps == 1 ? a_pl : 0u);
+                const uint32_t ww = w_lo + (ps == 2 ? w_pl : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    umma_bf16_lh(d0, aa + 2u * ks, ww + 2u * ks, dhi, ps == 0 ? id0 : id1, (ps | ks) ? 1u : (uint32_t)(j != 0));
+            }
+        }
+        a_lo += a_tap;
+        w_lo += w_tap;
+    }
+}
+
+template <int kPlanes>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                 const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                 const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                 const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
+                 const __grid_constant__ CUtensorMap map_yt_hi, const __grid_constant__ CUtensorMap map_yt_lo, const PairArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxX + 17];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float bias_s[2][64];
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler too: role values stay in uniform registers
+    const int lane = threadIdx.x & 31;
+    constexpr int planes = kPlanes;
+    constexpr int npass = kPlanes == 2 ? 3 : 1;
+    constexpr int CW = kPlanes == 2 ? 16 : 32;    // epilogue column chunk (registers: two planes double the live state)
+    const uint32_t row_bytes = (uint32_t)a.N * 2u;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t x_stage = a.x_plane_bytes * planes;
+    const uint32_t t_stage = a.t_plane_bytes * planes;
+    const uint32_t w_stage = a.w_plane_bytes * planes;     // one tap of one conv
+    const uint32_t o_slot = a.o_plane_bytes * planes;      // one epilogue-2 warp's 32-row staging box
+    const uint32_t smem_x = smem_base;
+    const uint32_t smem_w = smem_base + a.off_w;
+    const uint32_t smem_t = smem_base + a.off_t;
+    const uint32_t smem_o = smem_base + a.off_o;
+
+    uint32_t bp = smem_u32(&bars[0]);
+    const uint32_t bar_x_full = bp;   bp += 8 * kMaxX;
+    const uint32_t bar_x_empty = bp;  bp += 8 * kMaxX;
+    const uint32_t bar_a1_full = bp;  bp += 16;
+    const uint32_t bar_a1_empty = bp; bp += 16;
+    const uint32_t bar_t_full = bp;   bp += 16;
+    const uint32_t bar_t_empty = bp;  bp += 16;
+    const uint32_t bar_a2_full = bp;  bp += 16;
+    const uint32_t bar_a2_empty = bp; bp += 16;
+    const uint32_t bar_w = bp;
+
+    if (threadIdx.x < 2 * a.N) {
+        const int which = threadIdx.x / a.N, i = threadIdx.x % a.N;
+        bias_s[which][i] = which ? a.bias2[i] : a.bias1[i];
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w1_hi); prefetch_tmap(&map_w2_hi); prefetch_tmap(&map_y_hi); prefetch_tmap(&map_yt_hi);
+        if (planes > 1) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w1_lo); prefetch_tmap(&map_w2_lo); prefetch_tmap(&map_y_lo); prefetch_tmap(&map_yt_lo); }
+    }
+    if (warp == 3 && lane == 0) {
+        const uint32_t nmma = (uint32_t)a.mt;
+        for (int i = 0; i < a.n_x; ++i) { mbar_init(bar_x_full + 8 * i, 1); mbar_init(bar_x_empty + 8 * i, nmma + 4); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_a1_full + 8 * i, nmma); mbar_init(bar_a1_empty + 8 * i, 4);
+            mbar_init(bar_t_full + 8 * i, 4);     mbar_init(bar_t_empty + 8 * i, nmma);
+            mbar_init(bar_a2_full + 8 * i, nmma); mbar_init(bar_a2_empty + 8 * i, 4);
+        }
+        mbar_init(bar_w, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(&tmem_base_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_slot, 0);
+    const int acc_cols = a.mt * a.acc_n;                  // columns of one accumulator buffer; acc1[b] at b*acc_cols, acc2[b] at (2+b)*acc_cols
+    const int n_my = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===== producer: resident weights of both convs, then the x ring =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_w, (uint32_t)(2 * a.k * planes) * (uint32_t)a.N * row_bytes);
+            for (int cv = 0; cv < 2; ++cv)
+                for (int j = 0; j < a.k; ++j)
+                    for (int pl = 0; pl < planes; ++pl)
+                        tma_load_2d(smem_w + (uint32_t)(cv * a.k + j) * w_stage + pl * a.w_plane_bytes,
+                                    cv ? (pl ? &map_w2_lo : &map_w2_hi) : (pl ? &map_w1_lo : &map_w1_hi), bar_w, 0, j * a.N);
+            int sx = 0;
+            uint32_t px = 0;
+            pdl_wait();   // activations of the previous kernel are complete and visible from here on
+            for (int it = 0; it < n_my; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+                const int b = tl / a.tiles_per_item;
+                const int o0 = (tl - b * a.tiles_per_item) * a.V;
+                const int xr0 = o0 - a.h2 - a.h1;
+                mbar_wait(bar_x_empty + 8 * sx, px ^ 1u);
+                mbar_expect_tx(bar_x_full + 8 * sx, (uint32_t)a.x_rows * row_bytes * planes);
+                for (int pl = 0; pl < planes; ++pl)
+                    for (int pc = 0; pc < a.x_pieces; ++pc)
+                        tma_load_3d(smem_x + sx * x_stage + pl * a.x_plane_bytes + pc * a.x_box_rows * row_bytes,
+                                    pl ? &map_x_lo : &map_x_hi, bar_x_full + 8 * sx, 0, xr0 + pc * a.x_box_rows, b);
+                if (++sx == a.n_x) { sx = 0; px ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 8 && warp < 12) {
+        // ===== MMA issuers: warp 8 + cv*MT + ms issues conv cv (0: c1, 1: c2) of subtile ms =====
+        // One thread cannot issue small-N MMAs at the tensor pipe's rate, and c1 of tile i+1 must overlap the
+        // epilogues of tile i: c1 and c2 have their own issuers, ordered only by the barriers.
+        const int role = warp - 8;
+        const int cv = role / a.mt, ms = role % a.mt;
+        if (cv < 2) {
+            const bool leader = elect_one();
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * a.N) >> 3) << 17) | ((128u >> 4) << 24);
+            const bool concat = a.concat != 0;
+            const uint32_t id0 = concat ? idesc2 : idesc;
+            const uint32_t dhi = desc_hi(row_bytes);
+            const uint32_t sub_step = (128u * row_bytes) >> 4;
+            const uint32_t a_pl = (cv ? a.t_plane_bytes : a.x_plane_bytes) >> 4, w_pl = a.w_plane_bytes >> 4;
+            const bool k4 = a.N == 64;
+            const uint32_t a_tap = (uint32_t)(cv ? 1 : a.d) * (row_bytes >> 4);
+            const uint32_t w_tap = w_stage >> 4;
+            const uint32_t w_lo = desc_lo(smem_w + (uint32_t)(cv * a.k) * w_stage);
+            const uint32_t a_stage = cv ? t_stage : x_stage;
+            const uint32_t a_ring = desc_lo(cv ? smem_t : smem_x) + (uint32_t)ms * sub_step;
+            const uint32_t d_base = tmem_base + (uint32_t)(cv * 2 * acc_cols + ms * a.acc_n);
+            const int k = a.k, n_t = a.n_t, n_x = a.n_x;
+            const bool dbg_nomma = a.dbg == 2;
+            mbar_wait(bar_w, 0);
+            int sx = 0;
+            uint32_t px = 0;
+            for (int it = 0; it < n_my; ++it) {
+                const int buf = it & 1;
+                const uint32_t pb = ((uint32_t)it >> 1) & 1u;
+                int slot;
+                if (cv == 0) {
+                    slot = sx;
+                    mbar_wait(bar_a1_empty + 8 * buf, pb ^ 1u);
+                    mbar_wait(bar_x_full + 8 * sx, px);
+                } else {
+                    slot = n_t == 2 ? buf : 0;
+                    const uint32_t pt = n_t == 2 ? pb : ((uint32_t)it & 1u);
+                    mbar_wait(bar_a2_empty + 8 * buf, pb ^ 1u);
+                    mbar_wait(bar_t_full + 8 * slot, pt);
+                }
+                tc_fence_after();
+                const uint32_t d0 = d_base + (uint32_t)(buf * acc_cols);
+                const uint32_t a_lo = a_ring + (((uint32_t)slot * a_stage) >> 4);
+                const bool go = leader && !dbg_nomma;
+                if (kPlanes == 1) {
+                    if (k4) issue_taps<4, 1>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
+                    else issue_taps<2, 1>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
+                } else if (concat) {
+                    if (k4) issue_taps<4, 2>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
+                    else issue_taps<2, 2>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
+                } else {
+                    if (k4) issue_taps<4, 3>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
+                    else issue_taps<2, 3>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
+                }
+                if (leader) {
+                    if (cv == 0) { umma_commit(bar_a1_full + 8 * buf); umma_commit(bar_x_empty + 8 * sx); }
+                    else { umma_commit(bar_a2_full + 8 * buf); umma_commit(bar_t_empty + 8 * slot); }
+                }
+                if (++sx == n_x) { sx = 0; px ^= 1u; }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue 1: acc1 -> t tile (activated planes of c1's output, zero outside the sequence) =====
+        const int q = warp & 3;
+        const int nch = a.N / CW;
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+            const int b = tl / a.tiles_per_item;
+            const int g0 = (tl - b * a.tiles_per_item) * a.V - a.h2;      // sequence row of t tile row 0
+            const int buf = it & 1;
+            const int st = a.n_t == 2 ? (it & 1) : 0;
+            const uint32_t pt = a.n_t == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
+            mbar_wait(bar_a1_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
+            mbar_wait(bar_t_empty + 8 * st, pt ^ 1u);
+            tc_fence_after();
+            const uint32_t t_slot = smem_t + st * t_stage;
+            for (int ms = 0; ms < (a.dbg == 3 ? 0 : a.mt); ++ms) {
+                const uint32_t row_t = (uint32_t)(ms * 128 + q * 32 + lane);
+                const int g = g0 + (int)row_t;
+                const bool inside = g >= 0 && g < a.L;
+                const uint32_t dst = t_slot + row_t * row_bytes;
+                const uint32_t sx = swz(row_t, row_bytes);
+                for (int h = 0; h < nch; ++h) {
+                    uint32_t r[CW];
+                    const int col = h * CW;
+                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + ms * a.acc_n + col);
+                    tmem_ld<CW>(tcol, r);
+                    tmem_wait_ld();
+                    float v[CW];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) + bias_s[0][col + i];
+                    if (kPlanes == 2 && a.concat) {   // second half of the concatenated accumulator: A_hi x W_lo
+                        tmem_ld<CW>(tcol + (uint32_t)a.N, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < CW; ++i) v[i] += __uint_as_float(r[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = inside ? lrelu(v[i]) : 0.f;
+#pragma unroll
+                    for (int c = 0; c < CW / 8; ++c)
+                        store_planes8<kPlanes>(&v[c * 8], dst + ((((uint32_t)(h * (CW / 8) + c)) ^ sx) << 4), a.t_plane_bytes);
+                }
+            }
+            tc_fence_before();      // this warp has read the last of acc1[buf]
+            fence_proxy_async();    // t rows written through the generic proxy are read by tcgen05.mma (async proxy)
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_a1_empty + 8 * buf); mbar_arrive(bar_t_full + 8 * st); }
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue 2: acc2 + b2 + x (inverse lrelu of the x tile rows) -> activated planes -> TMA store =====
+        const int q = warp & 3;
+        const int nch = a.N / CW;
+        // staging box of this warp: 32 rows; C = 32 paired: two 64-byte time rows form one 128-byte row (SWIZZLE_128B)
+        const uint32_t orow_bytes = a.paired ? 128u : row_bytes;
+        const uint32_t o_row_off = a.paired ? (uint32_t)(lane >> 1) * 128u : (uint32_t)lane * row_bytes;
+        const uint32_t o_chunk0 = a.paired ? (uint32_t)(lane & 1) * 4u : 0u;
+        const uint32_t o_sx = a.paired ? (uint32_t)((lane >> 1) & 7) : swz((uint32_t)lane, orow_bytes);
+        const int rshift = a.paired ? 1 : 0;
+        pdl_wait();                                  // before the first global write (WAR against the previous kernel's reads)
+        int sx = 0, so = 0;
+        uint32_t px = 0;
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+            const int b = tl / a.tiles_per_item;
+            const int o0 = (tl - b * a.tiles_per_item) * a.V;
+            const int buf = it & 1;
+            mbar_wait(bar_a2_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
+            mbar_wait(bar_x_full + 8 * sx, px);      // completed long ago (c1 consumed it); orders this thread's reads after the TMA writes
+            tc_fence_after();
+            const uint32_t x_slot = smem_x + sx * x_stage;
+            for (int ms = 0; ms < (a.dbg == 1 ? 0 : a.mt); ++ms) {
+                const int rs = ms * 128 + q * 32;                    // first tile row of this warp's box
+                int nvalid = min(32, a.V - rs);
+                if (o0 + rs >= a.L) nvalid = 0;
+                const uint32_t row_x = (uint32_t)(rs + lane + a.h1 + a.h2);
+                const uint32_t xsrc = x_slot + row_x * row_bytes;
+                const uint32_t xsw = swz(row_x, row_bytes);
+                const uint32_t slot = smem_o + (uint32_t)(q * a.n_o + so) * o_slot;
+                if (lane == 0) { if (a.n_o == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the store that last used this slot has read it
+                __syncwarp();
+                for (int h = 0; h < nch; ++h) {
+                    uint32_t r[CW];
+                    const int col = h * CW;
+                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + buf) * acc_cols + ms * a.acc_n + col);
+                    tmem_ld<CW>(tcol, r);
+                    float res[CW];
+#pragma unroll
+                    for (int c = 0; c < CW / 8; ++c) {
+                        const uint32_t xa = xsrc + ((((uint32_t)(h * (CW / 8) + c)) ^ xsw) << 4);
+                        float f[8];
+                        unpack8(lds128(xa), f);
+                        if (planes > 1) {
+                            float fl[8];
+                            unpack8(lds128(xa + a.x_plane_bytes), fl);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] += fl[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) res[c * 8 + i] = inv_lrelu(f[i]);
+                    }
+                    tmem_wait_ld();
+                    float v[CW];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) + bias_s[1][col + i];
+                    if (kPlanes == 2 && a.concat) {
+                        tmem_ld<CW>(tcol + (uint32_t)a.N, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < CW; ++i) v[i] += __uint_as_float(r[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = lrelu(v[i] + res[i]);
+#pragma unroll
+                    for (int c = 0; c < CW / 8; ++c)
+                        store_planes8<kPlanes>(&v[c * 8], slot + o_row_off + (((o_chunk0 + (uint32_t)(h * (CW / 8) + c)) ^ o_sx) << 4), a.o_plane_bytes);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (nvalid > 0 && a.dbg != 4) {
+                        for (int pl = 0; pl < planes; ++pl) {
+                            const CUtensorMap* m = nvalid == 32 ? (pl ? &map_y_lo : &map_y_hi) : (pl ? &map_yt_lo : &map_yt_hi);
+                            tma_store_3d(m, slot + pl * a.o_plane_bytes, 0, (o0 + rs) >> rshift, b);
+                        }
+                    }
+                    bulk_commit();
+                }
+                if (++so == a.n_o) so = 0;
+            }
+            tc_fence_before();   // this warp has read the last of acc2[buf] and of the x slot
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_a2_empty + 8 * buf); mbar_arrive(bar_x_empty + 8 * sx); }
+            if (++sx == a.n_x) { sx = 0; px ^= 1u; }
+        }
+        if (lane == 0) bulk_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn pair_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+bool pair_encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                 uint32_t inner_bytes) {
+    EncodeTiledFn fn = pair_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+    const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (pair) failed (%d) rank %d dims %llu,%llu box %u,%u", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        set_error(buf);
+        return false;
+    }
+    return true;
+}
+
+int penv(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+uint32_t rup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct PairLaunch::Impl {
+    PairArgs a;
+    alignas(64) CUtensorMap map_x[2], map_w1[2], map_w2[2], map_y[2], map_yt[2];
+    int grid;
+    size_t smem;
+};
+
+bool pair_supported(const PairParams& p) {
+    if (penv("HFG_PAIR", 1) == 0) return false;
+    if (p.C != 32 && p.C != 64) return false;
+    if (p.k < 1 || p.k > 15 || p.k % 2 == 0 || p.d < 1) return false;
+    if (p.npass != 1 && p.npass != 3) return false;
+    const int maxc = penv(p.npass == 3 ? "HFG_PAIR_MAXC_X3" : "HFG_PAIR_MAXC", 64);
+    const int maxk = penv(p.npass == 3 ? "HFG_PAIR_MAXK_X3" : "HFG_PAIR_MAXK", 15);
+    if (p.C > maxc || p.k > maxk) return false;
+    return true;
+}
+
+int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
+    out->impl.reset();
+    if (!pair_supported(p)) return HFG_ERR_UNSUPPORTED;
+    std::shared_ptr<PairLaunch::Impl> I(new PairLaunch::Impl());
+    PairArgs& a = I->a;
+    memset(&a, 0, sizeof a);
+    const int planes = p.npass > 1 ? 2 : 1;
+    const int N = p.C;
+    const uint32_t row_bytes = (uint32_t)N * 2u;
+    a.B = p.B; a.L = p.L; a.N = N; a.k = p.k; a.d = p.d;
+    a.h1 = p.d * (p.k - 1) / 2; a.h2 = (p.k - 1) / 2;
+    a.planes = planes;
+    a.concat = (planes == 2 && N == 32) ? 1 : 0;
+    a.acc_n = a.concat ? 2 * N : N;
+    a.paired = (N == 32 && p.L % 2 == 0 && penv("HFG_PAIR_PAIRED", 1)) ? 1 : 0;
+    a.reverse = p.reverse;
+    a.dbg = penv("HFG_PAIR_DBG", 0);
+    a.bias1 = p.bias1; a.bias2 = p.bias2;
+    a.w_plane_bytes = rup((uint32_t)N * row_bytes, 1024);
+    if (a.concat && a.w_plane_bytes != (uint32_t)N * row_bytes) return HFG_ERR_UNSUPPORTED;
+    a.o_plane_bytes = 32u * row_bytes;
+    const uint32_t w_all = (uint32_t)(2 * p.k) * a.w_plane_bytes * planes;
+    const uint32_t budget = kSmemMax - 1024;   // alignment slack
+
+    // Choose (MT, x ring depth, t buffers, staging slots per warp): cycles per valid output row of a tile interval, the
+    // largest of tensor time (measured small-N MMA floors), HBM time and epilogue issue time, inflated when the x ring is
+    // too shallow to cover the fetch latency (x(i) stays live until epilogue 2 of tile i, i.e. for about two intervals).
+    auto floor_clk = [](double n) { return std::max(128.0 * n / 256.0, (4096.0 + 32.0 * n) / 128.0); };
+    const double step_clk = a.concat ? floor_clk(2.0 * N) + floor_clk(N) : p.npass * floor_clk(N);
+    const int ksteps = N / 16;
+    const int f_mt = penv("HFG_PAIR_MT", 0), f_nx = penv("HFG_PAIR_NX", 0), f_nt = penv("HFG_PAIR_NT", 0), f_no = penv("HFG_PAIR_NO", 0);
+    bool ok = false;
+    double best = 1e30;
+    for (int mt = 2; mt >= 1; --mt) {
+        if (f_mt && mt != f_mt) continue;
+        if (4 * mt * a.acc_n > 512) continue;
+        const int R = 128 * mt, V = R - (p.k - 1);
+        if (V < 64) continue;
+        const int rows_need = R + 2 * a.h1;
+        const int pieces = (rows_need + 255) / 256;
+        const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
+        const uint32_t x_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
+        const uint32_t t_plane = rup((uint32_t)((R + 2 * a.h2 + 7) / 8 * 8) * row_bytes, 1024);
+        const double t_mma = 2.0 * mt * p.k * ksteps * step_clk;
+        const double t_hbm = ((double)rows_need + V) * row_bytes * planes / 20.0;
+        const double t_epi = (double)mt * (N / 32) * (planes > 1 ? 1100.0 : 600.0);   // both epilogues share an SM sub-partition
+        const double t_int = std::max({t_mma, t_hbm, t_epi}) + 300.0;
+        for (int n_t = 2; n_t >= 1; --n_t) {
+            if (f_nt && n_t != f_nt) continue;
+            for (int n_o = 2; n_o >= 1; --n_o) {
+                if (f_no && n_o != f_no) continue;
+                const uint32_t fixed = w_all + (uint32_t)n_t * t_plane * planes + 4u * n_o * a.o_plane_bytes * planes;
+                if (fixed + 3 * x_plane * planes > budget) continue;
+                const int n_x_max = (int)std::min<uint32_t>((budget - fixed) / (x_plane * planes), (uint32_t)kMaxX);
+                for (int n_x = n_x_max; n_x >= 3; --n_x) {
+                    if (f_nx && n_x != f_nx) continue;
+                    const double f_x = std::min(1.0, (n_x - 2) * t_int / 3500.0);
+                    const long tiles = (long)((p.L + V - 1) / V) * p.B;
+                    const long waves = (tiles + sm_count - 1) / std::max(1, sm_count);
+                    const double fill = (double)tiles / (double)(waves * std::max(1, sm_count));
+                    const double cost = t_int / f_x / V / fill * (n_t == 1 ? 1.04 : 1.0) * (n_o == 1 ? 1.03 : 1.0);
+                    if (cost < best - 1e-9) {
+                        best = cost; ok = true;
+                        a.mt = mt; a.R = R; a.V = V;
+                        a.x_rows = pieces * box_rows; a.x_box_rows = box_rows; a.x_pieces = pieces;
+                        a.x_plane_bytes = x_plane; a.t_plane_bytes = t_plane;
+                        a.n_x = n_x; a.n_t = n_t; a.n_o = n_o;
+                        a.off_w = (uint32_t)n_x * x_plane * planes;
+                        a.off_t = a.off_w + w_all;
+                        a.off_o = a.off_t + (uint32_t)n_t * t_plane * planes;
+                        // > half an SM, so exactly one CTA (512 TMEM columns) lives on an SM
+                        I->smem = std::max<size_t>((size_t)a.off_o + 4u * n_o * a.o_plane_bytes * planes + 1024, 120u * 1024u);
+                    }
+                }
+            }
+        }
+    }
+    if (!ok) return HFG_ERR_UNSUPPORTED;
+    if (penv("HFG_PAIR_VERBOSE", 0))
+        fprintf(stderr, "pair plan C=%d k=%d d=%d planes=%d: mt=%d V=%d n_x=%d n_t=%d n_o=%d x_rows=%d smem=%zu cost=%.2f\n", N, p.k, p.d,
+                planes, a.mt, a.V, a.n_x, a.n_t, a.n_o, a.x_rows, I->smem, best);
+    a.tiles_per_item = (p.L + a.V - 1) / a.V;
+    a.total_tiles = a.tiles_per_item * p.B;
+    I->grid = std::min(a.total_tiles, std::max(1, sm_count));
+
+    const uint64_t dims3[3] = {(uint64_t)N, (uint64_t)p.L, (uint64_t)p.B};
+    const uint64_t str3[2] = {(uint64_t)N * 2, (uint64_t)p.L * N * 2};
+    {
+        const uint32_t box[3] = {(uint32_t)N, (uint32_t)a.x_box_rows, 1};
+        if (!pair_encode(&I->map_x[0], p.x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_x[1], planes > 1 ? p.x_lo : p.x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)N, (uint64_t)p.k * N};
+        const uint64_t str[1] = {(uint64_t)N * 2};
+        const uint32_t box[2] = {(uint32_t)N, (uint32_t)N};
+        if (!pair_encode(&I->map_w1[0], p.w1_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_w1[1], planes > 1 ? p.w1_lo : p.w1_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_w2[0], p.w2_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_w2[1], planes > 1 ? p.w2_lo : p.w2_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
+    }
+    {
+        const int pr = a.paired ? 2 : 1;
+        const int tail = 32 - (p.k - 1);   // rows of the one partial box per tile (k-1 is even, so paired boxes stay whole)
+        const uint64_t ydims[3] = {(uint64_t)N * pr, (uint64_t)p.L / pr, (uint64_t)p.B};
+        const uint64_t ystr[2] = {(uint64_t)N * pr * 2, (uint64_t)p.L * N * 2};
+        const uint32_t ybox[3] = {(uint32_t)N * pr, (uint32_t)(32 / pr), 1};
+        const uint32_t tbox[3] = {(uint32_t)N * pr, (uint32_t)(tail / pr), 1};
+        const uint32_t yb = (uint32_t)N * pr * 2u;
+        if (!pair_encode(&I->map_y[0], p.y_hi, 3, ydims, ystr, ybox, yb)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_y[1], planes > 1 ? p.y_lo : p.y_hi, 3, ydims, ystr, ybox, yb)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_yt[0], p.y_hi, 3, ydims, ystr, tbox, yb)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_yt[1], planes > 1 ? p.y_lo : p.y_hi, 3, ydims, ystr, tbox, yb)) return HFG_ERR_CUDA;
+    }
+    out->impl = I;
+    out->mt = a.mt; out->n_x = a.n_x; out->n_t = a.n_t; out->n_o = a.n_o; out->smem = I->smem; out->grid = I->grid;
+    return HFG_OK;
+}
+
+cudaError_t launch_conv_pair(const PairLaunch& L, cudaStream_t s) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev % 64]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e != cudaSuccess) return e;
+        configured[dev % 64] = true;
+    }
+    const PairLaunch::Impl& I = *L.impl;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(I.grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = I.smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const int use_pdl = penv("HFG_PDL", 1);
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t e;
+    if (I.a.planes == 2)
+        e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<2>, I.map_x[0], I.map_x[1], I.map_w1[0], I.map_w1[1], I.map_w2[0], I.map_w2[1],
+                               I.map_y[0], I.map_y[1], I.map_yt[0], I.map_yt[1], I.a);
+    else
+        e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<1>, I.map_x[0], I.map_x[1], I.map_w1[0], I.map_w1[1], I.map_w2[0], I.map_w2[1],
+                               I.map_y[0], I.map_y[1], I.map_yt[0], I.map_yt[1], I.a);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace hfg

@@ -260,6 +260,18 @@ class Engine:
                                            _abi.PRECISIONS[precision]))
         return y
 
+    def run_pair(self, resblock: int, m: int, x: np.ndarray, precision: str = "bf16x3"):
+        """One ResBlock step x + c2(lrelu(c1(lrelu(x)))) (hifigan_pretrained.py:66-70) in isolation; returns (y, fused)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 3:
+            raise ValueError(f"x must be [B, C, L], got {x.shape}")
+        B, _, L = x.shape
+        y = np.empty_like(x)
+        fused = ctypes.c_int32(0)
+        _abi.check(self._lib.hfg_run_pair(self._h, resblock, m, x.ctypes.data, B, L, y.ctypes.data, _abi.PRECISIONS[precision],
+                                          ctypes.byref(fused)))
+        return y, bool(fused.value)
+
     def get_tap(self, name: str, shape: Optional[Sequence[int]] = None) -> np.ndarray:
         n = ctypes.c_size_t(0)
         _abi.check(self._lib.hfg_get_tap(self._h, name.encode(), None, ctypes.byref(n)))

@@ -133,6 +133,79 @@ def test_layer_edges_one_row_and_tile_boundaries(mode):
 
 
 # ---------------------------------------------------------------------------
+# fused ResBlock step (hifigan_pretrained.py:66-70): convs1[m] -> lrelu -> convs2[m] -> + x in one kernel (C <= 64)
+# ---------------------------------------------------------------------------
+
+def _pair_ref(w, n, m, k, d, x):
+    t = F.conv1d(F.leaky_relu(x.double(), 0.1), w[f"resblocks.{n}.convs1.{m}.weight"].double(), w[f"resblocks.{n}.convs1.{m}.bias"].double(),
+                 dilation=d, padding=O.get_padding(k, d))
+    t = F.conv1d(F.leaky_relu(t, 0.1), w[f"resblocks.{n}.convs2.{m}.weight"].double(), w[f"resblocks.{n}.convs2.{m}.bias"].double(),
+                 padding=O.get_padding(k, 1))
+    return (t + x.double()).numpy()
+
+
+# V1: resblocks 6-8 are C = 64 (k = 3, 7, 11), 9-11 are C = 32; m indexes the dilation (1, 3, 5)
+V1_PAIRS = [(6, 0), (6, 2), (7, 1), (7, 2), (8, 1), (9, 0), (9, 2), (10, 1), (11, 0), (11, 2), (4, 1)]
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("n,m", V1_PAIRS)
+def test_v1_resblock_pair_parity(n, m, mode):
+    eng, sd = _engine("v1")
+    w = O.folded_weights(sd)
+    C = 512 >> (n // 3 + 1)
+    k, d = (3, 7, 11)[n % 3], (1, 3, 5)[m]
+    torch.manual_seed(100 * n + m)
+    x = torch.randn(2, C, 777)                     # ragged: not a multiple of any tile height
+    ref = _pair_ref(w, n, m, k, d, x)
+    y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
+    if C == 32 or (C == 64 and mode == "bf16" and k <= 7):
+        assert fused, "the plan is expected to fuse this pair"
+    err = np.abs(y - ref).max()
+    tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
+    assert err <= tol, f"resblocks.{n} pair {m} {mode} fused={fused}: max|err| {err:.3e} (ref max {np.abs(ref).max():.3f})"
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_resblock_pair_edges_and_equals_unfused(mode):
+    """Tile edges of the fused kernel (V = 128*MT - (k-1) valid rows per tile), the shortest inputs, odd lengths (C = 32 falls back
+    from paired 128-byte boxes to 64-byte rows) -- against the oracle and against the two-launch plan, whose bits it must
+    reproduce (same operand rounding, same accumulation order)."""
+    eng, sd = _engine("v1")
+    w = O.folded_weights(sd)
+    for (n, m), lengths in (((11, 2), (1, 2, 117, 118, 119, 128, 245, 246, 247, 493, 1031)), ((9, 1), (1, 125, 126, 127, 254, 255, 509)),
+                            ((7, 2), (1, 121, 122, 123, 244, 245, 700)), ((6, 0), (3, 126, 127, 253, 254, 600))):
+        C = 512 >> (n // 3 + 1)
+        k, d = (3, 7, 11)[n % 3], (1, 3, 5)[m]
+        for L in lengths:
+            torch.manual_seed(L)
+            x = torch.randn(1, C, L)
+            ref = _pair_ref(w, n, m, k, d, x)
+            y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
+            tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
+            assert np.abs(y - ref).max() <= tol, (n, m, L, fused)
+            if fused:
+                os.environ["HFG_PAIR"] = "0"
+                try:
+                    y2, fused2 = eng.run_pair(n, m, x.numpy(), precision=mode)
+                finally:
+                    del os.environ["HFG_PAIR"]
+                assert not fused2
+                np.testing.assert_array_equal(y, y2, err_msg=f"resblocks.{n} pair {m} L={L}")
+
+
+def test_resblock_pair_batch_items_are_independent():
+    eng, _ = _engine("v1")
+    torch.manual_seed(5)
+    x = torch.randn(5, 32, 900).numpy()
+    for mode in ("bf16x3", "bf16"):
+        y, fused = eng.run_pair(10, 2, x, precision=mode)
+        assert fused
+        for b in (0, 4):
+            np.testing.assert_array_equal(y[b], eng.run_pair(10, 2, x[b:b + 1], precision=mode)[0][0])
+
+
+# ---------------------------------------------------------------------------
 # end to end against the reference's own outputs
 # ---------------------------------------------------------------------------
 
