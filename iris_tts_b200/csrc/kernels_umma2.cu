@@ -76,6 +76,56 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     }
 }
 
+// One K-chunk of one 128-row subtile: all taps x passes x K=16 slices.  The loop is warp-uniform and lives in uniform registers
+// (descriptors advance by one add per tap); only the elected lane issues.  KS = K=16 slices per tap; NP = passes per tap:
+// 1 bf16 | 3 bf16x3 (hi,hi)(lo,hi)(hi,lo) | 2 concat (hi,[hi;lo])(lo,hi).  The generic loop this replaces rebuilt descriptors and
+// instruction words per MMA (~19 instructions, 100-130 cycles per MMA from one thread).
+template <int KS, int NP>
+__device__ __forceinline__ void issue_taps_resident(bool leader, int taps, uint32_t d0, uint32_t a_lo, uint32_t w_lo, uint32_t a_tap,
+                                                    uint32_t w_tap, uint32_t a_pl, uint32_t w_pl, uint32_t dhi, uint32_t id0, uint32_t id1,
+                                                    uint32_t acc_in) {
+#pragma unroll 1
+    for (int j = 0; j < taps; ++j) {
+        if (leader) {
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+                const uint32_t aa = a_lo + (ps == 1 ? a_pl : 0u);
+                const uint32_t ww = w_lo + (ps == 2 ? w_pl : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    umma_bf16_lh(d0, aa + 2u * ks, ww + 2u * ks, dhi, ps == 0 ? id0 : id1, (ps | ks) ? 1u : (acc_in | (uint32_t)(j != 0)));
+            }
+        }
+        a_lo += a_tap;
+        w_lo += w_tap;
+    }
+}
+// Same with the W tile of every tap arriving through the TMA ring (one barrier round trip per tap).
+template <int KS, int NP>
+__device__ __forceinline__ void issue_taps_streamed(bool leader, int taps, uint32_t d0, uint32_t a_lo, uint32_t w_ring, uint32_t a_tap,
+                                                    uint32_t w_stage16, uint32_t a_pl, uint32_t w_pl, uint32_t dhi, uint32_t id0, uint32_t id1,
+                                                    uint32_t acc_in, uint32_t bar_w_full, uint32_t bar_w_empty, int n_w, int& sw, uint32_t& pw) {
+#pragma unroll 1
+    for (int j = 0; j < taps; ++j) {
+        mbar_wait(bar_w_full + 8 * sw, pw);
+        tc_fence_after();
+        const uint32_t w_lo = w_ring + (uint32_t)sw * w_stage16;
+        if (leader) {
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+                const uint32_t aa = a_lo + (ps == 1 ? a_pl : 0u);
+                const uint32_t ww = w_lo + (ps == 2 ? w_pl : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    umma_bf16_lh(d0, aa + 2u * ks, ww + 2u * ks, dhi, ps == 0 ? id0 : id1, (ps | ks) ? 1u : (acc_in | (uint32_t)(j != 0)));
+            }
+            umma_commit(bar_w_empty + 8 * sw);
+        }
+        if (++sw == n_w) { sw = 0; pw ^= 1u; }
+        a_lo += a_tap;
+    }
+}
+
 template <int kPlanes, bool kHasRes>
 __global__ void __launch_bounds__(threads_for(kPlanes), 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -87,7 +137,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float bias_s[256];
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler too: role values stay in uniform registers
     const int lane = threadIdx.x & 31;
     constexpr int planes = kPlanes;          // 1: bf16 ; 2: bf16x3 (hi + lo operand planes, three MMA passes)
     constexpr int npass = kPlanes == 2 ? 3 : 1;
@@ -136,7 +186,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_slot, 0);
     const int acc_cols = a.mt * a.acc_n;   // columns of one accumulator buffer
     // Programmatic dependent launch: the next kernel of the plan may start its own prologue on SMs this grid has left;
     // nothing above reads or writes an activation.  Weights are static, so the resident-W loads below precede the wait.
@@ -193,51 +243,50 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const bool leader = elect_one();
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * a.N) >> 3) << 17) | ((128u >> 4) << 24);
-            const int np = a.concat ? 2 : npass;
+            const bool concat = a.concat != 0;
+            const uint32_t id0 = concat ? idesc2 : idesc;
             const uint32_t dhi = desc_hi(row_bytes);
             const uint32_t sub_step = (128u * row_bytes) >> 4;          // descriptor step between 128-row subtiles
-            const uint32_t a_pl_step = a.a_plane_bytes >> 4, w_pl_step = a.w_plane_bytes >> 4;
+            const uint32_t a_pl = a.a_plane_bytes >> 4, w_pl = a.w_plane_bytes >> 4;
             const bool k4 = a.kc == 64;
+            const bool resident = a.w_resident != 0;
+            const int taps = a.taps, nchunks = a.nchunks, n_a = a.n_a, n_w = a.n_w;
+            const uint32_t row16 = row_bytes >> 4;
+            const uint32_t a_tap = (uint32_t)a.tap_step * row16;        // may be negative (polyphase upsampler): wraps correctly
+            const uint32_t a_first = (uint32_t)(a.tap_off0 - a.lo) * row16 + (uint32_t)my_ms * sub_step;
+            const uint32_t a_ring = desc_lo(smem_a), a_stage16 = a_stage_bytes >> 4;
+            const uint32_t w_ring = desc_lo(smem_w), w_stage16 = w_stage_bytes >> 4;
+            const bool go = leader && a.dbg != 2;
+            const bool dbg3 = a.dbg == 3;
             int sa = 0, sw = 0;
             uint32_t pa = 0, pw = 0;
-            if (a.w_resident) mbar_wait(bar_wres, 0);
+            if (resident) mbar_wait(bar_wres, 0);
             int it = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(bar_acc_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols + my_ms * a.acc_n);
-                uint32_t acc = 0;
-                for (int c = 0; c < a.nchunks; ++c) {
-                    if (a.dbg != 3) mbar_wait(bar_a_full + 8 * sa, pa);
-                    const uint32_t a_stage_lo = desc_lo(smem_a + sa * a_stage_bytes) + (uint32_t)my_ms * sub_step;
-                    for (int j = 0; j < a.taps; ++j) {
-                        uint32_t w_lo0;
-                        if (a.w_resident) {
-                            w_lo0 = desc_lo(smem_w + (uint32_t)(c * a.taps + j) * w_stage_bytes);
-                        } else {
-                            mbar_wait(bar_w_full + 8 * sw, pw);
-                            w_lo0 = desc_lo(smem_w + sw * w_stage_bytes);
-                        }
-                        tc_fence_after();
-                        const uint32_t a_lo0 = a_stage_lo + (((uint32_t)(a.tap_off0 + j * a.tap_step - a.lo) * row_bytes) >> 4);
-                        for (int ps = 0; ps < np; ++ps) {
-                            const uint32_t a_lo = a_lo0 + (ps == 1 ? a_pl_step : 0u);   // (hi,hi) (lo,hi) (hi,lo) | concat: (hi,[hi;lo]) (lo,hi)
-                            const uint32_t w_lo = w_lo0 + ((ps == 2) ? w_pl_step : 0u);
-                            const uint32_t id = (a.concat && ps == 0) ? idesc2 : idesc;
-                            if (leader && a.dbg != 2) {
-                                if (k4) umma_ksteps<4>(d0, a_lo, w_lo, dhi, id, acc);
-                                else umma_ksteps<2>(d0, a_lo, w_lo, dhi, id, acc);
-                            }
-                            acc = 1;
-                        }
-                        if (!a.w_resident) {
-                            if (leader) umma_commit(bar_w_empty + 8 * sw);
-                            if (++sw == a.n_w) { sw = 0; pw ^= 1u; }
-                        }
-                    }
+                for (int c = 0; c < nchunks; ++c) {
+                    if (!dbg3) mbar_wait(bar_a_full + 8 * sa, pa);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_ring + (uint32_t)sa * a_stage16 + a_first;
+                    const uint32_t acc_in = c != 0;
+#define HFG_ISSUE(KS, NP)                                                                                                           \
+    do {                                                                                                                            \
+        if (resident)                                                                                                               \
+            issue_taps_resident<KS, NP>(go, taps, d0, a_lo, w_ring + (uint32_t)(c * taps) * w_stage16, a_tap, w_stage16, a_pl, w_pl, dhi, \
+                                        id0, idesc, acc_in);                                                                        \
+        else                                                                                                                        \
+            issue_taps_streamed<KS, NP>(go, taps, d0, a_lo, w_ring, a_tap, w_stage16, a_pl, w_pl, dhi, id0, idesc, acc_in, bar_w_full,  \
+                                        bar_w_empty, n_w, sw, pw);                                                                  \
+    } while (0)
+                    if (kPlanes == 1) { if (k4) HFG_ISSUE(4, 1); else HFG_ISSUE(2, 1); }
+                    else if (concat) { if (k4) HFG_ISSUE(4, 2); else HFG_ISSUE(2, 2); }
+                    else { if (k4) HFG_ISSUE(4, 3); else HFG_ISSUE(2, 3); }
+#undef HFG_ISSUE
                     if (leader) umma_commit(bar_a_empty + 8 * sa);
-                    if (++sa == a.n_a) { sa = 0; pa ^= 1u; }
+                    if (++sa == n_a) { sa = 0; pa ^= 1u; }
                 }
                 if (leader) umma_commit(bar_acc_full + 8 * buf);
                 __syncwarp();
