@@ -21,7 +21,8 @@
 // (tap, K-slice, pass) order that does not depend on the tile a row falls in, nor on B or L.
 //
 // Warps: 0 = TMA producer (resident weights of both convs, x ring), 2 = TMEM allocator, 3 = barrier init,
-//        4-7 = epilogue 1, 8..8+2*MT-1 = MMA issuers (one per conv and 128-row subtile), 12-15 = epilogue 2.
+//        4..4+2*MT-1 = MMA issuers (one per conv and 128-row subtile), 8-15 = epilogue 1, 16-23 = epilogue 2 (two groups of four
+//        warps each; group g takes the tiles with (i & 1) == g, so a group has two tile intervals for its tile).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -36,7 +37,7 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 768;   // 24 warps: the epilogues are issue-latency-bound, two groups of each alternate tiles
 constexpr int kMaxX = 8;
 constexpr uint32_t kSmemMax = 227u * 1024u - 2048u;   // dynamic smem; barriers / bias (static, < 2 KB) live outside
 
@@ -55,29 +56,44 @@ struct PairArgs {
     const float* bias2;
 };
 
-__device__ __forceinline__ float inv_lrelu(float p) { return p > 0.f ? p : p * (1.0f / kLreluSlope); }
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
+// ---- packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogues are issue-bound, a pair costs one instruction ----
+typedef uint64_t f2;
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 f2_bits(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// leaky_relu(v, 0.1) = max(v, 0.1 v) and its inverse p > 0 ? p : 10 p = min(p, 10 p): the same values as the select forms
+__device__ __forceinline__ f2 f2_lrelu(f2 v) {
+    float a, b, sa, sb;
+    f2_unpack(v, a, b);
+    f2_unpack(f2_mul(v, f2_pack(kLreluSlope, kLreluSlope)), sa, sb);
+    return f2_pack(fmaxf(a, sa), fmaxf(b, sb));
 }
-
-// hi (and lo = v - hi) planes of 8 consecutive channels -> 16-byte chunks
+__device__ __forceinline__ f2 f2_inv_lrelu(f2 p) {
+    float a, b, ta, tb;
+    f2_unpack(p, a, b);
+    f2_unpack(f2_mul(p, f2_pack(1.0f / kLreluSlope, 1.0f / kLreluSlope)), ta, tb);
+    return f2_pack(fminf(a, ta), fminf(b, tb));
+}
+// two bf16 (channels 2i, 2i+1 of one 32-bit word) -> fp32 pair
+__device__ __forceinline__ f2 f2_from_bf16x2(uint32_t w) { return f2_bits(w << 16, w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f2 v) {
+    float a, b;
+    f2_unpack(v, a, b);
+    return pack_bf16(a, b);
+}
+// hi (and lo = v - hi) planes of 8 consecutive channels (4 pairs) -> 16-byte chunks
 template <int kPlanes>
-__device__ __forceinline__ void store_planes8(const float* v, uint32_t addr, uint32_t plane_bytes) {
+__device__ __forceinline__ void store_planes8(const f2* v, uint32_t addr, uint32_t plane_bytes) {
     uint4 hi;
-    hi.x = pack_bf16(v[0], v[1]); hi.y = pack_bf16(v[2], v[3]); hi.z = pack_bf16(v[4], v[5]); hi.w = pack_bf16(v[6], v[7]);
+    hi.x = f2_to_bf16x2(v[0]); hi.y = f2_to_bf16x2(v[1]); hi.z = f2_to_bf16x2(v[2]); hi.w = f2_to_bf16x2(v[3]);
     sts128(addr, hi);
     if (kPlanes > 1) {
-        float fh[8];
-        unpack8(hi, fh);
         uint4 lo;
-        lo.x = pack_bf16(v[0] - fh[0], v[1] - fh[1]); lo.y = pack_bf16(v[2] - fh[2], v[3] - fh[3]);
-        lo.z = pack_bf16(v[4] - fh[4], v[5] - fh[5]); lo.w = pack_bf16(v[6] - fh[6], v[7] - fh[7]);
+        lo.x = f2_to_bf16x2(f2_sub(v[0], f2_from_bf16x2(hi.x))); lo.y = f2_to_bf16x2(f2_sub(v[1], f2_from_bf16x2(hi.y)));
+        lo.z = f2_to_bf16x2(f2_sub(v[2], f2_from_bf16x2(hi.z))); lo.w = f2_to_bf16x2(f2_sub(v[3], f2_from_bf16x2(hi.w)));
         sts128(addr + plane_bytes, lo);
     }
 }
@@ -125,7 +141,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     const int lane = threadIdx.x & 31;
     constexpr int planes = kPlanes;
     constexpr int npass = kPlanes == 2 ? 3 : 1;
-    constexpr int CW = kPlanes == 2 ? 16 : 32;    // epilogue column chunk (registers: two planes double the live state)
+    constexpr int CW = 16;                        // epilogue column chunk: 768 threads leave 80 registers per thread
     const uint32_t row_bytes = (uint32_t)a.N * 2u;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -208,11 +224,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             }
         }
         __syncwarp();
-    } else if (warp >= 8 && warp < 12) {
+    } else if (warp >= 4 && warp < 8) {
         // ===== MMA issuers: warp 8 + cv*MT + ms issues conv cv (0: c1, 1: c2) of subtile ms =====
         // One thread cannot issue small-N MMAs at the tensor pipe's rate, and c1 of tile i+1 must overlap the
         // epilogues of tile i: c1 and c2 have their own issuers, ordered only by the barriers.
-        const int role = warp - 8;
+        const int role = warp - 4;
         const int cv = role / a.mt, ms = role % a.mt;
         if (cv < 2) {
             const bool leader = elect_one();
@@ -271,11 +287,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 __syncwarp();
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 8 && warp < 16) {
         // ===== epilogue 1: acc1 -> t tile (activated planes of c1's output, zero outside the sequence) =====
-        const int q = warp & 3;
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int grp = (warp - 8) >> 2;             // group g owns the tiles with (it & 1) == g, i.e. accumulator buffer g
         const int nch = a.N / CW;
-        for (int it = 0; it < n_my; ++it) {
+        for (int it = grp; it < n_my; it += 2) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
             const int b = tl / a.tiles_per_item;
@@ -287,6 +304,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             mbar_wait(bar_t_empty + 8 * st, pt ^ 1u);
             tc_fence_after();
             const uint32_t t_slot = smem_t + st * t_stage;
+            const bool edge_tile = g0 < 0 || g0 + a.R > a.L;
             for (int ms = 0; ms < (a.dbg == 3 ? 0 : a.mt); ++ms) {
                 const uint32_t row_t = (uint32_t)(ms * 128 + q * 32 + lane);
                 const int g = g0 + (int)row_t;
@@ -299,20 +317,27 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + ms * a.acc_n + col);
                     tmem_ld<CW>(tcol, r);
                     tmem_wait_ld();
-                    float v[CW];
+                    f2 v[CW / 2];
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) + bias_s[0][col + i];
+                    for (int i = 0; i < CW / 2; ++i) {
+                        const float2 bv = *reinterpret_cast<const float2*>(&bias_s[0][col + 2 * i]);
+                        v[i] = f2_add(f2_bits(r[2 * i], r[2 * i + 1]), f2_pack(bv.x, bv.y));
+                    }
                     if (kPlanes == 2 && a.concat) {   // second half of the concatenated accumulator: A_hi x W_lo
                         tmem_ld<CW>(tcol + (uint32_t)a.N, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < CW; ++i) v[i] += __uint_as_float(r[i]);
+                        for (int i = 0; i < CW / 2; ++i) v[i] = f2_add(v[i], f2_bits(r[2 * i], r[2 * i + 1]));
                     }
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = inside ? lrelu(v[i]) : 0.f;
+                    for (int i = 0; i < CW / 2; ++i) v[i] = f2_lrelu(v[i]);
+                    if (edge_tile) {   // warp-uniform: only tiles that overlap a sequence end carry rows outside [0, L)
+#pragma unroll
+                        for (int i = 0; i < CW / 2; ++i) v[i] = inside ? v[i] : 0ull;
+                    }
 #pragma unroll
                     for (int c = 0; c < CW / 8; ++c)
-                        store_planes8<kPlanes>(&v[c * 8], dst + ((((uint32_t)(h * (CW / 8) + c)) ^ sx) << 4), a.t_plane_bytes);
+                        store_planes8<kPlanes>(&v[c * 4], dst + ((((uint32_t)(h * (CW / 8) + c)) ^ sx) << 4), a.t_plane_bytes);
                 }
             }
             tc_fence_before();      // this warp has read the last of acc1[buf]
@@ -320,9 +345,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_a1_empty + 8 * buf); mbar_arrive(bar_t_full + 8 * st); }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 16) {
         // ===== epilogue 2: acc2 + b2 + x (inverse lrelu of the x tile rows) -> activated planes -> TMA store =====
         const int q = warp & 3;
+        const int grp = (warp - 16) >> 2;
         const int nch = a.N / CW;
         // staging box of this warp: 32 rows; C = 32 paired: two 64-byte time rows form one 128-byte row (SWIZZLE_128B)
         const uint32_t orow_bytes = a.paired ? 128u : row_bytes;
@@ -331,9 +357,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         const uint32_t o_sx = a.paired ? (uint32_t)((lane >> 1) & 7) : swz((uint32_t)lane, orow_bytes);
         const int rshift = a.paired ? 1 : 0;
         pdl_wait();                                  // before the first global write (WAR against the previous kernel's reads)
-        int sx = 0, so = 0;
-        uint32_t px = 0;
-        for (int it = 0; it < n_my; ++it) {
+        int so = 0;
+        for (int it = grp; it < n_my; it += 2) {
+            const int sx = it % a.n_x;
+            const uint32_t px = (uint32_t)(it / a.n_x) & 1u;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
             const int b = tl / a.tiles_per_item;
@@ -350,7 +377,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 const uint32_t row_x = (uint32_t)(rs + lane + a.h1 + a.h2);
                 const uint32_t xsrc = x_slot + row_x * row_bytes;
                 const uint32_t xsw = swz(row_x, row_bytes);
-                const uint32_t slot = smem_o + (uint32_t)(q * a.n_o + so) * o_slot;
+                const uint32_t slot = smem_o + (uint32_t)((grp * 4 + q) * a.n_o + so) * o_slot;
                 if (lane == 0) { if (a.n_o == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the store that last used this slot has read it
                 __syncwarp();
                 for (int h = 0; h < nch; ++h) {
@@ -358,36 +385,40 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                     const int col = h * CW;
                     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + buf) * acc_cols + ms * a.acc_n + col);
                     tmem_ld<CW>(tcol, r);
-                    float res[CW];
+                    f2 res[CW / 2];
 #pragma unroll
                     for (int c = 0; c < CW / 8; ++c) {
                         const uint32_t xa = xsrc + ((((uint32_t)(h * (CW / 8) + c)) ^ xsw) << 4);
-                        float f[8];
-                        unpack8(lds128(xa), f);
+                        const uint4 ph = lds128(xa);
+                        const uint32_t wh[4] = {ph.x, ph.y, ph.z, ph.w};
                         if (planes > 1) {
-                            float fl[8];
-                            unpack8(lds128(xa + a.x_plane_bytes), fl);
+                            const uint4 pl = lds128(xa + a.x_plane_bytes);
+                            const uint32_t wl[4] = {pl.x, pl.y, pl.z, pl.w};
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] += fl[i];
+                            for (int i = 0; i < 4; ++i) res[c * 4 + i] = f2_inv_lrelu(f2_add(f2_from_bf16x2(wh[i]), f2_from_bf16x2(wl[i])));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) res[c * 4 + i] = f2_inv_lrelu(f2_from_bf16x2(wh[i]));
                         }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) res[c * 8 + i] = inv_lrelu(f[i]);
                     }
                     tmem_wait_ld();
-                    float v[CW];
+                    f2 v[CW / 2];
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) + bias_s[1][col + i];
+                    for (int i = 0; i < CW / 2; ++i) {
+                        const float2 bv = *reinterpret_cast<const float2*>(&bias_s[1][col + 2 * i]);
+                        v[i] = f2_add(f2_bits(r[2 * i], r[2 * i + 1]), f2_pack(bv.x, bv.y));
+                    }
                     if (kPlanes == 2 && a.concat) {
                         tmem_ld<CW>(tcol + (uint32_t)a.N, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < CW; ++i) v[i] += __uint_as_float(r[i]);
+                        for (int i = 0; i < CW / 2; ++i) v[i] = f2_add(v[i], f2_bits(r[2 * i], r[2 * i + 1]));
                     }
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = lrelu(v[i] + res[i]);
+                    for (int i = 0; i < CW / 2; ++i) v[i] = f2_lrelu(f2_add(v[i], res[i]));
 #pragma unroll
                     for (int c = 0; c < CW / 8; ++c)
-                        store_planes8<kPlanes>(&v[c * 8], slot + o_row_off + (((o_chunk0 + (uint32_t)(h * (CW / 8) + c)) ^ o_sx) << 4), a.o_plane_bytes);
+                        store_planes8<kPlanes>(&v[c * 4], slot + o_row_off + (((o_chunk0 + (uint32_t)(h * (CW / 8) + c)) ^ o_sx) << 4), a.o_plane_bytes);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -405,7 +436,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             tc_fence_before();   // this warp has read the last of acc2[buf] and of the x slot
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_a2_empty + 8 * buf); mbar_arrive(bar_x_empty + 8 * sx); }
-            if (++sx == a.n_x) { sx = 0; px ^= 1u; }
         }
         if (lane == 0) bulk_wait_read<0>();
     }
@@ -507,8 +537,8 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     const uint32_t budget = kSmemMax - 1024;   // alignment slack
 
     // Choose (MT, x ring depth, t buffers, staging slots per warp): cycles per valid output row of a tile interval, the
-    // largest of tensor time (measured small-N MMA floors), HBM time and epilogue issue time, inflated when the x ring is
-    // too shallow to cover the fetch latency (x(i) stays live until epilogue 2 of tile i, i.e. for about two intervals).
+    // largest of tensor time (measured small-N MMA floors), HBM time and epilogue issue time, inflated when the rings are
+    // too shallow for the lifetime of their slots (calibrated on tools/sweep_pair.sh runs).
     auto floor_clk = [](double n) { return std::max(128.0 * n / 256.0, (4096.0 + 32.0 * n) / 128.0); };
     const double step_clk = a.concat ? floor_clk(2.0 * N) + floor_clk(N) : p.npass * floor_clk(N);
     const int ksteps = N / 16;
@@ -531,18 +561,22 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
         const double t_int = std::max({t_mma, t_hbm, t_epi}) + 300.0;
         for (int n_t = 2; n_t >= 1; --n_t) {
             if (f_nt && n_t != f_nt) continue;
-            for (int n_o = 2; n_o >= 1; --n_o) {
+            // each epilogue-2 warp meets one of its slots again two tiles later (the groups alternate tiles): mt slots suffice
+            for (int n_o = std::min(mt, 2); n_o >= 1; --n_o) {
                 if (f_no && n_o != f_no) continue;
-                const uint32_t fixed = w_all + (uint32_t)n_t * t_plane * planes + 4u * n_o * a.o_plane_bytes * planes;
+                const uint32_t fixed = w_all + (uint32_t)n_t * t_plane * planes + 8u * n_o * a.o_plane_bytes * planes;
                 if (fixed + 3 * x_plane * planes > budget) continue;
                 const int n_x_max = (int)std::min<uint32_t>((budget - fixed) / (x_plane * planes), (uint32_t)kMaxX);
                 for (int n_x = n_x_max; n_x >= 3; --n_x) {
                     if (f_nx && n_x != f_nx) continue;
-                    const double f_x = std::min(1.0, (n_x - 2) * t_int / 3500.0);
+                    // an x slot lives from its load (~2500 cycles of HBM latency) through c1, epilogue 1, c2 and epilogue 2 of its
+                    // tile (the residual is read from it): about three intervals.  Measured: one t buffer costs ~1.4x (epilogue 1 of
+                    // tile i+1 waits for c2 of tile i), a staging slot shared by the two steps of a tile ~1.08x.
+                    const double f_x = std::min(1.0, n_x / (3.0 + 2500.0 / t_int));
                     const long tiles = (long)((p.L + V - 1) / V) * p.B;
                     const long waves = (tiles + sm_count - 1) / std::max(1, sm_count);
                     const double fill = (double)tiles / (double)(waves * std::max(1, sm_count));
-                    const double cost = t_int / f_x / V / fill * (n_t == 1 ? 1.04 : 1.0) * (n_o == 1 ? 1.03 : 1.0);
+                    const double cost = t_int / f_x / V / fill * (n_t == 1 ? 1.4 : 1.0) * (n_o < mt ? 1.08 : 1.0);
                     if (cost < best - 1e-9) {
                         best = cost; ok = true;
                         a.mt = mt; a.R = R; a.V = V;
@@ -553,7 +587,7 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
                         a.off_t = a.off_w + w_all;
                         a.off_o = a.off_t + (uint32_t)n_t * t_plane * planes;
                         // > half an SM, so exactly one CTA (512 TMEM columns) lives on an SM
-                        I->smem = std::max<size_t>((size_t)a.off_o + 4u * n_o * a.o_plane_bytes * planes + 1024, 120u * 1024u);
+                        I->smem = std::max<size_t>((size_t)a.off_o + 8u * n_o * a.o_plane_bytes * planes + 1024, 120u * 1024u);
                     }
                 }
             }

@@ -575,7 +575,10 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     a.y_hi = p.y_act; a.y_lo = p.y_act_lo;
     a.dbg = env_i("HFG_U2_DBG", 0);
     a.reverse = p.reverse;
-    a.concat = (planes == 2 && N <= env_i("HFG_U2_CONCAT_MAXN", 32)) ? 1 : 0;   // wider layers stream W: halving MT would double that traffic
+    // N = 32 always; N = 64 from 7 taps on (measured: k = 11 0.456 -> 0.420 ms, k = 7 0.316 -> 0.277 ms, k = 3 loses); wider layers
+    // stream W, where halving MT would double that traffic.  Depends on the layer only: bits never depend on B or L.
+    const int concat_maxn = env_i("HFG_U2_CONCAT_MAXN", 0);
+    a.concat = (planes == 2 && !ups && (concat_maxn ? N <= concat_maxn : (N <= 32 || (N == 64 && g.taps >= 7)))) ? 1 : 0;
     a.acc_n = a.concat ? 2 * N : N;
 
     // Choose (K-chunk width, epilogue box width, MT, resident W, ring depths) by a small cost model: cycles per output
