@@ -191,8 +191,18 @@ def ncu_traffic(precision, kernel):
         return None
 
 
-def roofline_from_records(recs, peaks, kernel="conv_umma2", precision=None):
-    """Dominant kernel = conv_umma2_kernel (the persistent tcgen05 conv: 72 of the 77 conv launches of a V1 forward)."""
+def roofline_from_records(recs, peaks, kernel=None, precision=None):
+    """Roofline record of one kernel family from the per-launch event timings (hfg_profile_*).  Default: the dominant kernel,
+    i.e. the tensor-core conv family with the largest share of the step (conv_umma2_kernel: the wide ResBlock convs; conv_pair_kernel:
+    the fused conv1 -> conv2 ResBlock steps of the C <= 64 stages)."""
+    if kernel is None:
+        share = {}
+        for r in recs:
+            if r["kernel"] in ("conv_umma2", "conv_pair", "conv_umma"):
+                share[r["kernel"]] = share.get(r["kernel"], 0.0) + r["ms"]
+        if not share:
+            return None
+        kernel = max(share, key=share.get)
     sel = [r for r in recs if r["kernel"] == kernel]
     if not sel:
         return None
@@ -207,7 +217,20 @@ def roofline_from_records(recs, peaks, kernel="conv_umma2", precision=None):
             # bf16x3 executes three bf16 MMAs per algorithmic one (hi*hi, lo*hi, hi*lo): the tensor pipe's own rate
             "executed_flop_factor": 3 if precision == "bf16x3" else 1,
             "executed_frac": (3 if precision == "bf16x3" else 1) * achieved / peaks["tflops"],
-            "algorithmic_flops_per_launch": flops / len(sel)}
+            "algorithmic_flops_per_launch": flops / len(sel),
+            "algorithmic_gbs": sum(r["bytes"] for r in sel) / (ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["gbs"]}
+
+
+def other_rooflines(recs, peaks, precision, dominant):
+    """The same record for the other tensor-core conv families of the step (explains the rest of the time)."""
+    out = []
+    for k in ("conv_umma2", "conv_pair", "conv_umma"):
+        if dominant and dominant["kernel"] == k + "_kernel":
+            continue
+        r = roofline_from_records(recs, peaks, kernel=k, precision=precision)
+        if r:
+            out.append(r)
+    return out
 
 
 def run_ours(args):
@@ -299,6 +322,7 @@ def run_ours(args):
         secondary = {"dtype": "bf16", "value": samples_per_step * args.steps / (ms2 * 1e-3), "unit": "samples/s",
                      "ms_per_step": ms2 / args.steps, "layer_roofline_ms": rl2 * 1e3, "layer_roofline_frac": rl2 * 1e3 / (ms2 / args.steps),
                      "roofline": roofline_from_records(recs2, peaks, precision="bf16"),
+                     "roofline_other_kernels": other_rooflines(recs2, peaks, "bf16", roofline_from_records(recs2, peaks, precision="bf16")),
                      "tolerance": "max-abs 1.5e-1 vs oracle on loud weights (tests/test_gpu_parity.py); 1e-3 at default init"}
 
     if rank != 0:
@@ -333,6 +357,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(B * T * hop * 4), "api": "iris.hifigan_pretrained.HiFiGANGenerator.__call__(np.ndarray)"},
         "gpu_launches": int(launches),
         "roofline": roofline_from_records(recs, peaks, precision=args.precision),
+        "roofline_other_kernels": other_rooflines(recs, peaks, args.precision, roofline_from_records(recs, peaks, precision=args.precision)),
         "layer_roofline": {"ms": rl * 1e3, "frac": rl * 1e3 / ms_step,
                            "definition": "sum_l max(F_l/P, Q_l/BW) (SURVEY 8d): " + ("bf16 peak, 2-byte activations" if args.precision == "bf16" else
                                          "fp32-class mode: P = bf16 peak / 2 (TF32-class), 4-byte activations"),

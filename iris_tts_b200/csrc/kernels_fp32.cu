@@ -332,6 +332,39 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat
     }
 }
 
+// MRF sum of NK branch planes at 8 consecutive channels: every plane's 16-byte load is issued before the first use
+// (the generic loop over a runtime nk serialises one DRAM latency per branch).  Arithmetic: ((x0 + x1) + x2 ...) as in
+// hifigan_pretrained.py:133-136, x_j = inverse-lrelu(plane j).
+template <int NK, bool LO>
+__device__ __forceinline__ void mrf_sum8(const MrfArgs& a, size_t i8, float (&v)[8]) {
+    uint4 h[NK], l[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+        h[j] = __ldg(reinterpret_cast<const uint4*>(a.hi[j]) + i8);
+        if (LO) l[j] = __ldg(reinterpret_cast<const uint4*>(a.lo[j]) + i8);
+    }
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+        const uint32_t w[4] = {h[j].x, h[j].y, h[j].z, h[j].w};
+        float f[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { f[2 * t] = __uint_as_float(w[t] << 16); f[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u); }
+        if (LO) {
+            const uint32_t wl[4] = {l[j].x, l[j].y, l[j].z, l[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { f[2 * t] += __uint_as_float(wl[t] << 16); f[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u); }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = j == 0 ? inv_lrelu(f[t]) : v[t] + inv_lrelu(f[t]);
+    }
+}
+// runtime nk -> the specialised sum (nk = 3 is every shipped config); false: caller runs the generic loop
+__device__ __forceinline__ bool mrf_sum8_dispatch(const MrfArgs& a, size_t i8, float (&v)[8]) {
+    if (a.nk == 3) { if (a.lo[0]) mrf_sum8<3, true>(a, i8, v); else mrf_sum8<3, false>(a, i8, v); return true; }
+    if (a.nk == 2) { if (a.lo[0]) mrf_sum8<2, true>(a, i8, v); else mrf_sum8<2, false>(a, i8, v); return true; }
+    return false;
+}
+
 // [rows][C_tc] planes -> [rows][C] fp32 (C <= C_tc: drops the zero padding channels of narrow stages)
 __global__ void planes_to_raw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ raw,
                                      size_t rows, int c8_tc, int c8) {
@@ -351,14 +384,16 @@ __global__ void planes_to_raw_kernel(const __nv_bfloat16* __restrict__ hi, const
 __global__ void mrf_combine_kernel(const MrfArgs a, size_t n8) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         float v[8];
-        load8(a.hi[0], a.lo[0], i, v);
+        if (!mrf_sum8_dispatch(a, i, v)) {
+            load8(a.hi[0], a.lo[0], i, v);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = inv_lrelu(v[t]);
-        for (int j = 1; j < a.nk; ++j) {
-            float f[8];
-            load8(a.hi[j], a.lo[j], i, f);
+            for (int t = 0; t < 8; ++t) v[t] = inv_lrelu(v[t]);
+            for (int j = 1; j < a.nk; ++j) {
+                float f[8];
+                load8(a.hi[j], a.lo[j], i, f);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = v[t] + inv_lrelu(f[t]);
+                for (int t = 0; t < 8; ++t) v[t] = v[t] + inv_lrelu(f[t]);
+            }
         }
         // mean: multiply by 1/nk (the tensor-core modes are not bit-faithful to fp32 anyway; conv_post_mrf uses the same form)
         const float rinv = 1.0f / (float)a.nk;
@@ -412,15 +447,18 @@ __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfAr
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (t >= 0 && t < L) {
             const size_t i8 = base8 + (size_t)t * c8n + c8;
-            load8(a.hi[0], a.lo[0], i8, v);
+            const bool summed = a.nk > 1 && mrf_sum8_dispatch(a, i8, v);
+            if (!summed) load8(a.hi[0], a.lo[0], i8, v);
             if (a.nk > 1) {
+                if (!summed) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = inv_lrelu(v[q]);
-                for (int j = 1; j < a.nk; ++j) {
-                    float f[8];
-                    load8(a.hi[j], a.lo[j], i8, f);
+                    for (int q = 0; q < 8; ++q) v[q] = inv_lrelu(v[q]);
+                    for (int j = 1; j < a.nk; ++j) {
+                        float f[8];
+                        load8(a.hi[j], a.lo[j], i8, f);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = v[q] + inv_lrelu(f[q]);
+                        for (int q = 0; q < 8; ++q) v[q] = v[q] + inv_lrelu(f[q]);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {

@@ -292,7 +292,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int grp = (warp - 8) >> 2;             // group g owns the tiles with (it & 1) == g, i.e. accumulator buffer g
         const int nch = a.N / CW;
-        for (int it = grp; it < n_my; it += 2) {
+        // With ONE t buffer the tiles must pass through epilogue 1 in order (the parity wait on bar_t_empty cannot tell "c2 of tile
+        // i-1 is done" from "c2 of tile i-3 is done"): group 0 takes every tile and group 1 idles.  With two buffers each group
+        // owns one and only ever waits for its own previous tile.
+        const int it0 = a.n_t == 1 ? (grp == 0 ? 0 : n_my) : grp;
+        const int it_step = a.n_t == 1 ? 1 : 2;
+        for (int it = it0; it < n_my; it += it_step) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
             const int b = tl / a.tiles_per_item;
@@ -594,6 +599,9 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
         }
     }
     if (!ok) return HFG_ERR_UNSUPPORTED;
+    // One t buffer serialises epilogue 1 behind c2 of the previous tile (and leaves one epilogue-1 group idle): measured slower than
+    // the two-launch plan (C = 64, k = 7: 0.256 vs 0.245 ms; bf16x3 C = 32, k = 11, d = 5: 0.80 vs 0.77 ms).  Leave those unfused.
+    if (a.n_t == 1 && !f_nt && !penv("HFG_PAIR_ALLOW_NT1", 0)) return HFG_ERR_UNSUPPORTED;
     if (penv("HFG_PAIR_VERBOSE", 0))
         fprintf(stderr, "pair plan C=%d k=%d d=%d planes=%d: mt=%d V=%d n_x=%d n_t=%d n_o=%d x_rows=%d smem=%zu cost=%.2f\n", N, p.k, p.d,
                 planes, a.mt, a.V, a.n_x, a.n_t, a.n_o, a.x_rows, I->smem, best);

@@ -159,7 +159,7 @@ def test_v1_resblock_pair_parity(n, m, mode):
     x = torch.randn(2, C, 777)                     # ragged: not a multiple of any tile height
     ref = _pair_ref(w, n, m, k, d, x)
     y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
-    if C == 32 or (C == 64 and mode == "bf16" and k <= 7):
+    if (C == 32 and not (mode == "bf16x3" and k == 11 and d == 5)) or (C == 64 and mode == "bf16" and k == 3):
         assert fused, "the plan is expected to fuse this pair"
     err = np.abs(y - ref).max()
     tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
@@ -173,6 +173,14 @@ def test_resblock_pair_edges_and_equals_unfused(mode):
     reproduce (same operand rounding, same accumulation order)."""
     eng, sd = _engine("v1")
     w = O.folded_weights(sd)
+    os.environ["HFG_PAIR_ALLOW_NT1"] = "1"      # also the plans with one t buffer, which the production planner leaves unfused
+    try:
+        _pair_edges(eng, w, mode)
+    finally:
+        del os.environ["HFG_PAIR_ALLOW_NT1"]
+
+
+def _pair_edges(eng, w, mode):
     for (n, m), lengths in (((11, 2), (1, 2, 117, 118, 119, 128, 245, 246, 247, 493, 1031)), ((9, 1), (1, 125, 126, 127, 254, 255, 509)),
                             ((7, 2), (1, 121, 122, 123, 244, 245, 700)), ((6, 0), (3, 126, 127, 253, 254, 600))):
         C = 512 >> (n // 3 + 1)

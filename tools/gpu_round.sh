@@ -14,7 +14,7 @@ timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $O
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary"
 timeout 300 $BENCH > $OUT/${TAG}_bench_short.json 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_ncu_launches.log 2>&1
-LAYERS=${NCU_LAYERS:-resblocks.2.convs1.2,resblocks.3.convs1.0,resblocks.5.convs1.2,resblocks.5.convs2.2,resblocks.8.convs1.2,resblocks.9.convs2.0,resblocks.11.convs1.2,ups.1,conv_post}
+LAYERS=${NCU_LAYERS:-resblocks.2.convs1.2,resblocks.3.convs1.0,resblocks.5.convs1.2,resblocks.5.convs2.2,resblocks.8.convs1.2,resblocks.6.pair.0,resblocks.7.pair.1,resblocks.9.pair.0,resblocks.10.pair.1,resblocks.11.pair.2,ups.1,conv_post}
 for MODE in ${NCU_MODES:-bf16x3 bf16}; do
   PROF="python tools/layer_times.py --mode $MODE --B 16 --T 862 --reps 1 --warm 1"
   HFG_NCU_LAYERS=$LAYERS timeout 300 $PROF > $OUT/${TAG}_prof_plain_${MODE}.log 2>&1 &&
@@ -22,7 +22,7 @@ for MODE in ${NCU_MODES:-bf16x3 bf16}; do
   # gpurun_out is capped at 64 MiB: keep CSV exports (all metrics per launch; per-instruction samples of two launches), drop the report
   if [ -f $OUT/${TAG}_prof_${MODE}.ncu-rep ]; then
     ncu -i $OUT/${TAG}_prof_${MODE}.ncu-rep --page raw --csv > $OUT/${TAG}_prof_${MODE}_raw.csv 2>/dev/null
-    for k in 0 3; do ncu -i $OUT/${TAG}_prof_${MODE}.ncu-rep --page source --csv --launch-skip $k --launch-count 1 > $OUT/${TAG}_prof_${MODE}_source_launch$k.csv 2>/dev/null; done
+    for k in ${NCU_SOURCE_LAUNCHES:-0 2 6 8}; do ncu -i $OUT/${TAG}_prof_${MODE}.ncu-rep --page source --csv --launch-skip $k --launch-count 1 > $OUT/${TAG}_prof_${MODE}_source_launch$k.csv 2>/dev/null; done
     rm -f $OUT/${TAG}_prof_${MODE}.ncu-rep
   fi
 done
