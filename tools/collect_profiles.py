@@ -59,7 +59,7 @@ def source_top(tag, mode, k, n=40):
     rows = list(csv.reader(open(src)))
     kernel = short(rows[0][1]) if len(rows[0]) > 1 else "?"
     hdr = rows[1]
-    data = [dict(zip(hdr, r)) for r in rows[2:] if len(r) == len(hdr)]
+    data = [dict(zip(hdr, r)) for r in rows[2:] if len(r) == len(hdr) and r[0] != "Address"]
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(d["# Samples"] or 0) for d in data)
     top = sorted(data, key=lambda d: -int(d["# Samples"] or 0))[:n]
