@@ -483,7 +483,10 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         Step w2{};
         work(s, c1, Lrows, x3 ? 4 : 2);
         work(w2, c2, Lrows, x3 ? 4 : 2);
-        s.kind = S_PAIR; s.label = label; s.flops += w2.flops; s.bytes += w2.bytes;
+        // algorithmic bytes of the FUSED step: x in, out, both weight sets (the intermediate never leaves the SM)
+        const double act_b = x3 ? 4.0 : 2.0;
+        s.kind = S_PAIR; s.label = label; s.flops += w2.flops;
+        s.bytes = 2.0 * c1.cin * (double)Lrows * B * act_b + 2.0 * (double)c1.cin * c1.cout * c1.k * act_b;
         plan->steps.push_back(std::move(s));
         return true;
     };
