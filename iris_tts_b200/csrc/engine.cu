@@ -118,6 +118,9 @@ struct hfg_engine {
     cudaStream_t stream = nullptr;
     std::vector<Layer> layers;
     std::map<std::string, int> index;
+    // time-folded twins of the layers of the narrow stages (C < 32), see build_folded
+    std::map<std::string, Layer> folded;
+    int stage_fold[HFG_MAX_UPSAMPLES] = {};   // fold factor of stage i's planes (1: not folded)
     bool finalized = false;
     int hop = 1;
     // workspace
@@ -142,6 +145,11 @@ namespace hfg {
 namespace {
 
 int get_padding(int k, int d) { return (k * d - d) / 2; }  // hifigan_pretrained.py:61-62
+
+int env_flag_early(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
 
 int validate_cfg(const hfg_config& c) {
     if (c.in_channels <= 0 || c.upsample_initial_channel <= 0) return fail(HFG_ERR_INVALID, "config: channels must be positive");
@@ -305,6 +313,106 @@ int upload_layer(Layer& L) {
     return HFG_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Time folding of the narrow stages (V2's 16- and 8-channel tail)
+//
+// A channels-last plane [L][C] with C < 32 is, byte for byte, the plane [L/f][f*C] with f = 32/C: f consecutive time steps
+// form one 32-channel "super-row".  A 'same' Conv1d(C -> C, k, dilation d) on the time axis becomes a 'same' Conv1d(32 -> 32,
+// k' = 2*ceil(pad/f) + 1, dilation 1) on super-rows whose weight blocks are the original taps placed by time parity:
+//
+//   out[f*S + eo] = sum_j w_j . in[f*S + eo + j*d - pad]      with  eo + j*d - pad = f*sigma + ei
+//   =>  W'[sigma][eo*C + co][ei*C + ci] = w[co][ci][j]
+//
+// and the stride-s ConvTranspose1d into such a stage (f_out = s * f_in) becomes a plain conv on super-rows as well
+// (kk = eo - f_out*sigma - s*ei + pad).  The narrow stages therefore run on the same tensor-core kernels as C = 32 -- on
+// DENSE planes (no zero channels in HBM: 2x / 4x fewer bytes than carrying them padded to 32) and with 2-4x fewer MMA rows.
+// leaky_relu, the residual add and the MRF mean are elementwise and do not see the folding.
+// ---------------------------------------------------------------------------
+int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+int upload_layer(Layer& L);
+
+int build_folded(hfg_engine* e) {
+    for (auto& kv : e->folded) free_layer_dev(kv.second);
+    e->folded.clear();
+    const hfg_config& c = e->cfg;
+    const int c0 = c.upsample_initial_channel, NU = c.num_upsamples;
+    for (int i = 0; i < NU; ++i) e->stage_fold[i] = 1;
+    if (env_flag_early("HFG_FOLD", 1) == 0 || c0 % 32 != 0) return HFG_OK;
+    // every narrow stage must fold consistently with the stage before it: f_i == f_{i-1} * rate_i
+    bool ok = true, any = false;
+    int fold[HFG_MAX_UPSAMPLES];
+    for (int i = 0; i < NU; ++i) {
+        const int ch = c0 >> (i + 1);
+        fold[i] = (ch < 32 && 32 % ch == 0) ? 32 / ch : 1;
+        if (ch < 32 && 32 % ch != 0) ok = false;
+        const int prev = i > 0 ? fold[i - 1] : 1;
+        if (fold[i] > 1) { any = true; if (fold[i] != prev * c.upsample_rates[i]) ok = false; }
+        else if (prev != 1) ok = false;
+    }
+    if (!ok || !any) return HFG_OK;
+    for (int i = 0; i < NU; ++i) e->stage_fold[i] = fold[i];
+
+    auto make = [&](const Layer& o, int f_in, int f_out) -> int {
+        Layer F;
+        F.name = o.name; F.transposed = false; F.cin = f_in * o.cin; F.cout = f_out * o.cout; F.dil = 1; F.stride = 1; F.set = true;
+        const int Kin = F.cin, Nout = F.cout;
+        int smin = 1 << 30, smax = -(1 << 30);
+        struct Item { int sigma, eo, ei, j; };
+        std::vector<Item> items;
+        if (!o.transposed) {
+            for (int j = 0; j < o.k; ++j)
+                for (int eo = 0; eo < f_out; ++eo) {
+                    const int q = eo + j * o.dil - o.pad;
+                    const int sg = floor_div(q, f_out);
+                    items.push_back({sg, eo, q - sg * f_out, j});
+                }
+        } else {
+            for (int kk = 0; kk < o.k; ++kk)
+                for (int eo = 0; eo < f_out; ++eo)
+                    for (int ei = 0; ei < f_in; ++ei) {
+                        const int num = eo - o.stride * ei + o.pad - kk;
+                        if (((num % f_out) + f_out) % f_out != 0) continue;
+                        items.push_back({floor_div(num, f_out), eo, ei, kk});
+                    }
+        }
+        for (const Item& it : items) { smin = std::min(smin, it.sigma); smax = std::max(smax, it.sigma); }
+        const int taps = smax - smin + 1;
+        F.k = taps; F.pad = -smin;
+        F.taps = taps; F.tap_off0 = smin; F.tap_step = 1; F.Np = Nout; F.ups_s = 1; F.ups_p = 0;
+        F.kc = 32; F.cin_pad = Kin; F.cout_tc = Nout; F.Np_tc = Nout;
+        F.w.assign((size_t)Nout * Kin * taps, 0.f);   // torch Conv1d layout [cout][cin][k]
+        for (const Item& it : items)
+            for (int co = 0; co < o.cout; ++co)
+                for (int ci = 0; ci < o.cin; ++ci) {
+                    const float v = o.transposed ? o.w[((size_t)ci * o.cout + co) * o.k + it.j] : o.w[((size_t)co * o.cin + ci) * o.k + it.j];
+                    F.w[((size_t)(it.eo * o.cout + co) * Kin + (it.ei * o.cin + ci)) * taps + (it.sigma - smin)] = v;
+                }
+        F.bias.resize(Nout);
+        for (int n = 0; n < Nout; ++n) F.bias[n] = o.bias[n % o.cout];
+        RET(upload_layer(F));
+        e->folded[o.name] = std::move(F);
+        return HFG_OK;
+    };
+    char buf[64];
+    int n = 0;
+    for (int i = 0; i < NU; ++i) {
+        const int f = fold[i], f_prev = i > 0 ? fold[i - 1] : 1;
+        if (f > 1) {
+            snprintf(buf, sizeof buf, "ups.%d", i);
+            RET(make(e->layers[e->index[buf]], f_prev, f));
+        }
+        for (int j = 0; j < c.num_kernels; ++j, ++n)
+            for (int m = 0; m < c.num_dilations[j] && f > 1; ++m) {
+                snprintf(buf, sizeof buf, "resblocks.%d.convs1.%d", n, m);
+                RET(make(e->layers[e->index[buf]], f, f));
+                snprintf(buf, sizeof buf, "resblocks.%d.convs2.%d", n, m);
+                RET(make(e->layers[e->index[buf]], f, f));
+            }
+    }
+    return HFG_OK;
+}
+
 ConvGeom geom_of(const Layer& L, int B, int Lin) {
     ConvGeom g;
     g.B = B; g.Lin = Lin; g.Cin = L.cin; g.Cout = L.cout;
@@ -443,7 +551,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.bytes = ((double)L.cin * Lin + (double)L.cout * Lout) * B * act_bytes + (double)L.cin * L.cout * L.k * act_bytes;
     };
     // one conv on planes: persistent pipelined kernel where it applies, the v1 kernel otherwise
-    auto umma = [&](const Layer& L, int Lin, Planes x, Planes res, float* y_raw, Planes y) -> int {
+    auto umma = [&](const Layer& L, int Lin, Planes x, Planes res, float* y_raw, Planes y, const Layer* acct = nullptr,
+                    int acct_Lin = 0) -> int {
         if (!real) return HFG_OK;
         Step s{};
         UmmaConvParams p;
@@ -454,7 +563,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
         p.a_per_tap = a_per_tap;
         p.reverse = snake ? (n_umma2++ & 1) : 0;
-        work(s, L, Lin, x3 ? 4 : 2);   // two bf16 planes carry what an fp32 activation would
+        if (acct) work(s, *acct, acct_Lin, x3 ? 4 : 2);   // a time-folded twin: report the reference layer's algorithmic work
+        else work(s, L, Lin, x3 ? 4 : 2);   // two bf16 planes carry what an fp32 activation would
         if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, L.d_wb_hi, L.d_wb_lo, e->sm_count) == HFG_OK) {
             s.kind = S_UMMA2;
         } else {
@@ -465,12 +575,13 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         return HFG_OK;
     };
     // convs1[m] -> lrelu -> convs2[m] -> + x  (:66-70) as one launch where the fused kernel applies (C <= 64); false otherwise
-    auto pair = [&](const Layer& c1, const Layer& c2, int Lrows, Planes x, Planes y, char const* label) -> bool {
+    auto pair = [&](const Layer& c1, const Layer& c2, int Lrows, Planes x, Planes y, char const* label, const Layer* a1 = nullptr,
+                    const Layer* a2 = nullptr, int acct_L = 0) -> bool {
         if (!real) return false;
-        if (c1.cin_pad != c1.cout_tc || c2.cin_pad != c1.cin_pad || c2.cout_tc != c1.cout_tc || c1.k != c2.k || c2.dil != 1) return false;
+        if (c1.cin_pad != c1.cout_tc || c2.cin_pad != c1.cin_pad || c2.cout_tc != c1.cout_tc || c2.dil != 1) return false;
         PairParams p;
         memset(&p, 0, sizeof p);
-        p.B = B; p.L = Lrows; p.C = c1.cin_pad; p.k = c1.k; p.d = c1.dil; p.npass = npass;
+        p.B = B; p.L = Lrows; p.C = c1.cin_pad; p.k1 = c1.k; p.k2 = c2.k; p.d = c1.dil; p.npass = npass;
         p.bias1 = c1.d_bias_tc; p.bias2 = c2.d_bias_tc;
         p.x_hi = x.hi; p.x_lo = x3 ? x.lo : nullptr;
         p.w1_hi = c1.d_wb_hi; p.w1_lo = c1.d_wb_lo; p.w2_hi = c2.d_wb_hi; p.w2_lo = c2.d_wb_lo;
@@ -481,12 +592,15 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         if (plan_conv_pair(&s.pl, p, e->sm_count) != HFG_OK) return false;
         ++n_umma2;
         Step w2{};
-        work(s, c1, Lrows, x3 ? 4 : 2);
-        work(w2, c2, Lrows, x3 ? 4 : 2);
+        const Layer& r1 = a1 ? *a1 : c1;   // reference layers for the work model (time-folded twins report the originals)
+        const Layer& r2 = a2 ? *a2 : c2;
+        const int rL = a1 ? acct_L : Lrows;
+        work(s, r1, rL, x3 ? 4 : 2);
+        work(w2, r2, rL, x3 ? 4 : 2);
         // algorithmic bytes of the FUSED step: x in, out, both weight sets (the intermediate never leaves the SM)
         const double act_b = x3 ? 4.0 : 2.0;
         s.kind = S_PAIR; s.label = label; s.flops += w2.flops;
-        s.bytes = 2.0 * c1.cin * (double)Lrows * B * act_b + 2.0 * (double)c1.cin * c1.cout * c1.k * act_b;
+        s.bytes = 2.0 * r1.cin * (double)rL * B * act_b + 2.0 * (double)r1.cin * r1.cout * r1.k * act_b;
         plan->steps.push_back(std::move(s));
         return true;
     };
@@ -504,9 +618,9 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         Step s{}; s.kind = S_P2RAW; s.b_in = p.hi; s.b_in_lo = x3 ? p.lo : nullptr; s.f_out = raw; s.n = rows; s.cpad = C_tc; s.C = C;
         push(std::move(s));
     };
-    auto tap_planes = [&](const char* name, Planes p, int C, int L) {
+    auto tap_planes = [&](const char* name, Planes p, int C, int L, bool dense = false) {   // dense: time-folded stage, no padding channels
         if (!keep_taps) return;
-        to_raw(p, tap_tmp, (size_t)B * L, std::max(32, C), C);
+        to_raw(p, tap_tmp, (size_t)B * L, dense ? C : std::max(32, C), C);
         tap(name, tap_tmp, C, L);
     };
 
@@ -533,31 +647,41 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         const int Lin = L;
         L *= up.stride;
         const bool tc_stage = i < n_tc;
-        const size_t ne = (size_t)B * L * (tc_stage ? up.cout_tc : ch);
+        // time-folded stage (C < 32): dense planes [L][ch] read as [L/f][32] by the folded twins of its layers (build_folded)
+        const int f = tc_stage ? e->stage_fold[i] : 1;
+        const int f_prev = (tc_stage && i > 0) ? e->stage_fold[i - 1] : 1;
+        const bool fold = f > 1;
+        const int ctc = fold ? ch : up.cout_tc;          // channels per time step of this stage's planes
+        const size_t ne = (size_t)B * L * (tc_stage ? ctc : ch);
+        auto twin = [&](const Layer& o) -> const Layer& { return fold ? e->folded.at(o.name) : o; };
         if (tc_stage) {
             const bool last_stage = i == NU - 1;
             const bool next_tc = i + 1 < n_tc;
             const bool want_planes = next_tc || last_stage;   // conv_post reads planes after a tensor-core stage
             const bool want_raw = (!last_stage && !next_tc) || keep_taps;   // an fp32-family stage follows (or the stage tap)
-            RET(umma(up, Lin, xp, Planes(), nullptr, u_p));   // lrelu -> ups  (:127-128)
+            if (fold) RET(umma(twin(up), Lin / f_prev, xp, Planes(), nullptr, u_p, &up, Lin));
+            else RET(umma(up, Lin, xp, Planes(), nullptr, u_p));   // lrelu -> ups  (:127-128)
             snprintf(nm, sizeof nm, "ups.%d", i);
-            tap_planes(nm, u_p, ch, L);
+            tap_planes(nm, u_p, ch, L, fold);
+            const int rows = L / f;
             for (int j = 0; j < nk; ++j, ++n) {
                 Planes xin = u_p;
                 const int nd = c.num_dilations[j];
                 for (int m = 0; m < nd; ++m) {
-                    const Layer& c1 = layer("resblocks.%d.convs1.%d", n, m);
-                    const Layer& c2 = layer("resblocks.%d.convs2.%d", n, m);
+                    const Layer& o1 = layer("resblocks.%d.convs1.%d", n, m);
+                    const Layer& o2 = layer("resblocks.%d.convs2.%d", n, m);
+                    const Layer& c1 = twin(o1);
+                    const Layer& c2 = twin(o2);
                     Planes xout = m == nd - 1 ? r_p[j] : pp[m & 1];
                     snprintf(nm, sizeof nm, "resblocks.%d.pair.%d", n, m);
-                    if (!pair(c1, c2, L, xin, xout, nm)) {
-                        RET(umma(c1, L, xin, Planes(), nullptr, xt_p));               // :66-67 (+ :68 in the epilogue)
-                        RET(umma(c2, L, xt_p, xin, nullptr, xout));                   // :69-70
+                    if (!pair(c1, c2, rows, xin, xout, nm, fold ? &o1 : nullptr, fold ? &o2 : nullptr, L)) {
+                        RET(umma(c1, rows, xin, Planes(), nullptr, xt_p, fold ? &o1 : nullptr, L));   // :66-67 (+ :68 in the epilogue)
+                        RET(umma(c2, rows, xt_p, xin, nullptr, xout, fold ? &o2 : nullptr, L));       // :69-70
                     }
                     xin = xout;
                 }
                 snprintf(nm, sizeof nm, "resblocks.%d", n);
-                tap_planes(nm, r_p[j], ch, L);
+                tap_planes(nm, r_p[j], ch, L, fold);
             }
             const bool fuse_post = last_stage && !keep_taps;   // the MRF mean of the last stage is computed inside conv_post
             if (!fuse_post) {   // xs = sum_j r_j ; x = xs / nk  (:133-137)
@@ -565,13 +689,11 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                 memset(&s.mrf, 0, sizeof s.mrf);
                 for (int j = 0; j < nk; ++j) { s.mrf.hi[j] = r_p[j].hi; s.mrf.lo[j] = x3 ? r_p[j].lo : nullptr; }
                 s.mrf.nk = nk;
-                s.mrf.out_hi = want_planes ? s_p.hi : nullptr;
-                s.mrf.out_lo = (want_planes && x3) ? s_p.lo : nullptr;
-                s.mrf.out_raw = (want_raw && up.cout_tc == ch) ? xs : nullptr;
-                s.mrf.out_hi = (want_planes || up.cout_tc != ch) ? s_p.hi : nullptr;
-                s.mrf.out_lo = ((want_planes || up.cout_tc != ch) && x3) ? s_p.lo : nullptr;
+                s.mrf.out_raw = (want_raw && ctc == ch) ? xs : nullptr;
+                s.mrf.out_hi = (want_planes || ctc != ch) ? s_p.hi : nullptr;
+                s.mrf.out_lo = ((want_planes || ctc != ch) && x3) ? s_p.lo : nullptr;
                 push(std::move(s));
-                if (want_raw && up.cout_tc != ch) to_raw(s_p, xs, (size_t)B * L, up.cout_tc, ch);
+                if (want_raw && ctc != ch) to_raw(s_p, xs, (size_t)B * L, ctc, ch);
             }
             snprintf(nm, sizeof nm, "stage.%d", i);
             tap(nm, xs, ch, L);
@@ -613,7 +735,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.w = post.d_w32; s.bias = post.d_bias; s.f_out = pass ? wave_dev : post_tap;
         s.B = B; s.L = L; s.C = post.cin; s.k = post.k; s.flag0 = 1; s.flag1 = pass;
         if (post_planes) {
-            s.w = post.d_w32_tc; s.C = post.cin_pad;
+            const bool dense = e->stage_fold[NU - 1] > 1;   // time-folded last stage: planes carry the real channels only
+            s.w = dense ? post.d_w32 : post.d_w32_tc; s.C = dense ? post.cin : post.cin_pad;
             // One kernel for both plans (identical arithmetic order): the production plan hands it the nk branch outputs and
             // it forms the MRF mean itself; the tap plan hands it the already combined stage planes (nk = 1).
             s.kind = S_POSTMRF;
@@ -778,6 +901,7 @@ void hfg_destroy(hfg_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& L : e->layers) free_layer_dev(L);
+    for (auto& kv : e->folded) free_layer_dev(kv.second);
     for (auto& kv : e->taps) cudaFree(kv.second.dev);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     cudaFree(e->arena);
@@ -847,6 +971,7 @@ int hfg_finalize(hfg_engine* e) {
     CK(cudaStreamSynchronize(e->stream));
     e->plans.clear();
     for (auto& L : e->layers) RET(upload_layer(L));
+    RET(build_folded(e));
     e->finalized = true;
     return HFG_OK;
 }
@@ -1039,7 +1164,7 @@ int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int
     CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, C, L, Cp, 1, st));
     PairParams pp;
     memset(&pp, 0, sizeof pp);
-    pp.B = B; pp.L = L; pp.C = Cp; pp.k = c1->k; pp.d = c1->dil; pp.npass = x3 ? 3 : 1;
+    pp.B = B; pp.L = L; pp.C = Cp; pp.k1 = c1->k; pp.k2 = c2->k; pp.d = c1->dil; pp.npass = x3 ? 3 : 1;
     pp.bias1 = c1->d_bias_tc; pp.bias2 = c2->d_bias_tc;
     pp.x_hi = a_hi; pp.x_lo = x3 ? a_lo : nullptr;
     pp.w1_hi = c1->d_wb_hi; pp.w1_lo = c1->d_wb_lo; pp.w2_hi = c2->d_wb_hi; pp.w2_lo = c2->d_wb_lo;

@@ -136,7 +136,8 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s);
 // hifigan_pretrained.py:66-70 as one kernel: the intermediate stays in shared memory, the residual comes from the staged x tile.
 struct PairParams {
     int B, L, C;          // planes are [B][L][C] bf16, C = 32 or 64 (already channel-padded)
-    int k, d;             // c1: k taps, dilation d ; c2: k taps, dilation 1 ; both 'same'-padded
+    int k1, k2, d;        // c1: k1 taps, dilation d ; c2: k2 taps, dilation 1 ; both 'same'-padded (k1 = k2 for a reference ResBlock;
+                          // they differ for the time-folded narrow stages, engine.cu)
     int npass;            // 1: bf16 ; 3: bf16x3
     int reverse;
     const float* bias1;

@@ -43,8 +43,8 @@ constexpr uint32_t kSmemMax = 227u * 1024u - 2048u;   // dynamic smem; barriers 
 
 struct PairArgs {
     int B, L, N;                 // N = C = 32 or 64 (operand rows of 64 / 128 bytes)
-    int k, d, h1, h2;            // c1: k taps, dilation d, halo h1 = d(k-1)/2 ; c2: k taps, dilation 1, halo h2 = (k-1)/2
-    int planes, mt, R, V;        // R = 128*mt conv rows per tile, V = R - (k-1) valid output rows
+    int k1, k2, d, h1, h2;       // c1: k1 taps, dilation d, halo h1 = d(k1-1)/2 ; c2: k2 taps, dilation 1, halo h2 = (k2-1)/2
+    int planes, mt, R, V;        // R = 128*mt conv rows per tile, V = R - (k2-1) valid output rows
     int tiles_per_item, total_tiles;
     int x_rows, x_box_rows, x_pieces;
     int n_x, n_t, n_o;
@@ -199,11 +199,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     if (warp == 0) {
         // ===== producer: resident weights of both convs, then the x ring =====
         if (lane == 0) {
-            mbar_expect_tx(bar_w, (uint32_t)(2 * a.k * planes) * (uint32_t)a.N * row_bytes);
+            mbar_expect_tx(bar_w, (uint32_t)((a.k1 + a.k2) * planes) * (uint32_t)a.N * row_bytes);
             for (int cv = 0; cv < 2; ++cv)
-                for (int j = 0; j < a.k; ++j)
+                for (int j = 0; j < (cv ? a.k2 : a.k1); ++j)
                     for (int pl = 0; pl < planes; ++pl)
-                        tma_load_2d(smem_w + (uint32_t)(cv * a.k + j) * w_stage + pl * a.w_plane_bytes,
+                        tma_load_2d(smem_w + (uint32_t)(cv * a.k1 + j) * w_stage + pl * a.w_plane_bytes,
                                     cv ? (pl ? &map_w2_lo : &map_w2_hi) : (pl ? &map_w1_lo : &map_w1_hi), bar_w, 0, j * a.N);
             int sx = 0;
             uint32_t px = 0;
@@ -242,11 +242,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             const bool k4 = a.N == 64;
             const uint32_t a_tap = (uint32_t)(cv ? 1 : a.d) * (row_bytes >> 4);
             const uint32_t w_tap = w_stage >> 4;
-            const uint32_t w_lo = desc_lo(smem_w + (uint32_t)(cv * a.k) * w_stage);
+            const uint32_t w_lo = desc_lo(smem_w + (uint32_t)(cv * a.k1) * w_stage);
             const uint32_t a_stage = cv ? t_stage : x_stage;
             const uint32_t a_ring = desc_lo(cv ? smem_t : smem_x) + (uint32_t)ms * sub_step;
             const uint32_t d_base = tmem_base + (uint32_t)(cv * 2 * acc_cols + ms * a.acc_n);
-            const int k = a.k, n_t = a.n_t, n_x = a.n_x;
+            const int k = cv ? a.k2 : a.k1, n_t = a.n_t, n_x = a.n_x;
             const bool dbg_nomma = a.dbg == 2;
             mbar_wait(bar_w, 0);
             int sx = 0;
@@ -509,11 +509,11 @@ struct PairLaunch::Impl {
 bool pair_supported(const PairParams& p) {
     if (penv("HFG_PAIR", 1) == 0) return false;
     if (p.C != 32 && p.C != 64) return false;
-    if (p.k < 1 || p.k > 15 || p.k % 2 == 0 || p.d < 1) return false;
+    if (p.k1 < 1 || p.k1 > 31 || p.k1 % 2 == 0 || p.k2 < 1 || p.k2 > 15 || p.k2 % 2 == 0 || p.d < 1) return false;
     if (p.npass != 1 && p.npass != 3) return false;
     const int maxc = penv(p.npass == 3 ? "HFG_PAIR_MAXC_X3" : "HFG_PAIR_MAXC", 64);
-    const int maxk = penv(p.npass == 3 ? "HFG_PAIR_MAXK_X3" : "HFG_PAIR_MAXK", 15);
-    if (p.C > maxc || p.k > maxk) return false;
+    const int maxk = penv(p.npass == 3 ? "HFG_PAIR_MAXK_X3" : "HFG_PAIR_MAXK", 31);
+    if (p.C > maxc || std::max(p.k1, p.k2) > maxk) return false;
     return true;
 }
 
@@ -526,8 +526,8 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     const int planes = p.npass > 1 ? 2 : 1;
     const int N = p.C;
     const uint32_t row_bytes = (uint32_t)N * 2u;
-    a.B = p.B; a.L = p.L; a.N = N; a.k = p.k; a.d = p.d;
-    a.h1 = p.d * (p.k - 1) / 2; a.h2 = (p.k - 1) / 2;
+    a.B = p.B; a.L = p.L; a.N = N; a.k1 = p.k1; a.k2 = p.k2; a.d = p.d;
+    a.h1 = p.d * (p.k1 - 1) / 2; a.h2 = (p.k2 - 1) / 2;
     a.planes = planes;
     a.concat = (planes == 2 && N == 32) ? 1 : 0;
     a.acc_n = a.concat ? 2 * N : N;
@@ -538,7 +538,7 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     a.w_plane_bytes = rup((uint32_t)N * row_bytes, 1024);
     if (a.concat && a.w_plane_bytes != (uint32_t)N * row_bytes) return HFG_ERR_UNSUPPORTED;
     a.o_plane_bytes = 32u * row_bytes;
-    const uint32_t w_all = (uint32_t)(2 * p.k) * a.w_plane_bytes * planes;
+    const uint32_t w_all = (uint32_t)(p.k1 + p.k2) * a.w_plane_bytes * planes;
     const uint32_t budget = kSmemMax - 1024;   // alignment slack
 
     // Choose (MT, x ring depth, t buffers, staging slots per warp): cycles per valid output row of a tile interval, the
@@ -553,14 +553,14 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     for (int mt = 2; mt >= 1; --mt) {
         if (f_mt && mt != f_mt) continue;
         if (4 * mt * a.acc_n > 512) continue;
-        const int R = 128 * mt, V = R - (p.k - 1);
+        const int R = 128 * mt, V = R - (p.k2 - 1);
         if (V < 64) continue;
         const int rows_need = R + 2 * a.h1;
         const int pieces = (rows_need + 255) / 256;
         const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
         const uint32_t x_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
         const uint32_t t_plane = rup((uint32_t)((R + 2 * a.h2 + 7) / 8 * 8) * row_bytes, 1024);
-        const double t_mma = 2.0 * mt * p.k * ksteps * step_clk;
+        const double t_mma = (double)mt * (p.k1 + p.k2) * ksteps * step_clk;
         const double t_hbm = ((double)rows_need + V) * row_bytes * planes / 20.0;
         const double t_epi = (double)mt * (N / 32) * (planes > 1 ? 1100.0 : 600.0);   // both epilogues share an SM sub-partition
         const double t_int = std::max({t_mma, t_hbm, t_epi}) + 300.0;
@@ -603,7 +603,7 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     // the two-launch plan (C = 64, k = 7: 0.256 vs 0.245 ms; bf16x3 C = 32, k = 11, d = 5: 0.80 vs 0.77 ms).  Leave those unfused.
     if (a.n_t == 1 && !f_nt && !penv("HFG_PAIR_ALLOW_NT1", 0)) return HFG_ERR_UNSUPPORTED;
     if (penv("HFG_PAIR_VERBOSE", 0))
-        fprintf(stderr, "pair plan C=%d k=%d d=%d planes=%d: mt=%d V=%d n_x=%d n_t=%d n_o=%d x_rows=%d smem=%zu cost=%.2f\n", N, p.k, p.d,
+        fprintf(stderr, "pair plan C=%d k=%d,%d d=%d planes=%d: mt=%d V=%d n_x=%d n_t=%d n_o=%d x_rows=%d smem=%zu cost=%.2f\n", N, p.k1, p.k2, p.d,
                 planes, a.mt, a.V, a.n_x, a.n_t, a.n_o, a.x_rows, I->smem, best);
     a.tiles_per_item = (p.L + a.V - 1) / a.V;
     a.total_tiles = a.tiles_per_item * p.B;
@@ -617,17 +617,18 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
         if (!pair_encode(&I->map_x[1], planes > 1 ? p.x_lo : p.x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)N, (uint64_t)p.k * N};
+        const uint64_t dims1[2] = {(uint64_t)N, (uint64_t)p.k1 * N};
+        const uint64_t dims2[2] = {(uint64_t)N, (uint64_t)p.k2 * N};
         const uint64_t str[1] = {(uint64_t)N * 2};
         const uint32_t box[2] = {(uint32_t)N, (uint32_t)N};
-        if (!pair_encode(&I->map_w1[0], p.w1_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
-        if (!pair_encode(&I->map_w1[1], planes > 1 ? p.w1_lo : p.w1_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
-        if (!pair_encode(&I->map_w2[0], p.w2_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
-        if (!pair_encode(&I->map_w2[1], planes > 1 ? p.w2_lo : p.w2_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_w1[0], p.w1_hi, 2, dims1, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_w1[1], planes > 1 ? p.w1_lo : p.w1_hi, 2, dims1, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_w2[0], p.w2_hi, 2, dims2, str, box, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_w2[1], planes > 1 ? p.w2_lo : p.w2_hi, 2, dims2, str, box, row_bytes)) return HFG_ERR_CUDA;
     }
     {
         const int pr = a.paired ? 2 : 1;
-        const int tail = 32 - (p.k - 1);   // rows of the one partial box per tile (k-1 is even, so paired boxes stay whole)
+        const int tail = 32 - (p.k2 - 1);   // rows of the one partial box per tile (k2-1 is even, so paired boxes stay whole)
         const uint64_t ydims[3] = {(uint64_t)N * pr, (uint64_t)p.L / pr, (uint64_t)p.B};
         const uint64_t ystr[2] = {(uint64_t)N * pr * 2, (uint64_t)p.L * N * 2};
         const uint32_t ybox[3] = {(uint32_t)N * pr, (uint32_t)(32 / pr), 1};
