@@ -234,9 +234,10 @@ def test_golden_end_to_end(case, mode):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
-@pytest.mark.parametrize("case", ["v1_loud", "v3_loud"])
+@pytest.mark.parametrize("case", ["v1_loud", "v2_loud", "v3_loud"])
 def test_golden_intermediate_activations(case, mode):
-    """HFG_KEEP_TAPS exposes conv_pre / ups.i / resblocks.n / conv_post like forward hooks on the reference modules."""
+    """HFG_KEEP_TAPS exposes conv_pre / ups.i / resblocks.n / conv_post like forward hooks on the reference modules.
+    (v2: the 16- and 8-channel stages run time-folded on dense planes -- every tap of those stages is checked too.)"""
     z, meta, name = _case(case)
     eng, _ = _engine(name, loud=True)
     B, T = meta["B"], meta["T"]
@@ -268,6 +269,31 @@ def test_batched_layer_matches_single_items():
             y = eng.run_layer(name, x, pre_lrelu=True, precision=mode)
             for b in (0, 4):
                 np.testing.assert_array_equal(y[b], eng.run_layer(name, x[b:b + 1], pre_lrelu=True, precision=mode)[0])
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_time_folded_narrow_stages_match_padded_plan(mode):
+    """V2's C = 16 / 8 stages: dense planes read as [L/f][32] with folded weights (engine.cu build_folded) against the plan that
+    carries them padded to 32 channels (HFG_FOLD=0).  Same products, different accumulation grouping: equal to fp32 rounding in
+    bf16x3; in bf16 the operand rounding is identical, so the results agree to the same level."""
+    from iris_tts_b200 import Engine
+    from iris_tts_b200.engine import V2
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    mel = O.synthetic_mel(3, 37, seed=11)
+    outs = []
+    for fold in ("1", "0"):
+        os.environ["HFG_FOLD"] = fold
+        try:
+            eng = Engine(V2, 0)
+            eng.load_state_dict(sd, strict=True)
+            eng.finalize()
+            outs.append(eng.forward(mel, precision=mode))
+            eng.close()
+        finally:
+            del os.environ["HFG_FOLD"]
+    ref = O.infer(sd, mel, O.V2)
+    assert np.abs(outs[0] - ref).max() <= E2E_TOL[mode]
+    assert np.abs(outs[0] - outs[1]).max() <= (1e-4 if mode == "bf16x3" else 2e-2)
 
 
 def test_fused_plan_equals_tapped_plan_bitwise():
