@@ -202,6 +202,31 @@ def _pair_edges(eng, w, mode):
                 np.testing.assert_array_equal(y, y2, err_msg=f"resblocks.{n} pair {m} L={L}")
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_v3_resblock_pairs_wide_dilations(mode):
+    """V3-args ResBlocks: k = 3 / 5 / 7 with dilations up to 12 (x halo of 36 rows each side, two TMA pieces) at C = 64 and 32."""
+    eng, sd = _engine("v3")
+    w = O.folded_weights(sd)
+    ks, dils = (3, 5, 7), ((1, 2), (2, 6), (3, 12))
+    for n, m in ((3, 1), (4, 1), (5, 0), (5, 1), (6, 0), (7, 1), (8, 1)):
+        C = 256 >> (n // 3 + 1)
+        k, d = ks[n % 3], dils[n % 3][m]
+        for L in (250, 1037):
+            torch.manual_seed(n * 10 + m + L)
+            x = torch.randn(2, C, L)
+            ref = _pair_ref(w, n, m, k, d, x)
+            y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
+            tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
+            assert np.abs(y - ref).max() <= tol, (n, m, L, fused)
+            if fused:
+                os.environ["HFG_PAIR"] = "0"
+                try:
+                    y2, _ = eng.run_pair(n, m, x.numpy(), precision=mode)
+                finally:
+                    del os.environ["HFG_PAIR"]
+                np.testing.assert_array_equal(y, y2, err_msg=f"v3 resblocks.{n} pair {m} L={L}")
+
+
 def test_resblock_pair_batch_items_are_independent():
     eng, _ = _engine("v1")
     torch.manual_seed(5)
