@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "hfg_internal.h"
+#include "umma_ptx.cuh"
 
 namespace hfg {
 
@@ -337,26 +338,28 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat
 // hifigan_pretrained.py:133-136, x_j = inverse-lrelu(plane j).
 template <int NK, bool LO>
 __device__ __forceinline__ void mrf_sum8(const MrfArgs& a, size_t i8, float (&v)[8]) {
+    using namespace ptx;
     uint4 h[NK], l[NK];
 #pragma unroll
     for (int j = 0; j < NK; ++j) {
         h[j] = __ldg(reinterpret_cast<const uint4*>(a.hi[j]) + i8);
         if (LO) l[j] = __ldg(reinterpret_cast<const uint4*>(a.lo[j]) + i8);
     }
+    f2 acc[4];   // packed pairs (FADD2 / FMUL2): same values as the scalar form, half the instructions
 #pragma unroll
     for (int j = 0; j < NK; ++j) {
         const uint32_t w[4] = {h[j].x, h[j].y, h[j].z, h[j].w};
-        float f[8];
+        const uint32_t wl[4] = {LO ? l[j].x : 0u, LO ? l[j].y : 0u, LO ? l[j].z : 0u, LO ? l[j].w : 0u};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { f[2 * t] = __uint_as_float(w[t] << 16); f[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u); }
-        if (LO) {
-            const uint32_t wl[4] = {l[j].x, l[j].y, l[j].z, l[j].w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { f[2 * t] += __uint_as_float(wl[t] << 16); f[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u); }
+        for (int t = 0; t < 4; ++t) {
+            f2 f = f2_from_bf16x2(w[t]);
+            if (LO) f = f2_add(f, f2_from_bf16x2(wl[t]));
+            f = f2_inv_lrelu(f);
+            acc[t] = j == 0 ? f : f2_add(acc[t], f);
         }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = j == 0 ? inv_lrelu(f[t]) : v[t] + inv_lrelu(f[t]);
     }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) f2_unpack(acc[t], v[2 * t], v[2 * t + 1]);
 }
 // runtime nk -> the specialised sum (nk = 3 is every shipped config); false: caller runs the generic loop
 __device__ __forceinline__ bool mrf_sum8_dispatch(const MrfArgs& a, size_t i8, float (&v)[8]) {

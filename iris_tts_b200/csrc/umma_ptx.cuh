@@ -161,6 +161,36 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 
+// ---- packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogues are issue-bound, a pair costs one instruction ----
+typedef uint64_t f2;   // two fp32 in one 64-bit register pair
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 f2_bits(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// leaky_relu(v, 0.1) = max(v, 0.1 v) and its inverse p > 0 ? p : 10 p = min(p, 10 p): the same values as the select forms
+__device__ __forceinline__ f2 f2_lrelu(f2 v) {
+    float a, b, sa, sb;
+    f2_unpack(v, a, b);
+    f2_unpack(f2_mul(v, f2_pack(kLreluSlope, kLreluSlope)), sa, sb);
+    return f2_pack(fmaxf(a, sa), fmaxf(b, sb));
+}
+__device__ __forceinline__ f2 f2_inv_lrelu(f2 p) {
+    float a, b, ta, tb;
+    f2_unpack(p, a, b);
+    f2_unpack(f2_mul(p, f2_pack(1.0f / kLreluSlope, 1.0f / kLreluSlope)), ta, tb);
+    return f2_pack(fminf(a, ta), fminf(b, tb));
+}
+// two bf16 (channels 2i, 2i+1 of one 32-bit word) -> fp32 pair
+__device__ __forceinline__ f2 f2_from_bf16x2(uint32_t w) { return f2_bits(w << 16, w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f2 v) {
+    float a, b;
+    f2_unpack(v, a, b);
+    return pack_bf16(a, b);
+}
+
 // ---- programmatic dependent launch: the prologue (barriers, TMEM, weights) of kernel N+1 overlaps the tail of kernel N ----
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
