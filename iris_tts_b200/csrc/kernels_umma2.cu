@@ -51,6 +51,7 @@ struct K2Args {
     int ecols, groups;
     int ups;      // polyphase ConvTranspose1d (k = 2s, N = s*C_out <= 256): GEMM row m, column half h lands on output half-row
                   // 2m - 1 + h of [B][2*L_in][N/2]; the two column groups ARE the halves, stored through a 4-D tensor map
+    int n_tiles, n_total;   // wide upsampler: the N = s*C_out columns are walked in n_tiles tiles of a.N columns (n_total = n_tiles * a.N)
     int cout;     // bias index = column % cout
     int reverse;  // walk the tiles last-to-first: consecutive kernels alternate, so the part of the input the previous kernel wrote
                   // last (still in the 126 MB L2) is the part this kernel reads first
@@ -164,7 +165,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const uint32_t bar_acc_empty = bp;         bp += 16;
     const uint32_t bar_wres = bp;
 
-    for (int i = threadIdx.x; i < a.N; i += blockDim.x) bias_s[i] = a.bias[i % a.cout];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) bias_s[i] = a.bias[i % a.cout];   // column n of the GEMM -> bias[n % cout]
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_y_hi);
         if (kHasRes) prefetch_tmap(&map_r_hi);
@@ -208,8 +209,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             pdl_wait();   // activations of the previous kernel are complete and visible from here on
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
-                const int b = tl / a.tiles_per_item;
-                const int m0 = (tl - b * a.tiles_per_item) * a.mt * 128;
+                const int tm = tl / a.n_tiles, n0 = (tl - tm * a.n_tiles) * a.N;   // column tile fastest: neighbours share the A tile in L2
+                const int b = tm / a.tiles_per_item;
+                const int m0 = (tm - b * a.tiles_per_item) * a.mt * 128;
                 for (int c = 0; c < a.nchunks; ++c) {
                     if (a.dbg != 3) {
                         mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
@@ -226,7 +228,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             mbar_expect_tx(bar_w_full + 8 * sw, (uint32_t)a.N * row_bytes * planes);
                             for (int pl = 0; pl < planes; ++pl)
                                 tma_load_2d(smem_w + sw * w_stage_bytes + pl * a.w_plane_bytes, pl ? &map_w_lo : &map_w_hi,
-                                            bar_w_full + 8 * sw, c * a.kc, j * a.N);
+                                            bar_w_full + 8 * sw, c * a.kc, j * a.n_total + n0);
                             if (++sw == a.n_w) { sw = 0; pw ^= 1u; }
                         }
                     }
@@ -299,7 +301,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t pe = 0;
             pdl_wait();
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+                const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;   // (a residual implies n_tiles == 1)
                 const int b = tl / a.tiles_per_item;
                 const int m0 = (tl - b * a.tiles_per_item) * a.mt * 128;
                 for (int ms = 0; ms < a.mt; ++ms) {
@@ -345,8 +347,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         int it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
-            const int b = tl / a.tiles_per_item;
-            const int m0 = (tl - b * a.tiles_per_item) * a.mt * 128;
+            const int tm = tl / a.n_tiles, n0 = (tl - tm * a.n_tiles) * a.N;
+            const int b = tm / a.tiles_per_item;
+            const int m0 = (tm - b * a.tiles_per_item) * a.mt * 128;
+            const int boff = n0 % a.cout;                     // bias of tile column c: bias_s[boff + c]
             const int buf = it & 1;
             mbar_wait(bar_acc_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
@@ -367,6 +371,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (kHasRes) mbar_wait(bar_e_full + 8 * se, pe);
                     else mbar_wait(bar_e_empty + 8 * se, pe ^ 1u);
                     const uint32_t slot = smem_e + se * e_slot_bytes;
+                    // upsampler: column n0 + g*ecols of the s*C_out GEMM columns -> (half-row parity, column inside the half-row)
+                    const int ucol = n0 + g * a.ecols;
+                    const int uhalf = a.ups ? ucol / (a.n_total / 2) : 0;
+                    const int ucg = a.ups ? ucol - uhalf * (a.n_total / 2) : 0;
                     for (int h = 0; h < (a.dbg == 5 ? 0 : halves); ++h) {
                         uint32_t r[32];
                         const int col = g * a.ecols + h * 32;
@@ -396,7 +404,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float4 bv = *reinterpret_cast<const float4*>(&bias_s[col + 4 * i]);
+                            const float4 bv = *reinterpret_cast<const float4*>(&bias_s[boff + col + 4 * i]);
                             v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bv.x;
                             v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv.y;
                             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv.z;
@@ -422,10 +430,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             hi.z = pack_bf16(v[cidx * 8 + 4], v[cidx * 8 + 5]);
                             hi.w = pack_bf16(v[cidx * 8 + 6], v[cidx * 8 + 7]);
                             sts128(addr[cidx], hi);
-                            const bool direct = a.ups && g == 0 && row0 + q * 32 == 0;   // box would start at q = -1: TMA stores fault there
-                            const size_t doff = direct && row >= 1
-                                ? ((((size_t)b * (a.L - 1) + (size_t)(row - 1)) * 2 + 1) * (size_t)(a.N / 2) + (size_t)(h * 32 + cidx * 8)) : 0;
-                            if (direct && row >= 1) *reinterpret_cast<uint4*>(a.y_hi + doff) = hi;
+                            const bool direct = a.ups && uhalf == 0 && row0 + q * 32 == 0;   // box would start at q = -1: TMA stores fault there
+                            const bool dwrite = direct && row >= 1 && row < a.L;   // GEMM rows 1 .. L_in of this box (plain stores are not clipped)
+                            const size_t doff = dwrite
+                                ? ((((size_t)b * (a.L - 1) + (size_t)(row - 1)) * 2 + 1) * (size_t)(a.n_total / 2) + (size_t)(ucg + h * 32 + cidx * 8)) : 0;
+                            if (dwrite) *reinterpret_cast<uint4*>(a.y_hi + doff) = hi;
                             if (planes > 1) {
                                 float fh[8];
                                 unpack8(hi, fh);
@@ -435,7 +444,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                                 lo.z = pack_bf16(v[cidx * 8 + 4] - fh[4], v[cidx * 8 + 5] - fh[5]);
                                 lo.w = pack_bf16(v[cidx * 8 + 6] - fh[6], v[cidx * 8 + 7] - fh[7]);
                                 sts128(addr[cidx] + a.e_plane_bytes, lo);
-                                if (direct && row >= 1) *reinterpret_cast<uint4*>(a.y_lo + doff) = lo;
+                                if (dwrite) *reinterpret_cast<uint4*>(a.y_lo + doff) = lo;
                             }
                         }
                     }
@@ -445,13 +454,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         mbar_arrive(bar_e_empty + 8 * se);
                     } else if (lane == 0) {
                         for (int pl = 0; pl < planes; ++pl) {
-                            // half g of GEMM rows m..m+31 -> (r, q) = (1, m - 1) for g = 0, (0, m) for g = 1.  TMA stores fault on a
+                            // half h of GEMM rows m..m+31 -> (r, q) = (1, m - 1) for h = 0, (0, m) for h = 1.  TMA stores fault on a
                             // negative start coordinate (measured), so the one box per item that starts at q = -1 was written
                             // with plain stores above (31 rows; GEMM row 0's first half lies before the sequence).
-                            if (a.ups && row0 + q * 32 - 1 + g < 0)
+                            if (a.ups && row0 + q * 32 - 1 + uhalf < 0)
                                 continue;
                             else if (a.ups)
-                                tma_store_4d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, 0, 1 - g, row0 + q * 32 - 1 + g, b);
+                                tma_store_4d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, ucg, 1 - uhalf, row0 + q * 32 - 1 + uhalf, b);
                             else
                                 tma_store_3d(pl ? &map_y_lo : &map_y_hi, slot + pl * a.e_plane_bytes + warp_off, g * a.ecols, (row0 + q * 32) >> rshift, b);
                         }
@@ -546,7 +555,8 @@ bool umma2_supported(const UmmaConvParams& p) {
     } else {   // polyphase upsampler with k = 2s (two taps, pad = s/2) whose whole N = s*C_out fits one tile
         if (env_i("HFG_U2_UPS", 1) == 0) return false;
         if (g.taps != 2 || g.tap_off0 != 0 || g.tap_step != -1 || g.ups_s % 2 != 0 || g.ups_p * 2 != g.ups_s) return false;
-        if (g.Np != g.ups_s * g.Cout || g.Np > 128 || g.Np % 64 != 0 || p.res_hi) return false;   // halves of <= 64 columns
+        if (g.Np != g.ups_s * g.Cout || g.Np % 64 != 0 || p.res_hi) return false;   // halves of <= 64 columns, or
+        if (g.Np > 128 && (g.Np % 256 != 0 || env_i("HFG_U2_UPS_WIDE", 1) == 0)) return false;   // wide: 128-column tiles, each inside one half
     }
     return true;
 }
@@ -561,7 +571,9 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     memset(&a, 0, sizeof a);
     const int planes = p.npass > 1 ? 2 : 1;
     const bool ups = g.ups_s > 1;
-    const int N = g.Np;                 // C_out, or s * C_out for the polyphase upsampler
+    const int N = (ups && g.Np > 128) ? 128 : g.Np;   // C_out, or s * C_out for the polyphase upsampler (wide ones: 128-column tiles)
+    const int n_tiles = g.Np / N;
+    a.n_tiles = n_tiles; a.n_total = g.Np;
     a.B = g.B; a.L = g.Mrows; a.N = N;   // GEMM rows per item (L_in + 1 for the upsampler: the last row only feeds its first half)
     a.ups = ups ? 1 : 0; a.cout = g.Cout;
     a.taps = g.taps; a.tap_off0 = g.tap_off0; a.tap_step = g.tap_step;
@@ -624,7 +636,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
             // epilogue: ~(250 + 120 per residual plane) issue cycles per 32-column step and warp, 4 warps in parallel
             const double t_epi = (double)mt * (N / 32) * (260.0 + (a.has_res ? 110.0 : 0.0) * planes + (planes > 1 ? 120.0 : 0.0)) + boxes * 150.0;
             for (int resident = 1; resident >= 0; --resident) {
-                if (resident && w_all > 140u * 1024u) continue;
+                if (resident && (w_all > 140u * 1024u || n_tiles > 1)) continue;   // every column tile has its own weights
                 if (force_res >= 0 && resident != force_res) continue;
                 const double w_bytes_tile = resident ? 0.0 : (double)w_all;
                 // streamed weights also cost one barrier round trip per (chunk, tap) in every issuer
@@ -646,7 +658,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
                             const double f_e = a.has_res ? std::max(0.6, std::min(1.0, std::max(0.5, (double)(n_e - pend - 1)) * (t_int / boxes) / lat_hbm))
                                                          : (n_e - pend >= 1 ? 1.0 : 0.5);
                             // small problems: a partly filled last wave of the persistent grid idles SMs (favours smaller tiles)
-                            const long tiles = (long)((g.Mrows + mt * 128 - 1) / (mt * 128)) * g.B;
+                            const long tiles = (long)((g.Mrows + mt * 128 - 1) / (mt * 128)) * g.B * n_tiles;
                             const long waves = (tiles + sm_count - 1) / std::max(1, sm_count);
                             const double fill = (double)tiles / (double)(waves * std::max(1, sm_count));
                             const double cost = t_int / std::min({f_a, f_w, f_e}) / (mt * 128.0) / fill;
@@ -675,7 +687,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     const uint32_t row_bytes = (uint32_t)a.kc * 2u;
     if (!ok) return HFG_ERR_UNSUPPORTED;
     a.tiles_per_item = (g.Mrows + a.mt * 128 - 1) / (a.mt * 128);
-    a.total_tiles = a.tiles_per_item * g.B;
+    a.total_tiles = a.tiles_per_item * g.B * n_tiles;
     I->grid = std::min(a.total_tiles, std::max(1, sm_count));
 
     const uint64_t dims3[3] = {(uint64_t)g.Cin, (uint64_t)g.Lin, (uint64_t)g.B};
@@ -686,7 +698,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
         if (!encode(&I->map_a[1], planes > 1 ? x_lo : x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)p.cin_pad, (uint64_t)g.taps * N};
+        const uint64_t dims[2] = {(uint64_t)p.cin_pad, (uint64_t)g.taps * g.Np};
         const uint64_t str[1] = {(uint64_t)p.cin_pad * 2};
         const uint32_t box[2] = {(uint32_t)a.kc, (uint32_t)N};
         if (!encode(&I->map_w[0], w_hi, 2, dims, str, box, row_bytes)) return HFG_ERR_CUDA;
@@ -705,9 +717,10 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
         if (!encode(&I->map_r[0], r0, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
         if (!encode(&I->map_r[1], r1, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
         if (ups) {   // output [B][L_in * s][C_out] viewed as [B][L_in][2][N/2]: (half-row parity r, q = half-row / 2)
-            const uint64_t ud[4] = {(uint64_t)N / 2, 2, (uint64_t)g.Lin, (uint64_t)g.B};
-            const uint64_t us[3] = {(uint64_t)N, (uint64_t)N * 2, (uint64_t)g.Lin * N * 2};
-            const uint32_t ub[4] = {(uint32_t)N / 2, 1, 32, 1};
+            const uint64_t NT = (uint64_t)g.Np;
+            const uint64_t ud[4] = {NT / 2, 2, (uint64_t)g.Lin, (uint64_t)g.B};
+            const uint64_t us[3] = {NT, NT * 2, (uint64_t)g.Lin * NT * 2};
+            const uint32_t ub[4] = {(uint32_t)a.ecols, 1, 32, 1};
             if (!encode(&I->map_y[0], p.y_act, 4, ud, us, ub, eb)) return HFG_ERR_CUDA;
             if (!encode(&I->map_y[1], planes > 1 ? p.y_act_lo : p.y_act, 4, ud, us, ub, eb)) return HFG_ERR_CUDA;
         } else {
