@@ -38,7 +38,7 @@ namespace {
 using namespace ptx;
 
 constexpr int kThreads = 768;   // 24 warps: the epilogues are issue-latency-bound, two groups of each alternate tiles
-constexpr int kMaxX = 8;
+constexpr int kMaxX = 8, kMaxW2 = 8;
 constexpr uint32_t kSmemMax = 227u * 1024u - 2048u;   // dynamic smem; barriers / bias (static, < 2 KB) live outside
 
 struct PairArgs {
@@ -48,6 +48,7 @@ struct PairArgs {
     int tiles_per_item, total_tiles;
     int x_rows, x_box_rows, x_pieces;
     int n_x, n_t, n_o;
+    int n_w2;                    // 0: c2's weights resident like c1's ; > 0: streamed per tile through a ring of n_w2 tap tiles
     int concat, acc_n, paired, reverse;
     int dbg;                     // HFG_PAIR_DBG (timing experiments only): 1 = epilogue 2 idle, 2 = no MMAs, 3 = epilogue 1 idle, 4 = no TMA stores
     uint32_t x_plane_bytes, t_plane_bytes, w_plane_bytes, o_plane_bytes;
@@ -79,7 +80,7 @@ __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t row_bytes) { retu
 // and ~100 cycles per MMA on rebuilding them, twice the tensor pipe's own time for N <= 64).
 template <int KS, int NP>
 __device__ __forceinline__ void issue_taps(bool leader, int k, uint32_t d0, uint32_t a_lo, uint32_t w_lo, uint32_t a_tap, uint32_t w_tap,
-                                           uint32_t a_pl, uint32_t w_pl, uint32_t dhi, uint32_t id0, uint32_t id1) {
+                                           uint32_t a_pl, uint32_t w_pl, uint32_t dhi, uint32_t id0, uint32_t id1, uint32_t acc_in = 0u) {
 #pragma unroll 1
     for (int j = 0; j < k; ++j) {
         if (leader) {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void issue_taps(bool leader, int k, uint32_t d0, uint
                 const uint32_t ww = w_lo + (ps == 2 ? w_pl : 0u);
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks)
-                    umma_bf16_lh(d0, aa + 2u * ks, ww + 2u * ks, dhi, ps == 0 ? id0 : id1, (ps | ks) ? 1u : (uint32_t)(j != 0));
+                    umma_bf16_lh(d0, aa + 2u * ks, ww + 2u * ks, dhi, ps == 0 ? id0 : id1, (ps | ks) ? 1u : (acc_in | (uint32_t)(j != 0)));
             }
         }
         a_lo += a_tap;
@@ -105,7 +106,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                  const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
                  const __grid_constant__ CUtensorMap map_yt_hi, const __grid_constant__ CUtensorMap map_yt_lo, const PairArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kMaxX + 17];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxX + 2 * kMaxW2 + 17];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float bias_s[2][64];
 
@@ -135,7 +136,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     const uint32_t bar_t_empty = bp;  bp += 16;
     const uint32_t bar_a2_full = bp;  bp += 16;
     const uint32_t bar_a2_empty = bp; bp += 16;
-    const uint32_t bar_w = bp;
+    const uint32_t bar_w = bp;        bp += 8;
+    const uint32_t bar_w2_full = bp;  bp += 8 * kMaxW2;
+    const uint32_t bar_w2_empty = bp;
 
     if (threadIdx.x < 2 * a.N) {
         const int which = threadIdx.x / a.N, i = threadIdx.x % a.N;
@@ -154,6 +157,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             mbar_init(bar_a2_full + 8 * i, nmma); mbar_init(bar_a2_empty + 8 * i, 4);
         }
         mbar_init(bar_w, 1);
+        for (int i = 0; i < a.n_w2; ++i) { mbar_init(bar_w2_full + 8 * i, 1); mbar_init(bar_w2_empty + 8 * i, nmma); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -171,8 +175,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     if (warp == 0) {
         // ===== producer: resident weights of both convs, then the x ring =====
         if (lane == 0) {
-            mbar_expect_tx(bar_w, (uint32_t)((a.k1 + a.k2) * planes) * (uint32_t)a.N * row_bytes);
-            for (int cv = 0; cv < 2; ++cv)
+            mbar_expect_tx(bar_w, (uint32_t)((a.k1 + (a.n_w2 ? 0 : a.k2)) * planes) * (uint32_t)a.N * row_bytes);
+            for (int cv = 0; cv < (a.n_w2 ? 1 : 2); ++cv)
                 for (int j = 0; j < (cv ? a.k2 : a.k1); ++j)
                     for (int pl = 0; pl < planes; ++pl)
                         tma_load_2d(smem_w + (uint32_t)(cv * a.k1 + j) * w_stage + pl * a.w_plane_bytes,
@@ -194,6 +198,22 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                                     pl ? &map_x_lo : &map_x_hi, bar_x_full + 8 * sx, 0, xr0 + pc * a.x_box_rows, b);
                 if (++sx == a.n_x) { sx = 0; px ^= 1u; }
             }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== c2 weight ring (only when both weight sets do not fit beside the tiles): k2 tap tiles per tile of work, from L2 =====
+        if (lane == 0 && a.n_w2 > 0) {
+            int sw = 0;
+            uint32_t pw = 0;
+            for (int it = 0; it < n_my; ++it)
+                for (int j = 0; j < a.k2; ++j) {
+                    mbar_wait(bar_w2_empty + 8 * sw, pw ^ 1u);
+                    mbar_expect_tx(bar_w2_full + 8 * sw, (uint32_t)a.N * row_bytes * planes);
+                    for (int pl = 0; pl < planes; ++pl)
+                        tma_load_2d(smem_w + (uint32_t)(a.k1 + sw) * w_stage + pl * a.w_plane_bytes, pl ? &map_w2_lo : &map_w2_hi,
+                                    bar_w2_full + 8 * sw, 0, j * a.N);
+                    if (++sw == a.n_w2) { sw = 0; pw ^= 1u; }
+                }
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 8) {
@@ -218,7 +238,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             const uint32_t a_stage = cv ? t_stage : x_stage;
             const uint32_t a_ring = desc_lo(cv ? smem_t : smem_x) + (uint32_t)ms * sub_step;
             const uint32_t d_base = tmem_base + (uint32_t)(cv * 2 * acc_cols + ms * a.acc_n);
-            const int k = cv ? a.k2 : a.k1, n_t = a.n_t, n_x = a.n_x;
+            const int k = cv ? a.k2 : a.k1, n_t = a.n_t, n_x = a.n_x, n_w2 = a.n_w2;
+            int sw2 = 0;
+            uint32_t pw2 = 0;
             const bool dbg_nomma = a.dbg == 2;
             mbar_wait(bar_w, 0);
             int sx = 0;
@@ -241,7 +263,30 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 const uint32_t d0 = d_base + (uint32_t)(buf * acc_cols);
                 const uint32_t a_lo = a_ring + (((uint32_t)slot * a_stage) >> 4);
                 const bool go = leader && !dbg_nomma;
-                if (kPlanes == 1) {
+                if (cv == 1 && n_w2 > 0) {
+                    // streamed c2 weights: one barrier round trip per tap
+                    const uint32_t w_ring = desc_lo(smem_w + (uint32_t)a.k1 * w_stage);
+                    uint32_t aa = a_lo;
+                    for (int j = 0; j < k; ++j) {
+                        mbar_wait(bar_w2_full + 8 * sw2, pw2);
+                        tc_fence_after();
+                        const uint32_t wl = w_ring + (uint32_t)sw2 * w_tap;
+                        const uint32_t acc_in = j != 0;
+                        if (kPlanes == 1) {
+                            if (k4) issue_taps<4, 1>(go, 1, d0, aa, wl, 0u, 0u, a_pl, w_pl, dhi, id0, idesc, acc_in);
+                            else issue_taps<2, 1>(go, 1, d0, aa, wl, 0u, 0u, a_pl, w_pl, dhi, id0, idesc, acc_in);
+                        } else if (concat) {
+                            if (k4) issue_taps<4, 2>(go, 1, d0, aa, wl, 0u, 0u, a_pl, w_pl, dhi, id0, idesc, acc_in);
+                            else issue_taps<2, 2>(go, 1, d0, aa, wl, 0u, 0u, a_pl, w_pl, dhi, id0, idesc, acc_in);
+                        } else {
+                            if (k4) issue_taps<4, 3>(go, 1, d0, aa, wl, 0u, 0u, a_pl, w_pl, dhi, id0, idesc, acc_in);
+                            else issue_taps<2, 3>(go, 1, d0, aa, wl, 0u, 0u, a_pl, w_pl, dhi, id0, idesc, acc_in);
+                        }
+                        if (leader) umma_commit(bar_w2_empty + 8 * sw2);
+                        if (++sw2 == n_w2) { sw2 = 0; pw2 ^= 1u; }
+                        aa += a_tap;
+                    }
+                } else if (kPlanes == 1) {
                     if (k4) issue_taps<4, 1>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
                     else issue_taps<2, 1>(go, k, d0, a_lo, w_lo, a_tap, w_tap, a_pl, w_pl, dhi, id0, idesc);
                 } else if (concat) {
@@ -510,7 +555,6 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     a.w_plane_bytes = rup((uint32_t)N * row_bytes, 1024);
     if (a.concat && a.w_plane_bytes != (uint32_t)N * row_bytes) return HFG_ERR_UNSUPPORTED;
     a.o_plane_bytes = 32u * row_bytes;
-    const uint32_t w_all = (uint32_t)(p.k1 + p.k2) * a.w_plane_bytes * planes;
     const uint32_t budget = kSmemMax - 1024;   // alignment slack
 
     // Choose (MT, x ring depth, t buffers, staging slots per warp): cycles per valid output row of a tile interval, the
@@ -522,6 +566,22 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     const int f_mt = penv("HFG_PAIR_MT", 0), f_nx = penv("HFG_PAIR_NX", 0), f_nt = penv("HFG_PAIR_NT", 0), f_no = penv("HFG_PAIR_NO", 0);
     bool ok = false;
     double best = 1e30;
+    // c2's weights: resident like c1's, or -- when both sets leave no room for two t buffers -- streamed per tile through a small
+    // ring (k2 tap tiles per tile of work from L2; a barrier round trip per tap in the c2 issuer)
+    const int f_w2 = penv("HFG_PAIR_W2RING", -1);
+    PairArgs resident_plan = a;
+    size_t resident_smem = 0;
+    bool resident_ok = false;
+    for (int n_w2 : {0, std::min(p.k2, 4)}) {
+      if (f_w2 >= 0 && (n_w2 != 0) != (f_w2 != 0)) continue;
+      if (n_w2 > 0) {
+          if ((ok && a.n_t == 2) || f_nt == 1) break;   // the resident plan already has both t buffers (or one is forced)
+          if (planes > 1 && f_w2 < 0) break;            // measured: bf16x3 C = 32, k = 11, d = 5 streamed 0.79 ms vs 0.77 ms as two launches
+          // otherwise any streamed plan with two t buffers is preferred; the resident one is kept in case there is none
+          resident_plan = a; resident_smem = I->smem; resident_ok = ok;
+          ok = false; best = 1e30;
+      }
+      const uint32_t w_all = (uint32_t)(p.k1 + (n_w2 ? n_w2 : p.k2)) * a.w_plane_bytes * planes;
     for (int mt = 2; mt >= 1; --mt) {
         if (f_mt && mt != f_mt) continue;
         if (4 * mt * a.acc_n > 512) continue;
@@ -532,11 +592,11 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
         const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
         const uint32_t x_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
         const uint32_t t_plane = rup((uint32_t)((R + 2 * a.h2 + 7) / 8 * 8) * row_bytes, 1024);
-        const double t_mma = (double)mt * (p.k1 + p.k2) * ksteps * step_clk;
+        const double t_mma = (double)mt * (p.k1 + p.k2) * ksteps * step_clk + (n_w2 ? p.k2 * 80.0 : 0.0);
         const double t_hbm = ((double)rows_need + V) * row_bytes * planes / 20.0;
         const double t_epi = (double)mt * (N / 32) * (planes > 1 ? 1100.0 : 600.0);   // both epilogues share an SM sub-partition
         const double t_int = std::max({t_mma, t_hbm, t_epi}) + 300.0;
-        for (int n_t = 2; n_t >= 1; --n_t) {
+        for (int n_t = 2; n_t >= (n_w2 ? 2 : 1); --n_t) {
             if (f_nt && n_t != f_nt) continue;
             // each epilogue-2 warp meets one of its slots again two tiles later (the groups alternate tiles): mt slots suffice
             for (int n_o = std::min(mt, 2); n_o >= 1; --n_o) {
@@ -559,7 +619,7 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
                         a.mt = mt; a.R = R; a.V = V;
                         a.x_rows = pieces * box_rows; a.x_box_rows = box_rows; a.x_pieces = pieces;
                         a.x_plane_bytes = x_plane; a.t_plane_bytes = t_plane;
-                        a.n_x = n_x; a.n_t = n_t; a.n_o = n_o;
+                        a.n_x = n_x; a.n_t = n_t; a.n_o = n_o; a.n_w2 = n_w2;
                         a.off_w = (uint32_t)n_x * x_plane * planes;
                         a.off_t = a.off_w + w_all;
                         a.off_o = a.off_t + (uint32_t)n_t * t_plane * planes;
@@ -570,13 +630,15 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
             }
         }
     }
+    }
+    if (!ok && resident_ok) { a = resident_plan; I->smem = resident_smem; ok = true; }
     if (!ok) return HFG_ERR_UNSUPPORTED;
     // One t buffer serialises epilogue 1 behind c2 of the previous tile (and leaves one epilogue-1 group idle): measured slower than
     // the two-launch plan (C = 64, k = 7: 0.256 vs 0.245 ms; bf16x3 C = 32, k = 11, d = 5: 0.80 vs 0.77 ms).  Leave those unfused.
     if (a.n_t == 1 && !f_nt && !penv("HFG_PAIR_ALLOW_NT1", 0)) return HFG_ERR_UNSUPPORTED;
     if (penv("HFG_PAIR_VERBOSE", 0))
-        fprintf(stderr, "pair plan C=%d k=%d,%d d=%d planes=%d: mt=%d V=%d n_x=%d n_t=%d n_o=%d x_rows=%d smem=%zu cost=%.2f\n", N, p.k1, p.k2, p.d,
-                planes, a.mt, a.V, a.n_x, a.n_t, a.n_o, a.x_rows, I->smem, best);
+        fprintf(stderr, "pair plan C=%d k=%d,%d d=%d planes=%d: mt=%d V=%d n_x=%d n_t=%d n_o=%d n_w2=%d x_rows=%d smem=%zu cost=%.2f\n", N, p.k1, p.k2, p.d,
+                planes, a.mt, a.V, a.n_x, a.n_t, a.n_o, a.n_w2, a.x_rows, I->smem, best);
     a.tiles_per_item = (p.L + a.V - 1) / a.V;
     a.total_tiles = a.tiles_per_item * p.B;
     I->grid = std::min(a.total_tiles, std::max(1, sm_count));

@@ -159,7 +159,7 @@ def test_v1_resblock_pair_parity(n, m, mode):
     x = torch.randn(2, C, 777)                     # ragged: not a multiple of any tile height
     ref = _pair_ref(w, n, m, k, d, x)
     y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
-    if (C == 32 and not (mode == "bf16x3" and k == 11 and d == 5)) or (C == 64 and mode == "bf16" and k == 3):
+    if (C == 32 and not (mode == "bf16x3" and k == 11 and d == 5)) or (C == 64 and mode == "bf16" and k <= 7):
         assert fused, "the plan is expected to fuse this pair"
     err = np.abs(y - ref).max()
     tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
