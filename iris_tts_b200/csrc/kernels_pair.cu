@@ -11,8 +11,10 @@
 //   t tile  --c2 taps-->  acc2 (TMEM)
 //   acc2 --epilogue 2: + b2 + inverse-lrelu(x rows of the SAME x tile), lrelu, bf16 plane(s)-->  staging -> TMA store
 //
-// Two streams (x in, out) instead of five.  A tile computes R = 128*MT conv rows of both convs; the last k-1 rows of c2 see
-// t rows this tile did not compute and are dropped: V = R - (k-1) valid output rows per tile (k <= 11: >= 92 % at MT = 1).
+// Two streams (x in, out) instead of five.  A tile computes R = 128*MT conv rows of both convs; the last k2-1 rows of c2 see
+// t rows this tile did not compute and are dropped: V = R - (k2-1) valid output rows per tile (k <= 11: >= 92 % at MT = 1).
+// c1 has k1 taps with dilation d, c2 k2 taps with dilation 1 (k1 = k2 for a reference ResBlock; the time-folded narrow stages of
+// engine.cu:build_folded give different counts).
 //
 // c1 and c2 have separate issuer warps ordered only by barriers: c1 of tile i+1 (and i+2) runs while epilogue 1 of tile i+1
 // and epilogue 2 of tile i work on their own warps, so the tensor pipe stays busy.  acc1 / acc2 are double-buffered in TMEM (4 * MT * N <= 512 columns).
@@ -20,7 +22,8 @@
 // Arithmetic is the unfused plan's: same bf16 (hi[, lo]) rounding of t, same fp32 accumulation per output row with a fixed
 // (tap, K-slice, pass) order that does not depend on the tile a row falls in, nor on B or L.
 //
-// Warps: 0 = TMA producer (resident weights of both convs, x ring), 2 = TMEM allocator, 3 = barrier init,
+// Warps: 0 = TMA producer (resident weights, x ring), 1 = c2 weight ring (only when c2's weights are streamed), 2 = TMEM allocator,
+//        3 = barrier init,
 //        4..4+2*MT-1 = MMA issuers (one per conv and 128-row subtile), 8-15 = epilogue 1, 16-23 = epilogue 2 (two groups of four
 //        warps each; group g takes the tiles with (i & 1) == g, so a group has two tile intervals for its tile).
 #include <algorithm>
@@ -217,7 +220,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 8) {
-        // ===== MMA issuers: warp 8 + cv*MT + ms issues conv cv (0: c1, 1: c2) of subtile ms =====
+        // ===== MMA issuers: warp 4 + cv*MT + ms issues conv cv (0: c1, 1: c2) of subtile ms =====
         // One thread cannot issue small-N MMAs at the tensor pipe's rate, and c1 of tile i+1 must overlap the
         // epilogues of tile i: c1 and c2 have their own issuers, ordered only by the barriers.
         const int role = warp - 4;

@@ -77,6 +77,26 @@ def synthesize_chunk(synth: Callable, mel, chunk: TimeChunk, hop: int):
     return wav[chunk.trim_front * hop: wav.numel() - chunk.trim_back * hop]
 
 
+def stream_chunks(frames: int, chunk_frames: int, halo: int = HALO_FRAMES) -> List[TimeChunk]:
+    """Consecutive chunks of at most ``chunk_frames`` mel frames (the last one may be shorter), halos on inner edges."""
+    if chunk_frames <= 0:
+        raise ValueError("chunk_frames must be positive")
+    if halo < 0:
+        raise ValueError("halo must be non-negative")
+    return [TimeChunk(s, min(frames, s + chunk_frames), max(0, s - halo), min(frames, s + chunk_frames + halo))
+            for s in range(0, frames, chunk_frames)]
+
+
+def synthesize_streaming(synth: Callable, mel, chunk_frames: int, hop: int = 256, halo: int = HALO_FRAMES):
+    """Streaming output on one device: yields the waveform of one long mel [1, C, T] piece by piece (``chunk_frames * hop``
+    samples each), every piece synthesised from its frames plus the receptive-field halo.  The concatenation of the pieces is
+    the waveform of the whole mel (same halo argument as ``synthesize_longform``); the first audio is available after one
+    chunk instead of after the whole utterance.  The reference has no streaming path (hifigan_pretrained.py:208-242 returns
+    the complete array)."""
+    for c in stream_chunks(int(mel.shape[-1]), chunk_frames, halo):
+        yield synthesize_chunk(synth, mel, c, hop)
+
+
 def synthesize_longform(synth: Callable, mel, hop: int = 256, group=None, dst: int = 0, halo: int = HALO_FRAMES,
                         all_ranks: bool = False):
     """Time-sharded synthesis of ONE long mel across the ranks of ``group``.

@@ -87,6 +87,23 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def test_streaming_pieces_concatenate_to_the_full_waveform():
+    """Streaming chunked output against the oracle forward: pieces of 40 frames + 16-frame halo == unchunked."""
+    from oracle import hifigan_oracle as O
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    mel = torch.from_numpy(O.synthetic_mel(1, 130, seed=5))
+    synth = lambda m: O.forward(sd, m, O.V2)                  # noqa: E731
+    full = synth(mel).reshape(-1)
+    chunks = sharding.stream_chunks(130, 40)
+    assert [(c.start, c.stop) for c in chunks] == [(0, 40), (40, 80), (80, 120), (120, 130)]
+    assert chunks[0].lo == 0 and chunks[1].lo == 24 and chunks[-1].hi == 130
+    pieces = list(sharding.synthesize_streaming(synth, mel, 40))
+    assert [p.numel() for p in pieces] == [40 * 256, 40 * 256, 40 * 256, 10 * 256]
+    assert float((torch.cat(pieces) - full).abs().max()) <= 2e-6
+    with pytest.raises(ValueError):
+        sharding.stream_chunks(10, 0)
+
+
 def test_world_size_2_gloo_longform_gather_and_batch_shards():
     world = 2
     ctx = mp.get_context("spawn")
