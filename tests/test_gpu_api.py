@@ -68,6 +68,19 @@ def test_model_object_on_cuda_and_cpu_tensors():
         m(torch.zeros(1, 79, 4))
 
 
+def test_streaming_output_equals_the_full_forward_on_the_engine():
+    """sharding.synthesize_streaming on the CUDA engine: 100-frame pieces (+ 16-frame halo) concatenate to the whole waveform."""
+    import iris.hifigan_pretrained as hp
+    from iris_tts_b200 import sharding
+    torch.manual_seed(0)
+    m = hp.HiFiGANModel().eval().to("cuda:0")
+    mel = torch.from_numpy(O.synthetic_mel(1, 431, seed=9, realistic=True))
+    full = m(mel).reshape(-1)
+    pieces = list(sharding.synthesize_streaming(m, mel, 100))
+    assert [p.numel() for p in pieces] == [25600, 25600, 25600, 25600, 31 * 256]
+    assert float((torch.cat(pieces) - full).abs().max()) <= 2e-5
+
+
 def test_keras_surface_matches_the_oracle_with_permuted_weights(tmp_path):
     """create_vocoder().infer: Keras layouts (Conv1D [k, ci, co], Conv1DTranspose [k, co, ci]); restated mapping."""
     import iris.vocoder as kv
