@@ -394,6 +394,19 @@ def test_ragged_and_minimal_shapes(mode):
         assert np.abs(out - ref).max() <= E2E_TOL[mode], (B, T)
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_v1_minimal_lengths_through_the_wide_upsamplers(mode):
+    """T = 1, 2, 3 frames on V1: the 128-column-tiled upsamplers ups.0/1 see 2..25 GEMM rows (their first output box is written with
+    plain stores that must stop at the end of the sequence), the pair kernels a single partial tile."""
+    eng, sd = _engine("v1")
+    for B, T in ((1, 1), (2, 2), (3, 3)):
+        mel = O.synthetic_mel(B, T, seed=40 + T)
+        ref = O.infer(sd, mel)
+        out = eng.forward(mel, precision=mode)
+        assert out.shape == (B, T * 256)
+        assert np.abs(out - ref).max() <= E2E_TOL[mode], (B, T)
+
+
 def test_empty_batch_and_bad_arguments():
     from iris_tts_b200 import Engine, _abi
     from iris_tts_b200.engine import V2
