@@ -99,6 +99,7 @@ struct Plan {
     float* wave_dev = nullptr;  // [B][T*hop]
     size_t bytes = 0;
     bool keep_taps = false;
+    std::vector<size_t> guards;   // HFG_GUARD: canary regions between the workspace buffers
 };
 
 struct Tap {
@@ -448,10 +449,16 @@ ConvParams conv32(const Layer& L, int B, int Lin, const float* x, float* y, cons
 struct Bump {
     uint8_t* base;
     size_t off = 0;
+    size_t guard = 0;                      // HFG_GUARD: bytes of canary after every buffer (compute-sanitizer is not available here)
+    std::vector<size_t>* guards = nullptr;  // offsets of the canary regions
     template <typename T>
     T* take(size_t count) {
         T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
         off += (count * sizeof(T) + 255) / 256 * 256;
+        if (guard) {
+            if (guards && base) guards->push_back(off);
+            off += guard;
+        }
         return p;
     }
 };
@@ -465,6 +472,9 @@ size_t stage_elems_max(const hfg_engine* e, int B, int T, int min_ch = 1) {
     }
     return mx;
 }
+
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardByte = 0xA5;
 
 int env_flag(const char* name, int dflt) {
     const char* s = getenv(name);
@@ -498,6 +508,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     const bool any_32 = n_tc < NU;   // some stage (or everything) runs on the fp32 family
 
     Bump bump{base};
+    if (env_flag("HFG_GUARD", 0)) { bump.guard = kGuardBytes; bump.guards = plan ? &plan->guards : nullptr; }
     const size_t smax = stage_elems_max(e, B, T);
     const size_t smax_tc = stage_elems_max(e, B, T, 32);   // planes of the tensor-core family
     const size_t n_pre = (size_t)B * T * c0;
@@ -1050,8 +1061,27 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     Plan* plan = it->second.get();
     const size_t mel_bytes = (size_t)B * e->cfg.in_channels * T * sizeof(float);
     const size_t wave_bytes = (size_t)B * T * e->hop * sizeof(float);
+    // HFG_GUARD=1 (debug): canaries between all workspace buffers, refilled before and verified after every forward -- the
+    // stand-in for a memcheck pass: a kernel that writes past the end (or before the start) of a plane trips the next canary.
+    for (size_t off : plan->guards) CK(cudaMemsetAsync(e->arena + off, kGuardByte, kGuardBytes, e->stream));
     CK(cudaMemcpyAsync(plan->mel_dev, mel, mel_bytes, mel_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
     RET(run_plan(e, plan));
+    if (!plan->guards.empty()) {
+        if (env_flag("HFG_GUARD_SELFTEST", 0))   // prove the check itself: clobber one canary byte like a stray store would
+            CK(cudaMemsetAsync(e->arena + plan->guards[plan->guards.size() / 2] + 7, 0, 1, e->stream));
+        std::vector<uint8_t> host(kGuardBytes);
+        CK(cudaStreamSynchronize(e->stream));
+        for (size_t gi = 0; gi < plan->guards.size(); ++gi) {
+            CK(cudaMemcpy(host.data(), e->arena + plan->guards[gi], kGuardBytes, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < kGuardBytes; ++i)
+                if (host[i] != (uint8_t)kGuardByte) {
+                    char buf[160];
+                    snprintf(buf, sizeof buf, "HFG_GUARD: canary %zu of %zu (arena offset %zu) overwritten at byte %zu", gi,
+                             plan->guards.size(), plan->guards[gi], i);
+                    return fail(HFG_ERR_CUDA, buf);
+                }
+        }
+    }
     CK(cudaMemcpyAsync(wave, plan->wave_dev, wave_bytes, wave_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     if (!(flags & HFG_NO_SYNC)) CK(cudaStreamSynchronize(e->stream));
     return HFG_OK;

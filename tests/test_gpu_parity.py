@@ -407,6 +407,48 @@ def test_v1_minimal_lengths_through_the_wide_upsamplers(mode):
         assert np.abs(out - ref).max() <= E2E_TOL[mode], (B, T)
 
 
+@pytest.mark.parametrize("cfg_name", ["v1", "v2", "v3"])
+def test_no_kernel_writes_outside_its_buffers(cfg_name):
+    """HFG_GUARD=1 puts a 4 KB canary after every workspace buffer and verifies all of them after each forward (compute-sanitizer
+    is not available on the GPU pool): ragged and minimal shapes, every mode, with and without intermediate taps."""
+    from iris_tts_b200 import Engine
+    cfg, ocfg = _cfgs(cfg_name)
+    sd = O.random_state_dict(ocfg, seed=0, loud=True)
+    os.environ["HFG_GUARD"] = "1"
+    try:
+        eng = Engine(cfg, 0)
+        eng.load_state_dict(sd, strict=True)
+        eng.finalize()
+        for B, T in ((1, 1), (2, 3), (1, 37), (3, 130)):
+            mel = O.synthetic_mel(B, T, seed=B * 10 + T)
+            ref = O.infer(sd, mel, ocfg)
+            for mode in MODES:
+                out = eng.forward(mel, precision=mode)              # raises HfgError if a canary was overwritten
+                assert np.abs(out - ref).max() <= E2E_TOL[mode], (B, T, mode)
+            eng.forward(mel, precision="bf16x3", keep_taps=True)
+        eng.close()
+    finally:
+        del os.environ["HFG_GUARD"]
+
+
+def test_guard_mode_detects_a_stray_store():
+    from iris_tts_b200 import Engine, _abi
+    from iris_tts_b200.engine import V2
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    os.environ["HFG_GUARD"] = "1"
+    os.environ["HFG_GUARD_SELFTEST"] = "1"
+    try:
+        eng = Engine(V2, 0)
+        eng.load_state_dict(sd, strict=True)
+        eng.finalize()
+        with pytest.raises(_abi.HfgError) as ei:
+            eng.forward(O.synthetic_mel(1, 5, seed=1), precision="bf16")
+        assert "canary" in str(ei.value)
+        eng.close()
+    finally:
+        del os.environ["HFG_GUARD"], os.environ["HFG_GUARD_SELFTEST"]
+
+
 def test_empty_batch_and_bad_arguments():
     from iris_tts_b200 import Engine, _abi
     from iris_tts_b200.engine import V2
