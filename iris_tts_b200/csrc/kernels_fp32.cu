@@ -428,14 +428,17 @@ __global__ void mrf_combine_kernel(const MrfArgs a, size_t n8) {
 }
 
 // conv_post on the nk branch-output planes of the last stage: stage tile = lrelu(mean_j inverse-lrelu(plane_j)) in fp32
-// shared memory (row stride C + 4 floats: conflict-free float4 reads by consecutive rows), one output sample per thread.
+// shared memory, then a sliding-window conv.  Row stride C + 2 floats and channel PAIRS interleaved over the four lanes of an
+// output group (lane q owns pairs q, q+4, q+8, ...): the 32 lanes of a warp (8 groups x 4 lanes) then read 16 distinct 8-byte
+// bank pairs twice -- the 2-wavefront minimum of an LDS.64.  (Stride C + 4 with 8 consecutive channels per lane put the 8 groups
+// on the same banks: ncu counted 27 M bank conflicts per launch and 88 % l1tex utilisation, 3.1 of 6.5 TB/s.)
 constexpr int kPostMrfTile = 256;
 __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfArgs a, const float* __restrict__ w, const float* __restrict__ bias,
                                                                     float* __restrict__ wave, int L, int C, int k, int apply_tanh) {
     extern __shared__ __align__(16) float smem[];
     const int pad = (k - 1) / 2;
     const int rows = kPostMrfTile + k - 1;
-    const int stride = C + 4;
+    const int stride = C + 2;
     float* in_s = smem;                    // [rows][stride]
     float* w_s = in_s + rows * stride;     // [k][C]
     const int tid = threadIdx.x;
@@ -471,19 +474,19 @@ __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfAr
                 }
             }
         }
-        float* dst = in_s + r * stride + c8 * 8;
-        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        float* dst = in_s + r * stride + c8 * 8;   // rows are 8-byte aligned (stride even)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(dst + 2 * i) = make_float2(v[2 * i], v[2 * i + 1]);
     }
     for (int idx = tid; idx < k * C; idx += kPostMrfTile) w_s[idx] = __ldg(w + idx);
     __syncthreads();
     // Thread = (group of 4 consecutive outputs) x (quarter of the channels): a sliding window over k + 3 staged rows feeds
     // 4 accumulators, so one shared-memory row read serves up to 4 outputs; the 4 channel quarters meet in two shuffles.
     const int q = tid & 3, og = tid >> 2;
-    const int cq = C / 4;                      // channels per quarter (multiple of 2; 8 for C = 32)
+    const int cq = C / 4;                      // channels per lane (multiple of 2; 8 for C = 32), as interleaved pairs
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < cq; c += 2) {
-        const int ch = q * cq + c;
+        const int ch = 2 * q + 4 * c;          // pair index q + 4*(c/2)
         float2 win[4];                         // rows o .. o+3 of the window for this channel pair
 #pragma unroll
         for (int i = 0; i < 3; ++i) win[i + 1] = *reinterpret_cast<const float2*>(in_s + (og * 4 + i) * stride + ch);
@@ -596,7 +599,7 @@ cudaError_t launch_mrf_combine(const MrfArgs& a, size_t n, cudaStream_t s) {
 cudaError_t launch_conv_post_mrf(const MrfArgs& a, const float* w, const float* bias, float* wave, int B, int L, int C, int k,
                                  int apply_tanh, cudaStream_t s) {
     if (C % 8 != 0 || a.nk < 1 || a.nk > HFG_MAX_KERNELS) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)((kPostMrfTile + k - 1) * (C + 4) + k * C) * sizeof(float);
+    const size_t smem = (size_t)((kPostMrfTile + k - 1) * (C + 2) + k * C) * sizeof(float);
     static size_t configured[kMaxDevices] = {};
     int dev = 0;
     cudaGetDevice(&dev);
