@@ -325,6 +325,20 @@ def run_ours(args):
                      "roofline_other_kernels": other_rooflines(recs2, peaks, "bf16", roofline_from_records(recs2, peaks, precision="bf16")),
                      "tolerance": "max-abs 1.5e-1 vs oracle on loud weights (tests/test_gpu_parity.py); 1e-3 at default init"}
 
+    # the north-star's own target case (BASELINE.json: V1 at batch 32 x 10 s, bf16 tensor-core mode, 1 GPU: >= 50 % of the
+    # per-layer roofline), reported beside the headline; single GPU only, 5 steps
+    north = None
+    if world == 1 and not args.no_secondary:
+        B32 = 32
+        mel32 = torch.randn(B32, 80, T, device="cuda")
+        out32 = torch.empty(B32, T * hop, dtype=torch.float32, device="cuda")
+        ms32, _, _ = time_device_steps(eng, stream, mel32, out32, B32, T, "bf16", 5, 3, barrier)
+        rl32 = work.layer_roofline_seconds(voc.model.config, B32, T, 2, peaks["tflops"] * 1e12, peaks["gbs"] * 1e9)
+        north = {"workload": f"HiFiGAN V1, {B32} x {T}-frame (10 s) mels, bf16, 1 GPU", "ms_per_step": ms32 / 5,
+                 "value": B32 * T * hop * 5 / (ms32 * 1e-3), "unit": "samples/s", "layer_roofline_ms": rl32 * 1e3,
+                 "layer_roofline_frac": rl32 * 1e3 / (ms32 / 5), "target_frac": 0.5}
+        del mel32, out32
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -366,6 +380,8 @@ def run_ours(args):
     }
     if secondary:
         line["bf16_mode"] = secondary
+    if north:
+        line["north_star_b32_bf16"] = north
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_oracle_throughput(T, 3, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
