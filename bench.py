@@ -1,16 +1,25 @@
 #!/usr/bin/env python
 """Vocoder throughput bench: generated audio samples/s of the HiFiGAN V1 generator on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|fp16|bf16|fp32]
 
 A step = one mel -> waveform pass over one batch (BASELINE.json configs[1]: V1 random-init, batch 16 x 10 s mels
 = [16, 80, 862], fp32-class arithmetic).  N > 1 (torchrun, one rank per GPU): the batch of utterances is sharded,
 every rank synthesises its own 16 utterances, no collective on the data path ("weak" scaling).
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what each key means.
+
+Beside the headline the same line carries (secondary keys, each a separately timed leg):
+  bf16_mode / fp16_mode         the single-pass tensor-core modes on the headline workload
+  north_star_b32                BASELINE's target case (V1, 32 x 10 s, one GPU), bf16 and fp16
+  batch_sweep_bf16, v2_b64, v3_b64   BASELINE configs 3 and 5 (N = 1)
+  longform_120s                 BASELINE config 4: one 10,336-frame mel; N > 1: time-chunked + ONE NCCL gather
+  strong_scaling_b64            BASELINE config 3 at N > 1: a fixed global batch of 64 sharded over the N GPUs
+  per_rank_ms                   min / median / max of the per-rank step times (attributes the weak-scaling loss)
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -25,6 +34,8 @@ if ROOT not in sys.path:
 
 SAMPLE_RATE = 22050
 METRIC = "vocoder_audio_samples_per_sec"
+REF_FILE = os.path.join(ROOT, "baseline", "_ref", "iris", "hifigan_pretrained.py")
+LONGFORM_FRAMES = 10336   # 120 s at hop 256 / 22050 Hz
 
 
 def parse_args():
@@ -33,11 +44,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step")
     ap.add_argument("--frames", type=int, default=862, help="mel frames per utterance (862 = 10 s at hop 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the separately reported bf16 tensor-core mode")
+    ap.add_argument("--no-secondary", action="store_true", help="headline only: skip every secondary leg")
     return ap.parse_args()
 
 
@@ -106,46 +117,102 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle (torch-functional restatement of the reference forward) on the host cores
+# CPU baseline / reference arm: the reference's own module on the host cores (baseline/_ref, installed by
+# baseline/install_ref.py); the oracle port only where that copy did not travel.
 # ---------------------------------------------------------------------------
 
-def cpu_oracle_throughput(frames: int, steps: int, warmup: int):
-    """Bounded sample: B=1 utterance of `frames` mel frames per step, all host threads."""
-    import torch
+def load_reference_module():
+    """The unmodified reference module, loaded by file path under an alias (it cannot shadow this repo's ``iris``)."""
+    if not os.path.exists(REF_FILE):
+        return None
+    import warnings
 
-    from oracle import hifigan_oracle as O
+    warnings.filterwarnings("ignore", category=FutureWarning)   # nn.utils.weight_norm deprecation notice
+    spec = importlib.util.spec_from_file_location("_ref_hifigan", REF_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_ref_hifigan"] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = O.random_state_dict(O.V1, seed=0)
-    mel = torch.from_numpy(O.synthetic_mel(1, frames, seed=1234))
-    for _ in range(warmup):
-        O.forward(sd, mel, O.V1)
-    ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        O.forward(sd, mel, O.V1)
-        ts.append(time.perf_counter() - t0)
-    samples = frames * O.V1.hop
-    total = sum(ts)
-    return {"value": samples * steps / total, "ms_per_step": 1e3 * total / steps, "best_ms": 1e3 * min(ts), "cores": cores,
-            "threads": torch.get_num_threads(), "samples_per_step": samples}
+
+class CpuGenerator:
+    """``forward(mel tensor [B, 80, T]) -> tensor`` of the seed-0 V1 generator on the host: the reference's stock
+    ``HiFiGANModel.forward`` (weight-norm re-folded on every call, as the reference does) or, if baseline/_ref is absent,
+    the oracle port (which also folds on every call)."""
+
+    def __init__(self):
+        import torch
+
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.threads = torch.get_num_threads()
+        ref = load_reference_module()
+        if ref is not None:
+            torch.manual_seed(0)
+            self.model = ref.HiFiGANModel().eval()
+            self.kind = "reference"
+            self.what = (f"baseline/_ref/iris/hifigan_pretrained.py HiFiGANModel.forward (unmodified reference, torch {torch.__version__} "
+                         "oneDNN, weight-norm re-folded every forward)")
+            self._fwd = lambda m: self.model(m)
+        else:
+            from oracle import hifigan_oracle as O
+
+            sd = O.random_state_dict(O.V1, seed=0)
+            self.kind = "port"
+            self.what = f"oracle/hifigan_oracle.py (port; torch {torch.__version__} oneDNN, weight-norm re-folded every forward)"
+            self._fwd = lambda m: O.forward(sd, m, O.V1)
+
+    def time(self, batch: int, frames: int, steps: int, warmup: int):
+        import torch
+
+        torch.manual_seed(1234)
+        mel = torch.randn(batch, 80, frames)
+        with torch.no_grad():
+            for _ in range(warmup):
+                self._fwd(mel)
+            ts = []
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                self._fwd(mel)
+                ts.append(time.perf_counter() - t0)
+        samples = batch * frames * 256
+        return {"value": samples * len(ts) / sum(ts), "ms_per_step": 1e3 * sum(ts) / len(ts), "best_ms": 1e3 * min(ts),
+                "samples_per_step": samples}
+
+
+def keras_jax_status():
+    try:
+        import jax  # noqa: F401
+        import keras  # noqa: F401
+        return "importable (not timed: the Keras generator is the same graph; see DESIGN.md)"
+    except Exception as ex:  # noqa: BLE001
+        return f"not runnable: {type(ex).__name__}: {ex} (keras / jax not installed in this image, no network)"
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    r = cpu_oracle_throughput(args.frames, args.steps, args.warmup)
-    sample = (f"1 utterance x {args.frames} frames per step (1/{args.batch} of the step's batch), fp32, oracle/hifigan_oracle.py "
-              f"(torch {__import__('torch').__version__} oneDNN conv1d/conv_transpose1d, weight-norm folded once), {r['threads']} threads")
+    gen = CpuGenerator()
+    B, T = args.batch, args.frames
+    # one untimed full-batch forward decides whether the whole batch fits the time box (a few minutes for K + W steps)
+    t0 = time.perf_counter()
+    gen.time(B, T, 1, 0)
+    t_full = time.perf_counter() - t0
+    budget_s = 240.0
+    n_steps = args.steps + args.warmup
+    b_step = B if t_full * n_steps <= budget_s else max(1, int(B * budget_s / (t_full * n_steps)))
+    r = gen.time(b_step, T, args.steps, args.warmup)
+    same = b_step == B
+    sample = (f"{b_step} of the step's {B} utterances x {T} frames per step" if not same else f"the full step: {B} utterances x {T} frames") + \
+             f", fp32, {gen.what}, {gen.threads} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "x_realtime": r["value"] / SAMPLE_RATE,
-        "config": {"workload": f"HiFiGAN V1 random-init, {args.batch} x {args.frames}-frame (10 s) mels per GPU, fp32-class",
-                   "sampled_as": sample},
-        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "config": {"workload": f"HiFiGAN V1 random-init, {B} x {T}-frame (10 s) mels per GPU, fp32-class",
+                   "sampled_as": sample, "same_config": same, "batch_timed": b_step},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": gen.cores, "kind": gen.kind, "sample": sample},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -156,28 +223,54 @@ def run_reference(args):
 # Our arm
 # ---------------------------------------------------------------------------
 
-def time_device_steps(eng, stream, mel_dev, out_dev, B, T, precision, steps, warmup, barrier):
-    import torch
+class Timer:
+    """Device timing of engine forwards with inputs resident in HBM (CUDA events on the engine's stream)."""
 
-    for _ in range(warmup):
-        eng.forward_ptr(mel_dev.data_ptr(), B, T, out_dev.data_ptr(), precision, mel_on_device=True, wave_on_device=True, sync=False)
-    eng.sync()
-    eng.profile(True)
-    l0 = eng.launch_count
-    barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        eng.forward_ptr(mel_dev.data_ptr(), B, T, out_dev.data_ptr(), precision, mel_on_device=True, wave_on_device=True, sync=False)
-    e1.record(stream)
-    eng.sync()
-    torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    recs = eng.profile_records()
-    eng.profile(False)
-    return ms, eng.launch_count - l0, recs
+    def __init__(self, eng, stream, barrier, world):
+        self.eng, self.stream, self.barrier, self.world = eng, stream, barrier, world
+
+    def run(self, mel_dev, out_dev, B, T, precision, steps, warmup, profile=False):
+        """(ms for `steps` forwards on this rank, launches, per-launch records if profile).  Without `profile` the production path
+        runs: one CUDA graph per forward, programmatic dependent launch between the kernels, no events inside."""
+        import torch
+
+        eng = self.eng
+        fwd = lambda: eng.forward_ptr(mel_dev.data_ptr(), B, T, out_dev.data_ptr(), precision, mel_on_device=True,  # noqa: E731
+                                      wave_on_device=True, sync=False)
+        for _ in range(max(warmup, 2)):   # >= 2: the second forward of a plan captures its graph
+            fwd()
+        eng.sync()
+        if profile:
+            eng.profile(True)
+        l0 = eng.launch_count
+        self.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            fwd()
+        e1.record(self.stream)
+        eng.sync()
+        torch.cuda.synchronize()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        recs = None
+        if profile:
+            recs = eng.profile_records()
+            eng.profile(False)
+        return ms, eng.launch_count - l0, recs
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms, [ms]
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        allv = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(allv, t)
+        vals = [float(v.item()) for v in allv]
+        return max(vals), vals
 
 
 def ncu_traffic(precision, kernel):
@@ -218,7 +311,8 @@ def roofline_from_records(recs, peaks, kernel=None, precision=None):
             "executed_flop_factor": 3 if precision == "bf16x3" else 1,
             "executed_frac": (3 if precision == "bf16x3" else 1) * achieved / peaks["tflops"],
             "algorithmic_flops_per_launch": flops / len(sel),
-            "algorithmic_gbs": sum(r["bytes"] for r in sel) / (ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["gbs"]}
+            "algorithmic_gbs": sum(r["bytes"] for r in sel) / (ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["gbs"],
+            "timing": "CUDA events around every launch in a SEPARATE profiled pass (the headline pass has no events inside)"}
 
 
 def other_rooflines(recs, peaks, precision, dominant):
@@ -231,6 +325,82 @@ def other_rooflines(recs, peaks, precision, dominant):
         if r:
             out.append(r)
     return out
+
+
+def measure_tf32_peak(seconds=1.5):
+    """Sustained dense TF32 throughput the way MEASURED_PEAKS.json measures bf16 (torch.matmul 8192^3 back to back): the
+    denominator of the fp32-class layer roofline (SURVEY 8(d) asked for a measured TF32 peak instead of bf16 / 2)."""
+    import torch
+
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        n, t0 = 0, time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(10):
+                a @ b
+            n += 10
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        return 2.0 * 8192 ** 3 * n / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def longform_leg(model, precision, world, rank, reps=5):
+    """BASELINE config 4: one 120 s mel (10,336 frames).  N > 1: chunks of T/N frames + halo per rank, ONE NCCL gather to rank 0
+    (iris_tts_b200.sharding.synthesize_longform); N = 1: the unchunked forward.  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from iris_tts_b200 import sharding
+
+    old = model.precision
+    model.precision = precision
+    torch.manual_seed(4321)
+    mel = (torch.randn(1, 80, LONGFORM_FRAMES) * 2.0 - 5.0).cuda()
+    halo = sharding.HALO_FRAMES
+    assert halo >= sharding.halo_frames(model.config)
+    synth = lambda m: model(m)  # noqa: E731   (CUDA tensor in -> CUDA tensor out, no host round trip)
+    out = None
+    for _ in range(3):
+        out = sharding.synthesize_longform(synth, mel, hop=256, halo=halo)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = sharding.synthesize_longform(synth, mel, hop=256, halo=halo)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rec = None
+    if rank == 0:
+        full = model(mel).reshape(-1)
+        chunks = sharding.time_chunks(LONGFORM_FRAMES, world, halo)
+        rec = {"workload": f"one {LONGFORM_FRAMES}-frame (120 s) mel over {world} GPU(s), {precision}" +
+                           (f", {halo}-frame halo, one NCCL gather" if world > 1 else ", unchunked"),
+               "ms": float(ms.item()), "value": LONGFORM_FRAMES * 256 / (float(ms.item()) * 1e-3), "unit": "samples/s",
+               "x_realtime": LONGFORM_FRAMES * 256 / (float(ms.item()) * 1e-3) / SAMPLE_RATE,
+               "gather_bytes_per_rank": (max(c.frames for c in chunks) * 256 * 4) if world > 1 else 0,
+               "max_abs_vs_unchunked": float((out - full).abs().max()), "samples": int(out.numel())}
+        del full
+    model.precision = old
+    del mel
+    return rec
 
 
 def run_ours(args):
@@ -256,6 +426,7 @@ def run_ours(args):
         hfg_build.build()
     barrier()
     import iris.hifigan_pretrained as hp
+    from iris_tts_b200 import engine as E
     from iris_tts_b200 import work
 
     B, T = args.batch, args.frames
@@ -268,6 +439,7 @@ def run_ours(args):
     eng = voc.model.engine
     hop = eng.hop
     stream = torch.cuda.ExternalStream(eng.stream)
+    timer = Timer(eng, stream, barrier, world)
 
     torch.manual_seed(1234 + rank)
     mel_host = torch.randn(B, 80, T).numpy()
@@ -276,19 +448,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     peaks = measured_peaks()
     samples_per_step = B * T * hop * world
+    P, BW = peaks["tflops"] * 1e12, peaks["gbs"] * 1e9
 
+    # ---- headline: device-timed, production path (graph + PDL, no events inside the timed region) ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, launches, recs = time_device_steps(eng, stream, mel_dev, out_dev, B, T, args.precision, args.steps, args.warmup, barrier)
+    ms_rank, launches, _ = timer.run(mel_dev, out_dev, B, T, args.precision, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, ms_all = timer.max_over_ranks(ms_rank)
     value = samples_per_step * args.steps / (ms * 1e-3)
 
-    # end to end through the drop-in call: numpy in -> numpy out, H2D and D2H inside the timed region
+    # ---- end to end through the drop-in call: numpy in -> numpy out, H2D and D2H inside the timed region ----
     for _ in range(max(1, min(args.warmup, 3))):
         voc(mel_host)
     barrier()
@@ -304,40 +475,104 @@ def run_ours(args):
     barrier()
     e2e_ms = max(s0.elapsed_time(s1), wall_ms)
     assert wav.shape == (B, T * hop) and wav.dtype == np.float32
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms, e2e_all = timer.max_over_ranks(e2e_ms)
     e2e_value = samples_per_step * args.steps / (e2e_ms * 1e-3)
 
-    # the bf16 single-pass tensor-core mode, reported separately (BASELINE config 3)
-    secondary = None
-    if not args.no_secondary and args.precision != "bf16":
-        ms2, _, recs2 = time_device_steps(eng, stream, mel_dev, out_dev, B, T, "bf16", args.steps, args.warmup, barrier)
-        if world > 1:
-            t = torch.tensor([ms2], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = float(t.item())
-        rl2 = work.layer_roofline_seconds(voc.model.config, B, T, 2, peaks["tflops"] * 1e12, peaks["gbs"] * 1e9)
-        secondary = {"dtype": "bf16", "value": samples_per_step * args.steps / (ms2 * 1e-3), "unit": "samples/s",
-                     "ms_per_step": ms2 / args.steps, "layer_roofline_ms": rl2 * 1e3, "layer_roofline_frac": rl2 * 1e3 / (ms2 / args.steps),
-                     "roofline": roofline_from_records(recs2, peaks, precision="bf16"),
-                     "roofline_other_kernels": other_rooflines(recs2, peaks, "bf16", roofline_from_records(recs2, peaks, precision="bf16")),
-                     "tolerance": "max-abs 1.5e-1 vs oracle on loud weights (tests/test_gpu_parity.py); 1e-3 at default init"}
+    # ---- per-launch records for the roofline: a separate profiled pass (events around every launch, no graph) ----
+    prof_steps = max(1, min(args.steps, 5))
+    ms_prof, _, recs = timer.run(mel_dev, out_dev, B, T, args.precision, prof_steps, 1, profile=True)
 
-    # the north-star's own target case (BASELINE.json: V1 at batch 32 x 10 s, bf16 tensor-core mode, 1 GPU: >= 50 % of the
-    # per-layer roofline), reported beside the headline; single GPU only, 5 steps
+    def mode_leg(mode, batch, mel_d, out_d, steps, warm, cfg):
+        """One single-pass tensor-core mode on (batch, T): production timing + a profiled pass for its kernel records."""
+        m, _, _ = timer.run(mel_d, out_d, batch, T, mode, steps, warm)
+        m, _ = timer.max_over_ranks(m)
+        rl = work.layer_roofline_seconds(cfg, batch, T, 2, P, BW)
+        return m / steps, rl
+
+    secondary = {}
     north = None
-    if world == 1 and not args.no_secondary:
-        B32 = 32
-        mel32 = torch.randn(B32, 80, T, device="cuda")
-        out32 = torch.empty(B32, T * hop, dtype=torch.float32, device="cuda")
-        ms32, _, _ = time_device_steps(eng, stream, mel32, out32, B32, T, "bf16", 5, 3, barrier)
-        rl32 = work.layer_roofline_seconds(voc.model.config, B32, T, 2, peaks["tflops"] * 1e12, peaks["gbs"] * 1e9)
-        north = {"workload": f"HiFiGAN V1, {B32} x {T}-frame (10 s) mels, bf16, 1 GPU", "ms_per_step": ms32 / 5,
-                 "value": B32 * T * hop * 5 / (ms32 * 1e-3), "unit": "samples/s", "layer_roofline_ms": rl32 * 1e3,
-                 "layer_roofline_frac": rl32 * 1e3 / (ms32 / 5), "target_frac": 0.5}
-        del mel32, out32
+    sweep = None
+    small = {}
+    longform = None
+    strong = None
+    tf32_peak = None
+    if not args.no_secondary:
+        # the single-pass tensor-core modes on the headline workload (BASELINE config 3's mode), reported separately
+        for mode in ("bf16", "fp16"):
+            if mode == args.precision:
+                continue
+            ms_m, rl = mode_leg(mode, B, mel_dev, out_dev, args.steps, args.warmup, voc.model.config)
+            _, _, recs_m = timer.run(mel_dev, out_dev, B, T, mode, 2, 1, profile=True)
+            dom = roofline_from_records(recs_m, peaks, precision=mode)
+            secondary[mode] = {
+                "dtype": mode, "value": samples_per_step / (ms_m * 1e-3), "unit": "samples/s", "ms_per_step": ms_m,
+                "layer_roofline_ms": rl * 1e3, "layer_roofline_frac": rl * 1e3 / ms_m, "roofline": dom,
+                "roofline_other_kernels": other_rooflines(recs_m, peaks, mode, dom),
+                "tolerance": {"bf16": "max-abs <= 6e-2 vs oracle on loud weights (output std 0.23), 1.5e-1 on the loud realistic-mel golden; "
+                                      "1e-3 at default init (tests/test_gpu_parity.py)",
+                              "fp16": "max-abs <= 8e-3 vs oracle on loud weights (TF32-class; emulation 2.2e-3 at T = 64), 3e-2 on the loud "
+                                      "realistic-mel golden; 1e-3 at default init (tests/test_gpu_parity.py)"}[mode]}
+        # the north-star's own target case (BASELINE.json: V1 at batch 32 x 10 s, 16-bit tensor-core mode, 1 GPU: >= 50 % of the
+        # per-layer roofline); single GPU only
+        if world == 1:
+            B32 = 32
+            mel32 = torch.randn(B32, 80, T, device="cuda")
+            out32 = torch.empty(B32, T * hop, dtype=torch.float32, device="cuda")
+            north = {"workload": f"HiFiGAN V1, {B32} x {T}-frame (10 s) mels, 1 GPU", "target_frac": 0.5, "steps": 8}
+            for mode in ("bf16", "fp16"):
+                ms_m, rl = mode_leg(mode, B32, mel32, out32, 8, 3, voc.model.config)
+                north[mode] = {"ms_per_step": ms_m, "value": B32 * T * hop / (ms_m * 1e-3), "unit": "samples/s",
+                               "layer_roofline_ms": rl * 1e3, "layer_roofline_frac": rl * 1e3 / ms_m}
+            del mel32, out32
+            # BASELINE config 3 at N = 1: batch sweep in the bf16 tensor-core mode
+            sweep = []
+            for b in (1, 2, 4, 8, 16, 32, 64):
+                mel_b = torch.randn(b, 80, T, device="cuda")
+                out_b = torch.empty(b, T * hop, dtype=torch.float32, device="cuda")
+                ms_m, rl = mode_leg("bf16", b, mel_b, out_b, 8 if b <= 16 else 5, 3, voc.model.config)
+                sweep.append({"batch": b, "ms_per_step": ms_m, "value": b * T * hop / (ms_m * 1e-3), "layer_roofline_frac": rl * 1e3 / ms_m})
+                del mel_b, out_b
+            # BASELINE config 5: the small generators at batch 64 (memory-bound regime)
+            for name, cfg in (("v2_b64", E.V2), ("v3_b64", E.V3)):
+                torch.manual_seed(0)
+                kw = dict(upsample_rates=list(cfg.upsample_rates), upsample_kernel_sizes=list(cfg.upsample_kernel_sizes),
+                          upsample_initial_channel=cfg.upsample_initial_channel, resblock_kernel_sizes=list(cfg.resblock_kernel_sizes),
+                          resblock_dilation_sizes=[list(d) for d in cfg.resblock_dilation_sizes])
+                m2 = hp.HiFiGANModel(**kw)
+                m2.eval().to(f"cuda:{local_rank}")
+                e2 = m2.engine
+                t2 = Timer(e2, torch.cuda.ExternalStream(e2.stream), barrier, world)
+                mel_b = torch.randn(64, 80, T, device="cuda")
+                out_b = torch.empty(64, T * e2.hop, dtype=torch.float32, device="cuda")
+                rec = {"workload": f"{name.split('_')[0].upper()} ({'C0=128' if name.startswith('v2') else 'C0=256, rates 8/8/4'}), 64 x {T} frames, 1 GPU"}
+                for mode in ("bf16", "fp16", "bf16x3"):
+                    m, _, _ = t2.run(mel_b, out_b, 64, T, mode, 5, 3)
+                    rl = work.layer_roofline_seconds(cfg, 64, T, 2 if mode != "bf16x3" else 4, P if mode != "bf16x3" else P / 2, BW)
+                    rec[mode] = {"ms_per_step": m / 5, "value": 64 * T * e2.hop / (m / 5 * 1e-3), "layer_roofline_ms": rl * 1e3,
+                                 "layer_roofline_frac": rl * 1e3 / (m / 5)}
+                small[name] = rec
+                del mel_b, out_b
+                e2.close()
+            tf32_peak = measure_tf32_peak()
+        else:
+            # BASELINE config 3 at N > 1: a FIXED global batch of 64 utterances sharded over the N GPUs (strong scaling)
+            from iris_tts_b200 import sharding
+
+            s, e = sharding.batch_shards(64, world)[rank]
+            bl = e - s
+            mel_b = torch.randn(max(bl, 1), 80, T, device="cuda")
+            out_b = torch.empty(max(bl, 1), T * hop, dtype=torch.float32, device="cuda")
+            strong = {"workload": f"HiFiGAN V1, global batch 64 x {T} frames sharded over {world} GPUs ({64 // world} per GPU), no collective"}
+            for mode in ("bf16", args.precision):
+                m, _, _ = timer.run(mel_b, out_b, max(bl, 1), T, mode, 5, 3)
+                m, _ = timer.max_over_ranks(m)
+                strong[mode] = {"ms_per_step": m / 5, "value": 64 * T * hop / (m / 5 * 1e-3), "unit": "samples/s"}
+            del mel_b, out_b
+        # BASELINE config 4: the 120 s mel (every rank takes part)
+        longform = {}
+        for mode in ("bf16x3", "bf16"):
+            longform[mode] = longform_leg(voc.model, mode, world, rank)
+        voc.model.precision = args.precision
 
     if rank != 0:
         if world > 1:
@@ -345,48 +580,74 @@ def run_ours(args):
         return
 
     # R_layer = sum_l max(F_l/P, Q_l/BW).  fp32-class arithmetic is rated against the TF32-class tensor peak
-    # (P/2) with 4-byte activations, the bf16 mode against the bf16 peak with 2-byte activations.
-    rl_bf16 = work.layer_roofline_seconds(voc.model.config, B, T, 2, peaks["tflops"] * 1e12, peaks["gbs"] * 1e9)
-    rl_fp32 = work.layer_roofline_seconds(voc.model.config, B, T, 4, peaks["tflops"] * 0.5e12, peaks["gbs"] * 1e9)
-    rl = rl_bf16 if args.precision == "bf16" else rl_fp32
+    # with 4-byte activations (measured here when possible, else bf16 peak / 2), the 16-bit modes against the bf16 peak, 2 bytes.
+    rl_bf16 = work.layer_roofline_seconds(voc.model.config, B, T, 2, P, BW)
+    rl_fp32 = work.layer_roofline_seconds(voc.model.config, B, T, 4, P * 0.5, BW)
+    rl_fp32_meas = work.layer_roofline_seconds(voc.model.config, B, T, 4, tf32_peak * 1e12, BW) if tf32_peak else None
+    rl = rl_bf16 if args.precision in ("bf16", "fp16") else rl_fp32
     ms_step = ms / args.steps
     by_kernel = {}
     for r in recs:
         k = by_kernel.setdefault(r["kernel"], {"ms": 0.0, "launches": 0})
-        k["ms"] += r["ms"] / args.steps
+        k["ms"] += r["ms"] / prof_steps
         k["launches"] += 1
     for k in by_kernel.values():
-        k["launches"] //= args.steps
+        k["launches"] //= prof_steps
+    dom = roofline_from_records(recs, peaks, precision=args.precision)
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3 (split-bf16 operands, 3 tcgen05 MMAs, fp32 accumulate: fp32-class)", "bf16": "bf16",
+        "dtype": {"bf16x3": "bf16x3 (split-bf16 operands, 3 tcgen05 MMAs, fp32 accumulate: fp32-class)", "bf16": "bf16", "fp16": "f16",
                   "fp32": "f32"}[args.precision],
         "data": "synthetic", "x_realtime": value / SAMPLE_RATE,
         "config": {"workload": f"HiFiGAN V1 random-init (seed 0) via infer_hifigan path, {B} x {T}-frame (10 s) mels per GPU, "
                                f"{args.precision}", "batch_per_gpu": B, "frames": T, "global_batch": B * world, "sharding": f"batch x{world}, no collective",
-                   "l2": "no flush: each step streams ~3 GB of stage activations (452 MB per tensor) >> 126 MB L2"},
+                   "l2": "no flush: each step streams ~3 GB of stage activations (452 MB per tensor) >> 126 MB L2",
+                   "timed_path": "production: one CUDA graph per forward, programmatic dependent launch, no events inside the timed region"},
         "clocks": clocks,
+        "per_rank_ms": {"min": min(ms_all) / args.steps, "median": statistics.median(ms_all) / args.steps, "max": max(ms_all) / args.steps,
+                        "all": [m / args.steps for m in ms_all],
+                        "e2e_all": [m / args.steps for m in e2e_all]},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(B * 80 * T * 4),
-                "d2h_bytes_per_step": int(B * T * hop * 4), "api": "iris.hifigan_pretrained.HiFiGANGenerator.__call__(np.ndarray)"},
+                "d2h_bytes_per_step": int(B * T * hop * 4), "api": "iris.hifigan_pretrained.HiFiGANGenerator.__call__(np.ndarray)",
+                "gap_vs_device": e2e_ms / ms - 1.0},
         "gpu_launches": int(launches),
-        "roofline": roofline_from_records(recs, peaks, precision=args.precision),
-        "roofline_other_kernels": other_rooflines(recs, peaks, args.precision, roofline_from_records(recs, peaks, precision=args.precision)),
+        "roofline": dom,
+        "roofline_other_kernels": other_rooflines(recs, peaks, args.precision, dom),
         "layer_roofline": {"ms": rl * 1e3, "frac": rl * 1e3 / ms_step,
-                           "definition": "sum_l max(F_l/P, Q_l/BW) (SURVEY 8d): " + ("bf16 peak, 2-byte activations" if args.precision == "bf16" else
-                                         "fp32-class mode: P = bf16 peak / 2 (TF32-class), 4-byte activations"),
-                           "bf16_definition_ms": rl_bf16 * 1e3, "bf16_definition_frac": rl_bf16 * 1e3 / ms_step},
+                           "definition": "sum_l max(F_l/P, Q_l/BW) (SURVEY 8d): " + ("bf16 peak, 2-byte activations" if args.precision in ("bf16", "fp16") else
+                                         "fp32-class mode: P = bf16 peak / 2 (TF32-class, SURVEY's provisional figure), 4-byte activations"),
+                           "bf16_definition_ms": rl_bf16 * 1e3, "bf16_definition_frac": rl_bf16 * 1e3 / ms_step,
+                           "tf32_peak_measured_tflops": tf32_peak,
+                           "measured_tf32_definition_ms": rl_fp32_meas * 1e3 if rl_fp32_meas else None,
+                           "measured_tf32_definition_frac": rl_fp32_meas * 1e3 / ms_step if rl_fp32_meas else None},
         "kernels_ms_per_step": by_kernel,
+        "profiled_pass_ms_per_step": ms_prof / prof_steps,
     }
-    if secondary:
-        line["bf16_mode"] = secondary
+    if "bf16" in secondary:
+        line["bf16_mode"] = secondary["bf16"]
+    if "fp16" in secondary:
+        line["fp16_mode"] = secondary["fp16"]
     if north:
-        line["north_star_b32_bf16"] = north
+        line["north_star_b32"] = north
+        line["north_star_b32_bf16"] = dict(north["bf16"], workload=north["workload"] + ", bf16", target_frac=0.5)
+    if sweep:
+        line["batch_sweep_bf16"] = sweep
+    line.update(small)
+    if strong:
+        line["strong_scaling_b64"] = strong
+    if longform:
+        line["longform_120s"] = longform
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_oracle_throughput(T, 3, 2)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                                "sample": f"1 utterance x {T} frames, 3 timed forwards after 2 warm-ups, oracle/hifigan_oracle.py "
-                                          f"(torch oneDNN fp32), {r['threads']} threads", "ms_per_utterance": r["ms_per_step"]}
+        gen = CpuGenerator()
+        r = gen.time(1, T, 3, 2)
+        r1 = gen.time(1, 256, 3, 2)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": gen.cores, "kind": gen.kind,
+                                "sample": f"1 utterance x {T} frames, 3 timed forwards after 2 warm-ups, {gen.what}, {gen.threads} threads",
+                                "ms_per_utterance": r["ms_per_step"],
+                                "config1_b1_t256": {"value": r1["value"], "ms": r1["ms_per_step"], "x_realtime": r1["value"] / SAMPLE_RATE,
+                                                    "what": "BASELINE config 1 shape (B = 1, 256 frames) on the torch path"},
+                                "keras_jax": keras_jax_status()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define HFG_ABI_VERSION 1
+#define HFG_ABI_VERSION 2
 #define HFG_MAX_UPSAMPLES 8
 #define HFG_MAX_KERNELS 8
 #define HFG_MAX_DILATIONS 8
@@ -56,7 +56,9 @@ typedef enum hfg_status {
 typedef enum hfg_precision {
     HFG_PREC_FP32 = 0,    /* fp32 FFMA on CUDA cores, fp32 activations (bit-faithful class)  */
     HFG_PREC_BF16 = 1,    /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulation        */
-    HFG_PREC_BF16X3 = 2   /* tcgen05, operands split hi+lo bf16, 3 MMAs: fp32-class accuracy */
+    HFG_PREC_BF16X3 = 2,  /* tcgen05, operands split hi+lo bf16, 3 MMAs: fp32-class accuracy */
+    HFG_PREC_FP16 = 3     /* tcgen05 kind::f16, fp16 operands (11-bit significand: TF32-class accuracy at the bf16 mode's speed
+                             and bytes), fp32 TMEM accumulation; activations saturate at +-65504                             */
 } hfg_precision;
 
 /* hfg_forward flags */
@@ -140,6 +142,11 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
  * *fused (optional) reports which. */
 int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int32_t B, int32_t L, float* y,
                  int32_t precision, int32_t* fused);
+/* The same step as the LAST one of a ResBlock whose branch sum is folded into its epilogue (:133-137):
+ * y = (x + convs2[m](lrelu(convs1[m](lrelu(x)))) + mrf_sum) * out_scale; mrf_sum [B][C][L] is the running sum of the
+ * previous branches' outputs (NULL: plain hfg_run_pair), out_scale = 1 or 1/num_kernels. */
+int hfg_run_pair_mrf(hfg_engine* e, int32_t resblock, int32_t m, const float* x, const float* mrf_sum, float out_scale,
+                     int32_t B, int32_t L, float* y, int32_t precision, int32_t* fused);
 
 /* After hfg_forward(..., HFG_KEEP_TAPS): copy an intermediate activation to
  * host as fp32 [B][C][L] (reference layout).  Names: "conv_pre", "ups.<i>",

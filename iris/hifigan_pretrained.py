@@ -8,7 +8,8 @@ initialisation, tensors in/out - never for the arithmetic of the forward.  There
 path: constructing a model without a CUDA device raises.
 
 Precision: ``IRIS_HIFIGAN_PRECISION`` = ``bf16x3`` (default; tcgen05 with split-bf16 operands,
-fp32-class accuracy), ``fp32`` (CUDA-core FFMA) or ``bf16`` (tcgen05 single pass, looser tolerance).
+fp32-class accuracy), ``fp32`` (CUDA-core FFMA), ``fp16`` (tcgen05 single pass, fp16 operands: TF32-class
+accuracy) or ``bf16`` (tcgen05 single pass, bf16 operands: loosest tolerance).
 """
 from __future__ import annotations
 
@@ -59,6 +60,32 @@ class ResBlock:
     def _get_padding(self, kernel_size: int, dilation: int = 1):
         return int((kernel_size * dilation - dilation) / 2)
 
+    def __setstate__(self, state):
+        # A ResBlock pickled by the REFERENCE module (an nn.Module: ``_modules`` holds convs1 / convs2) is rebuilt as this
+        # class without __init__; keep its modules so HiFiGANModel.__setstate__ can read weights and architecture from them.
+        self.__dict__.update(state)
+        mods = state.get("_modules")
+        if mods and "convs1" in mods:
+            convs1 = list(mods["convs1"])
+            self.channels = int(convs1[0].in_channels)
+            self.kernel_size = int(convs1[0].kernel_size[0])
+            self.dilations = [int(c.dilation[0]) for c in convs1]
+
+
+def _walk_module_tensors(obj, prefix: str, out: Dict[str, "torch.Tensor"]) -> None:
+    """state_dict() of an nn.Module tree whose custom classes were unpickled as plain objects (their ``__dict__`` still has
+    torch's ``_parameters`` / ``_buffers`` / ``_modules``)."""
+    d = obj.__dict__
+    for name, p in (d.get("_parameters") or {}).items():
+        if p is not None:
+            out[prefix + name] = p.detach()
+    for name, b in (d.get("_buffers") or {}).items():
+        if b is not None:
+            out[prefix + name] = b.detach()
+    for name, m in (d.get("_modules") or {}).items():
+        if m is not None:
+            _walk_module_tensors(m, prefix + name + ".", out)
+
 
 class HiFiGANModel:
     """Reference ``HiFiGANModel`` (:74-143) on the B200 engine.
@@ -96,6 +123,39 @@ class HiFiGANModel:
         self._engine = None
         self._device_index: Optional[int] = None
         self._dirty = True
+
+    # -- pickling -------------------------------------------------------------
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None          # the CUDA engine handle is rebuilt on first use
+        st["_dirty"] = True
+        return st
+
+    def __setstate__(self, state):
+        """``torch.load`` of a checkpoint that holds a pickled *model object* (reference :168-171 uses such an object as
+        is).  A model pickled by the reference has class path ``iris.hifigan_pretrained.HiFiGANModel``, so it is rebuilt
+        as THIS class without running ``__init__`` and ``state`` is torch's nn.Module ``__dict__``: read the architecture
+        and the parameters from its submodules and re-host them on the engine."""
+        if "_modules" not in state:
+            self.__dict__.update(state)
+            return
+        mods = state["_modules"]
+        pre, ups, blocks = mods["conv_pre"], list(mods["ups"]), list(mods["resblocks"])
+        nk = int(state.get("num_kernels") or (len(blocks) // max(len(ups), 1)))
+        shell = type("_Shell", (), {})()
+        shell.__dict__.update(state)
+        sd: Dict[str, "torch.Tensor"] = {}
+        _walk_module_tensors(shell, "", sd)
+        self.__init__(
+            in_channels=int(pre.in_channels),
+            upsample_rates=[int(u.stride[0]) for u in ups],
+            upsample_kernel_sizes=[int(u.kernel_size[0]) for u in ups],
+            upsample_initial_channel=int(pre.out_channels),
+            resblock_kernel_sizes=[int(b.kernel_size) for b in blocks[:nk]],
+            resblock_dilation_sizes=[list(b.dilations) for b in blocks[:nk]],
+        )
+        self.load_state_dict(sd, strict=True)
+        self.training = bool(state.get("training", False))
 
     # -- parameters ----------------------------------------------------------
     def _default_init(self) -> Dict[str, "torch.Tensor"]:
@@ -252,9 +312,14 @@ class HiFiGANGenerator:
 
         checkpoint = torch.load(str(self.checkpoint_path), map_location="cpu", weights_only=False)
 
-        if hasattr(checkpoint, "eval") and hasattr(checkpoint, "state_dict"):
-            # A pickled model object (reference :168-171 uses it as is).  Its parameters are
-            # re-hosted on the engine; the architecture is read from its tensor shapes.
+        if isinstance(checkpoint, HiFiGANModel):
+            # A pickled model object (reference :168-171 uses it as is): HiFiGANModel.__setstate__ has already read its
+            # architecture (any constructor arguments, not only the defaults) and parameters from the pickled submodules.
+            self.model = checkpoint
+            logger.info("Loaded model directly from checkpoint")
+        elif hasattr(checkpoint, "eval") and hasattr(checkpoint, "state_dict"):
+            # Some other module object with the reference's parameter names: its parameters are re-hosted on the engine;
+            # the architecture is read from its tensor shapes (default rates / dilations only).
             state_dict = checkpoint.state_dict()
             self.model = _model_from_state_dict(state_dict)
             logger.info("Loaded model directly from checkpoint")

@@ -5,14 +5,14 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
 
-HFG_ABI_VERSION = 1
+HFG_ABI_VERSION = 2
 MAX_UPSAMPLES = MAX_KERNELS = MAX_DILATIONS = 8
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
 MEL_ON_DEVICE, WAVE_ON_DEVICE, KEEP_TAPS, NO_SYNC = 1, 2, 4, 8
 
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 
 
 class HfgConfig(ctypes.Structure):
@@ -54,6 +54,7 @@ SIGNATURES = {
                                 POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "hfg_run_layer": (c_int, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32]),
     "hfg_run_pair": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "hfg_run_pair_mrf": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "hfg_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_size_t)]),
 }
 

@@ -38,6 +38,20 @@ int cuda_fail(cudaError_t e, const char* what) {
         cudaError_t _e = (expr);                              \
         if (_e != cudaSuccess) return cuda_fail(_e, #expr);   \
     } while (0)
+// Every ABI entry point runs on the engine's device and leaves the caller's current device as it found it
+// (a torch process that calls an engine on cuda:1 keeps torch.cuda.current_device() == 0).
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != d) err = cudaSetDevice(d);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define GUARD(e)                       \
+    DeviceGuard _guard((e)->device);   \
+    CK(_guard.err)
 #define RET(expr)                     \
     do {                              \
         int _r = (expr);              \
@@ -63,6 +77,7 @@ struct Layer {
     float* d_w32_tc = nullptr;         // conv_post only: [k][cin_pad], zero padded
     __nv_bfloat16* d_wb_hi = nullptr;  // [taps*Np][cin_pad]
     __nv_bfloat16* d_wb_lo = nullptr;
+    __nv_bfloat16* d_wh = nullptr;     // same layout, fp16 values (HFG_PREC_FP16); 16-bit storage shares the pointer type
 };
 
 enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_PAIR, S_POST32, S_ACCUM, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP };
@@ -84,7 +99,7 @@ struct Step {
     const float* w = nullptr;
     const float* bias = nullptr;
     int B = 0, L = 0, C = 0, k = 0, cpad = 0;
-    int flag0 = 0, flag1 = 0;
+    int flag0 = 0, flag1 = 0, f16 = 0;
     float fval = 0.f;
     size_t n = 0;
     std::string tap_name;
@@ -100,6 +115,13 @@ struct Plan {
     size_t bytes = 0;
     bool keep_taps = false;
     std::vector<size_t> guards;   // HFG_GUARD: canary regions between the workspace buffers
+    // CUDA graph of the plan's kernel launches (captured on the second forward of a plan; the H2D / D2H copies stay outside
+    // because their host pointers change per call).  Programmatic-dependent-launch edges survive capture.
+    cudaGraphExec_t graph = nullptr;
+    bool graph_failed = false;
+    int runs = 0;
+    int kernels = 0;              // launches per forward (steps that are not tap copies)
+    ~Plan() { if (graph) cudaGraphExecDestroy(graph); }
 };
 
 struct Tap {
@@ -241,8 +263,8 @@ Layer* find_layer(hfg_engine* e, const char* name) {
 }
 
 void free_layer_dev(Layer& L) {
-    cudaFree(L.d_w32); cudaFree(L.d_bias); cudaFree(L.d_wb_hi); cudaFree(L.d_wb_lo); cudaFree(L.d_bias_tc); cudaFree(L.d_w32_tc);
-    L.d_w32 = L.d_bias = L.d_bias_tc = L.d_w32_tc = nullptr; L.d_wb_hi = L.d_wb_lo = nullptr;
+    cudaFree(L.d_w32); cudaFree(L.d_bias); cudaFree(L.d_wb_hi); cudaFree(L.d_wb_lo); cudaFree(L.d_bias_tc); cudaFree(L.d_w32_tc); cudaFree(L.d_wh);
+    L.d_w32 = L.d_bias = L.d_bias_tc = L.d_w32_tc = nullptr; L.d_wb_hi = L.d_wb_lo = L.d_wh = nullptr;
 }
 
 inline uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat16_rn
@@ -252,6 +274,21 @@ inline uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2bfloat1
     return (uint16_t)(u >> 16);
 }
 inline float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+inline uint16_t f2h(float f) {   // fp32 -> fp16, round-to-nearest-even, saturating to +-65504 (like cvt.rn.satfinite.f16.f32)
+    uint32_t u; memcpy(&u, &f, 4);
+    const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+    const uint32_t ax = u & 0x7fffffffu;
+    if (ax > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);          // NaN
+    if (ax >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);         // >= 65520 rounds past the largest finite value: saturate
+    if (ax < 0x33000001u) return sign;                                 // <= 2^-25: rounds to zero
+    int e = (int)(ax >> 23) - 127;
+    uint32_t m = (ax & 0x7fffffu) | 0x800000u;                         // 24-bit significand
+    int shift = e < -14 ? 13 + (-14 - e) : 13;                         // subnormal results lose extra bits
+    uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+    uint32_t h = e < -14 ? q : (((uint32_t)(e + 15) << 10) + (q - 0x400u));   // a carry out of the significand bumps the exponent
+    return (uint16_t)(sign | h);
+}
 
 int upload_layer(Layer& L) {
     free_layer_dev(L);
@@ -296,7 +333,7 @@ int upload_layer(Layer& L) {
     CK(cudaMemcpy(L.d_w32, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
     // tensor-core pack: [taps*Np_tc][cin_pad] bf16 hi/lo, K-major (rows of padded output channels and columns of padded
     // input channels stay zero)
-    std::vector<uint16_t> hi((size_t)L.taps * L.Np_tc * L.cin_pad, 0), lo(hi.size(), 0);
+    std::vector<uint16_t> hi((size_t)L.taps * L.Np_tc * L.cin_pad, 0), lo(hi.size(), 0), hf(hi.size(), 0);
     for (int j = 0; j < L.taps; ++j)
         for (int ci = 0; ci < Cin; ++ci)
             for (int n = 0; n < L.Np; ++n) {
@@ -306,11 +343,14 @@ int upload_layer(Layer& L) {
                 const size_t o = ((size_t)j * L.Np_tc + n_tc) * L.cin_pad + ci;
                 hi[o] = h;
                 lo[o] = f2bf(v - bf2f(h));
+                hf[o] = f2h(v);
             }
     CK(cudaMalloc(&L.d_wb_hi, hi.size() * 2));
     CK(cudaMalloc(&L.d_wb_lo, lo.size() * 2));
+    CK(cudaMalloc(&L.d_wh, hf.size() * 2));
     CK(cudaMemcpy(L.d_wb_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(L.d_wb_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.d_wh, hf.data(), hf.size() * 2, cudaMemcpyHostToDevice));
     return HFG_OK;
 }
 
@@ -493,8 +533,14 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     typedef __nv_bfloat16 bf;
     const hfg_config& c = e->cfg;
     const bool x3 = prec == HFG_PREC_BF16X3;
+    const int f16 = prec == HFG_PREC_FP16 ? 1 : 0;   // single-plane mode with fp16 operand planes / weights instead of bf16
     const int npass = x3 ? 3 : 1;
+    auto wts_hi = [&](const Layer& L) { return f16 ? L.d_wh : L.d_wb_hi; };
     const int a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
+    // MRF sum folded into the producers (:133-137): the last convs2 of branch j >= 1 adds the running sum of branches 0..j-1 in its
+    // epilogue, the last branch also applies 1/nk and writes the stage output -- no separate combine pass.  The tap plan keeps
+    // the separate pass (it must expose every branch output).
+    const bool mrf_fold = env_flag("HFG_MRF_FOLD", 1) != 0 && !keep_taps && c.num_kernels > 1;
     const int snake = env_flag("HFG_SNAKE", 1);   // alternate the tile direction of consecutive convs (L2 reuse)
     int n_umma2 = 0;
     const int c0 = c.upsample_initial_channel;
@@ -563,40 +609,42 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     };
     // one conv on planes: persistent pipelined kernel where it applies, the v1 kernel otherwise
     auto umma = [&](const Layer& L, int Lin, Planes x, Planes res, float* y_raw, Planes y, const Layer* acct = nullptr,
-                    int acct_Lin = 0) -> int {
+                    int acct_Lin = 0, Planes mrf = Planes(), float out_scale = 1.f) -> int {
         if (!real) return HFG_OK;
         Step s{};
         UmmaConvParams p;
         memset(&p, 0, sizeof p);
         p.g = geom_tc(L, B, Lin);
-        p.cin_pad = L.cin_pad; p.kc = L.kc; p.npass = npass;
+        p.cin_pad = L.cin_pad; p.kc = L.kc; p.npass = npass; p.f16 = f16;
         p.bias = L.d_bias_tc; p.res_hi = res.hi; p.res_lo = x3 ? res.lo : nullptr;
+        p.mrf_hi = mrf.hi; p.mrf_lo = x3 ? mrf.lo : nullptr; p.out_scale = out_scale;
         p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
         p.a_per_tap = a_per_tap;
         p.reverse = snake ? (n_umma2++ & 1) : 0;
         if (acct) work(s, *acct, acct_Lin, x3 ? 4 : 2);   // a time-folded twin: report the reference layer's algorithmic work
         else work(s, L, Lin, x3 ? 4 : 2);   // two bf16 planes carry what an fp32 activation would
-        if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, L.d_wb_hi, L.d_wb_lo, e->sm_count) == HFG_OK) {
+        if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, wts_hi(L), L.d_wb_lo, e->sm_count) == HFG_OK) {
             s.kind = S_UMMA2;
         } else {
             s.kind = S_UMMA;
-            RET(plan_conv_umma(&s.ul, p, x.hi, x.lo, L.d_wb_hi, L.d_wb_lo));
+            RET(plan_conv_umma(&s.ul, p, x.hi, x.lo, wts_hi(L), L.d_wb_lo));
         }
         plan->steps.push_back(std::move(s));
         return HFG_OK;
     };
     // convs1[m] -> lrelu -> convs2[m] -> + x  (:66-70) as one launch where the fused kernel applies (C <= 64); false otherwise
     auto pair = [&](const Layer& c1, const Layer& c2, int Lrows, Planes x, Planes y, char const* label, const Layer* a1 = nullptr,
-                    const Layer* a2 = nullptr, int acct_L = 0) -> bool {
+                    const Layer* a2 = nullptr, int acct_L = 0, Planes mrf = Planes(), float out_scale = 1.f) -> bool {
         if (!real) return false;
         if (c1.cin_pad != c1.cout_tc || c2.cin_pad != c1.cin_pad || c2.cout_tc != c1.cout_tc || c2.dil != 1) return false;
         PairParams p;
         memset(&p, 0, sizeof p);
-        p.B = B; p.L = Lrows; p.C = c1.cin_pad; p.k1 = c1.k; p.k2 = c2.k; p.d = c1.dil; p.npass = npass;
+        p.B = B; p.L = Lrows; p.C = c1.cin_pad; p.k1 = c1.k; p.k2 = c2.k; p.d = c1.dil; p.npass = npass; p.f16 = f16;
         p.bias1 = c1.d_bias_tc; p.bias2 = c2.d_bias_tc;
         p.x_hi = x.hi; p.x_lo = x3 ? x.lo : nullptr;
-        p.w1_hi = c1.d_wb_hi; p.w1_lo = c1.d_wb_lo; p.w2_hi = c2.d_wb_hi; p.w2_lo = c2.d_wb_lo;
+        p.w1_hi = wts_hi(c1); p.w1_lo = c1.d_wb_lo; p.w2_hi = wts_hi(c2); p.w2_lo = c2.d_wb_lo;
         p.y_hi = y.hi; p.y_lo = x3 ? y.lo : nullptr;
+        p.mrf_hi = mrf.hi; p.mrf_lo = x3 ? mrf.lo : nullptr; p.out_scale = out_scale;
         p.reverse = snake ? (n_umma2 & 1) : 0;
         if (!pair_supported(p)) return false;
         Step s{};
@@ -627,6 +675,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     };
     auto to_raw = [&](Planes p, float* raw, size_t rows, int C_tc, int C) {   // [rows][C_tc] planes -> [rows][C] fp32
         Step s{}; s.kind = S_P2RAW; s.b_in = p.hi; s.b_in_lo = x3 ? p.lo : nullptr; s.f_out = raw; s.n = rows; s.cpad = C_tc; s.C = C;
+        s.f16 = f16;
         push(std::move(s));
     };
     auto tap_planes = [&](const char* name, Planes p, int C, int L, bool dense = false) {   // dense: time-folded stage, no padding channels
@@ -640,7 +689,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     Planes xp;                      // activated planes (tensor-core family)
     if (any_tc) {
         { Step s{}; s.kind = S_MEL_CLBF; s.f_in = mel_dev; s.b_out = mel_p.hi; s.b_out_lo = mel_p.lo; s.B = B; s.C = c.in_channels;
-          s.L = T; s.cpad = pre.cin_pad; push(std::move(s)); }
+          s.L = T; s.cpad = pre.cin_pad; s.f16 = f16; push(std::move(s)); }
         RET(umma(pre, T, mel_p, Planes(), x0_raw, n_tc > 0 ? x0_p : Planes()));
         if (n_tc > 0) tap_planes("conv_pre", x0_p, c0, T); else tap("conv_pre", x0_raw, c0, T);
         x_raw = x0_raw; xp = x0_p;
@@ -683,11 +732,18 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                     const Layer& o2 = layer("resblocks.%d.convs2.%d", n, m);
                     const Layer& c1 = twin(o1);
                     const Layer& c2 = twin(o2);
-                    Planes xout = m == nd - 1 ? r_p[j] : pp[m & 1];
+                    const bool last_m = m == nd - 1;
+                    // folded MRF sum: the last step of branch j >= 1 adds r_p[j-1] (the running sum); the last branch writes
+                    // the stage output s_p = sum / nk
+                    const bool fold_in = mrf_fold && last_m && j > 0;
+                    const bool fold_out = mrf_fold && last_m && j == nk - 1;
+                    Planes xout = fold_out ? s_p : (last_m ? r_p[j] : pp[m & 1]);
+                    const Planes mrf_in = fold_in ? r_p[j - 1] : Planes();
+                    const float osc = fold_out ? 1.0f / (float)nk : 1.0f;
                     snprintf(nm, sizeof nm, "resblocks.%d.pair.%d", n, m);
-                    if (!pair(c1, c2, rows, xin, xout, nm, fold ? &o1 : nullptr, fold ? &o2 : nullptr, L)) {
+                    if (!pair(c1, c2, rows, xin, xout, nm, fold ? &o1 : nullptr, fold ? &o2 : nullptr, L, mrf_in, osc)) {
                         RET(umma(c1, rows, xin, Planes(), nullptr, xt_p, fold ? &o1 : nullptr, L));   // :66-67 (+ :68 in the epilogue)
-                        RET(umma(c2, rows, xt_p, xin, nullptr, xout, fold ? &o2 : nullptr, L));       // :69-70
+                        RET(umma(c2, rows, xt_p, xin, nullptr, xout, fold ? &o2 : nullptr, L, mrf_in, osc));   // :69-70 (+ :133-137)
                     }
                     xin = xout;
                 }
@@ -695,9 +751,10 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                 tap_planes(nm, r_p[j], ch, L, fold);
             }
             const bool fuse_post = last_stage && !keep_taps;   // the MRF mean of the last stage is computed inside conv_post
-            if (!fuse_post) {   // xs = sum_j r_j ; x = xs / nk  (:133-137)
+            if (!fuse_post && !mrf_fold) {   // xs = sum_j r_j ; x = xs / nk  (:133-137)
                 Step s{}; s.kind = S_MRF; s.n = ne;
                 memset(&s.mrf, 0, sizeof s.mrf);
+                s.mrf.f16 = f16;
                 for (int j = 0; j < nk; ++j) { s.mrf.hi[j] = r_p[j].hi; s.mrf.lo[j] = x3 ? r_p[j].lo : nullptr; }
                 s.mrf.nk = nk;
                 s.mrf.out_raw = (want_raw && ctc == ch) ? xs : nullptr;
@@ -752,7 +809,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
             // it forms the MRF mean itself; the tap plan hands it the already combined stage planes (nk = 1).
             s.kind = S_POSTMRF;
             memset(&s.mrf, 0, sizeof s.mrf);
-            if (keep_taps) { s.mrf.hi[0] = xp.hi; s.mrf.lo[0] = x3 ? xp.lo : nullptr; s.mrf.nk = 1; }
+            s.mrf.f16 = f16;
+            if (keep_taps || mrf_fold) { s.mrf.hi[0] = xp.hi; s.mrf.lo[0] = x3 ? xp.lo : nullptr; s.mrf.nk = 1; }
             else { for (int j = 0; j < nk; ++j) { s.mrf.hi[j] = r_p[j].hi; s.mrf.lo[j] = x3 ? r_p[j].lo : nullptr; } s.mrf.nk = nk; }
         } else {
             s.kind = S_POST32; s.f_in = x_raw;
@@ -795,6 +853,40 @@ const char* kind_label(StepKind k) {
     }
 }
 
+int run_plan(hfg_engine* e, Plan* plan);
+
+// Launches the plan's kernels: as ONE CUDA graph once the plan has run before (production path: no per-launch driver work
+// on the host, which is what bounds short inputs), directly otherwise (first forward of a shape, profiling, taps, canaries, ncu).
+int launch_plan(hfg_engine* e, Plan* plan) {
+    static const int use_graph = env_flag("HFG_GRAPH", 1);
+    const bool eligible = use_graph && !e->profiling && !plan->keep_taps && plan->guards.empty() && e->ncu_layers.empty();
+    if (eligible && !plan->graph && !plan->graph_failed && plan->runs >= 1) {
+        cudaGraph_t g = nullptr;
+        const uint64_t l0 = e->launches;
+        cudaError_t err = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+        if (err == cudaSuccess) {
+            const int r = run_plan(e, plan);
+            err = cudaStreamEndCapture(e->stream, &g);
+            if (r != HFG_OK && err == cudaSuccess) err = cudaErrorUnknown;
+        }
+        if (err == cudaSuccess) err = cudaGraphInstantiate(&plan->graph, g, 0);
+        if (g) cudaGraphDestroy(g);
+        e->launches = l0;   // capture enqueued nothing
+        if (err != cudaSuccess) {   // not fatal: keep launching kernel by kernel
+            cudaGetLastError();
+            plan->graph = nullptr;
+            plan->graph_failed = true;
+        }
+    }
+    ++plan->runs;
+    if (eligible && plan->graph) {
+        CK(cudaGraphLaunch(plan->graph, e->stream));
+        e->launches += (uint64_t)plan->kernels;
+        return HFG_OK;
+    }
+    return run_plan(e, plan);
+}
+
 int run_plan(hfg_engine* e, Plan* plan) {
     cudaStream_t st = e->stream;
     size_t nev = e->prof_used;
@@ -815,13 +907,13 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_UMMA: CK(launch_conv_umma(s.ul, st)); break;
             case S_UMMA2: CK(launch_conv_umma2(s.u2, st)); break;
             case S_PAIR: CK(launch_conv_pair(s.pl, st)); break;
-            case S_P2RAW: CK(launch_planes_to_raw(s.b_in, s.b_in_lo, s.f_out, s.n, s.cpad, s.C, st)); break;
+            case S_P2RAW: CK(launch_planes_to_raw(s.b_in, s.b_in_lo, s.f_out, s.n, s.cpad, s.C, s.f16, st)); break;
             case S_MRF: CK(launch_mrf_combine(s.mrf, s.n, st)); break;
             case S_POSTMRF: CK(launch_conv_post_mrf(s.mrf, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag1, st)); break;
             case S_POST32: CK(launch_conv_post_fp32(s.f_in, s.w, s.bias, s.f_out, s.B, s.L, s.C, s.k, s.flag0, s.flag1, st)); break;
             case S_ACCUM: CK(launch_accum_fp32(s.f_out, s.f_in, s.n, s.flag0, s.fval, st)); break;
             case S_MEL_CL32: CK(launch_transpose_cf_to_cl(s.f_in, s.f_out, s.B, s.C, s.L, st)); break;
-            case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, 0, st)); break;
+            case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, 0, s.f16, st)); break;
             case S_TAP: RET(store_tap(e, s)); break;   // a copy, not one of our kernels
         }
         if (ncu) cudaProfilerStop();
@@ -854,7 +946,8 @@ int ensure_arena(hfg_engine* e, size_t bytes) {
 }
 
 int check_prec(int prec) {
-    if (prec != HFG_PREC_FP32 && prec != HFG_PREC_BF16 && prec != HFG_PREC_BF16X3) return fail(HFG_ERR_INVALID, "unknown precision");
+    if (prec != HFG_PREC_FP32 && prec != HFG_PREC_BF16 && prec != HFG_PREC_BF16X3 && prec != HFG_PREC_FP16)
+        return fail(HFG_ERR_INVALID, "unknown precision");
     return HFG_OK;
 }
 
@@ -882,7 +975,8 @@ int hfg_create(const hfg_config* cfg, int device, hfg_engine** out) {
     const int n = hfg_device_count();
     if (n <= 0) return fail(HFG_ERR_CUDA, "hfg_create: no CUDA device available (this engine has no CPU fallback)");
     if (device < 0 || device >= n) return fail(HFG_ERR_INVALID, "hfg_create: device index out of range");
-    CK(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CK(guard.err);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -909,8 +1003,9 @@ int hfg_create(const hfg_config* cfg, int device, hfg_engine** out) {
 
 void hfg_destroy(hfg_engine* e) {
     if (!e) return;
-    cudaSetDevice(e->device);
+    DeviceGuard guard(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    e->plans.clear();
     for (auto& L : e->layers) free_layer_dev(L);
     for (auto& kv : e->folded) free_layer_dev(kv.second);
     for (auto& kv : e->taps) cudaFree(kv.second.dev);
@@ -976,7 +1071,7 @@ int hfg_set_weight_norm(hfg_engine* e, const char* layer, const float* g, const 
 
 int hfg_finalize(hfg_engine* e) {
     if (!e) return fail(HFG_ERR_INVALID, "hfg_finalize: null engine");
-    CK(cudaSetDevice(e->device));
+    GUARD(e);
     for (auto& L : e->layers)
         if (!L.set) return fail(HFG_ERR_STATE, "hfg_finalize: layer not set: " + L.name);
     CK(cudaStreamSynchronize(e->stream));
@@ -1012,7 +1107,7 @@ int hfg_profile_count(const hfg_engine* e) { return e ? (int)e->prof_recs.size()
 int hfg_profile_get(hfg_engine* e, int i, char* layer, size_t layer_len, char* kernel, size_t kernel_len, float* ms,
                     double* flops, double* bytes) {
     if (!e || i < 0 || i >= (int)e->prof_recs.size()) return fail(HFG_ERR_INVALID, "hfg_profile_get: bad index");
-    CK(cudaSetDevice(e->device));
+    GUARD(e);
     const auto& r = e->prof_recs[i];
     if (layer && layer_len) { strncpy(layer, r.label.c_str(), layer_len - 1); layer[layer_len - 1] = 0; }
     if (kernel && kernel_len) { strncpy(kernel, kind_label((StepKind)r.kind), kernel_len - 1); kernel[kernel_len - 1] = 0; }
@@ -1027,7 +1122,7 @@ int hfg_profile_get(hfg_engine* e, int i, char* layer, size_t layer_len, char* k
 
 int hfg_sync(hfg_engine* e) {
     if (!e) return fail(HFG_ERR_INVALID, "hfg_sync: null engine");
-    CK(cudaSetDevice(e->device));
+    GUARD(e);
     CK(cudaStreamSynchronize(e->stream));
     return HFG_OK;
 }
@@ -1040,7 +1135,7 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     const bool mel_dev = flags & HFG_MEL_ON_DEVICE, wave_dev = flags & HFG_WAVE_ON_DEVICE;
     const bool keep = flags & HFG_KEEP_TAPS;
     if ((flags & HFG_NO_SYNC) && !(mel_dev && wave_dev)) return fail(HFG_ERR_INVALID, "hfg_forward: HFG_NO_SYNC needs device pointers");
-    CK(cudaSetDevice(e->device));
+    GUARD(e);
 
     const auto key = std::make_tuple((int)B, (int)T, (int)precision, keep ? 1 : 0);
     auto it = e->plans.find(key);
@@ -1056,6 +1151,7 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
         plan->bytes = bytes;
         // All plans share the arena from offset 0: they run one after another on one stream.
         RET(build_plan(e, B, T, precision, keep, e->arena, plan.get(), nullptr));
+        for (const Step& st : plan->steps) plan->kernels += st.kind != S_TAP;
         it = e->plans.emplace(key, std::move(plan)).first;
     }
     Plan* plan = it->second.get();
@@ -1065,7 +1161,7 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     // stand-in for a memcheck pass: a kernel that writes past the end (or before the start) of a plane trips the next canary.
     for (size_t off : plan->guards) CK(cudaMemsetAsync(e->arena + off, kGuardByte, kGuardBytes, e->stream));
     CK(cudaMemcpyAsync(plan->mel_dev, mel, mel_bytes, mel_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
-    RET(run_plan(e, plan));
+    RET(launch_plan(e, plan));
     if (!plan->guards.empty()) {
         if (env_flag("HFG_GUARD_SELFTEST", 0))   // prove the check itself: clobber one canary byte like a stray store would
             CK(cudaMemsetAsync(e->arena + plan->guards[plan->guards.size() / 2] + 7, 0, 1, e->stream));
@@ -1095,7 +1191,7 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
     if (!e->finalized) return fail(HFG_ERR_STATE, "hfg_run_layer: call hfg_finalize first");
     Layer* lay = find_layer(e, layer);
     if (!lay) return fail(HFG_ERR_INVALID, std::string("unknown layer: ") + (layer ? layer : "(null)"));
-    CK(cudaSetDevice(e->device));
+    GUARD(e);
     const ConvGeom g = geom_of(*lay, B, L);
     const size_t n_in = (size_t)B * lay->cin * L, n_out = (size_t)B * lay->cout * g.Lout;
     const size_t n_in_pad = (size_t)B * lay->cin_pad * L, n_out_pad = (size_t)B * lay->cout_tc * g.Lout;
@@ -1132,21 +1228,23 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
         // The forward's production path for this layer: activated operand planes in (channel-padded like the plan's),
         // activated planes out, inverted back to the raw conv output for the caller.
         const bool x3 = precision == HFG_PREC_BF16X3;
-        CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, lay->cin, L, lay->cin_pad, pre_lrelu, st));
+        const int f16 = precision == HFG_PREC_FP16 ? 1 : 0;
+        const __nv_bfloat16* w_hi = f16 ? lay->d_wh : lay->d_wb_hi;
+        CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, lay->cin, L, lay->cin_pad, pre_lrelu, f16, st));
         UmmaConvParams p;
         memset(&p, 0, sizeof p);
-        p.g = geom_tc(*lay, B, L); p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1;
+        p.g = geom_tc(*lay, B, L); p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1; p.f16 = f16;
         p.bias = lay->d_bias_tc; p.a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
         p.y_act = y_hi; p.y_act_lo = x3 ? y_lo : nullptr;
         Umma2Launch u2;
-        if (umma2_supported(p) && plan_conv_umma2(&u2, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo, e->sm_count) == HFG_OK) {
+        if (umma2_supported(p) && plan_conv_umma2(&u2, p, a_hi, a_lo, w_hi, lay->d_wb_lo, e->sm_count) == HFG_OK) {
             CK(launch_conv_umma2(u2, st));
         } else {
             UmmaLaunch ul;
-            RET(plan_conv_umma(&ul, p, a_hi, a_lo, lay->d_wb_hi, lay->d_wb_lo));
+            RET(plan_conv_umma(&ul, p, a_hi, a_lo, w_hi, lay->d_wb_lo));
             CK(launch_conv_umma(ul, st));
         }
-        CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, (size_t)B * g.Lout, lay->cout_tc, lay->cout, st));
+        CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, (size_t)B * g.Lout, lay->cout_tc, lay->cout, f16, st));
         CK(launch_transpose_cl_to_cf(y_cl, y_cf, B, lay->cout, g.Lout, st));
         e->launches += 4;
     }
@@ -1157,6 +1255,11 @@ int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, i
 
 int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int32_t B, int32_t L, float* y, int32_t precision,
                  int32_t* fused) {
+    return hfg_run_pair_mrf(e, resblock, m, x, nullptr, 1.0f, B, L, y, precision, fused);
+}
+
+int hfg_run_pair_mrf(hfg_engine* e, int32_t resblock, int32_t m, const float* x, const float* mrf_sum, float out_scale, int32_t B,
+                     int32_t L, float* y, int32_t precision, int32_t* fused) {
     if (!e || !x || !y) return fail(HFG_ERR_INVALID, "hfg_run_pair: null argument");
     if (B <= 0 || L <= 0) return fail(HFG_ERR_INVALID, "hfg_run_pair: B and L must be positive");
     RET(check_prec(precision));
@@ -1168,11 +1271,12 @@ int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int
     Layer* c1 = find_layer(e, n1);
     Layer* c2 = find_layer(e, n2);
     if (!c1 || !c2) return fail(HFG_ERR_INVALID, std::string("unknown layer: ") + n1);
-    CK(cudaSetDevice(e->device));
+    GUARD(e);
     const bool x3 = precision == HFG_PREC_BF16X3;
+    const int f16 = precision == HFG_PREC_FP16 ? 1 : 0;
     const int C = c1->cin, Cp = c1->cin_pad;
     const size_t n_raw = (size_t)B * C * L, n_pad = (size_t)B * Cp * L;
-    const size_t need = 2 * n_raw * sizeof(float) + 6 * n_pad * 2 + 16 * 256;
+    const size_t need = 2 * n_raw * sizeof(float) + 8 * n_pad * 2 + 16 * 256;
     if (need > e->scratch_bytes) {
         CK(cudaStreamSynchronize(e->stream));
         cudaFree(e->scratch);
@@ -1189,16 +1293,26 @@ int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int
     __nv_bfloat16* t_lo = bump.take<__nv_bfloat16>(n_pad);
     __nv_bfloat16* y_hi = bump.take<__nv_bfloat16>(n_pad);
     __nv_bfloat16* y_lo = bump.take<__nv_bfloat16>(n_pad);
+    __nv_bfloat16* s_hi = bump.take<__nv_bfloat16>(n_pad);
+    __nv_bfloat16* s_lo = bump.take<__nv_bfloat16>(n_pad);
     cudaStream_t st = e->stream;
+    if (mrf_sum) {   // planes of lrelu(running sum), like the forward keeps them
+        CK(cudaMemcpyAsync(x_cf, mrf_sum, n_raw * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(launch_mel_to_cl_bf16(x_cf, s_hi, x3 ? s_lo : nullptr, B, C, L, Cp, 1, f16, st));
+        e->launches += 1;
+    }
     CK(cudaMemcpyAsync(x_cf, x, n_raw * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, C, L, Cp, 1, st));
+    CK(launch_mel_to_cl_bf16(x_cf, a_hi, x3 ? a_lo : nullptr, B, C, L, Cp, 1, f16, st));
+    const __nv_bfloat16* w1h = f16 ? c1->d_wh : c1->d_wb_hi;
+    const __nv_bfloat16* w2h = f16 ? c2->d_wh : c2->d_wb_hi;
     PairParams pp;
     memset(&pp, 0, sizeof pp);
-    pp.B = B; pp.L = L; pp.C = Cp; pp.k1 = c1->k; pp.k2 = c2->k; pp.d = c1->dil; pp.npass = x3 ? 3 : 1;
+    pp.B = B; pp.L = L; pp.C = Cp; pp.k1 = c1->k; pp.k2 = c2->k; pp.d = c1->dil; pp.npass = x3 ? 3 : 1; pp.f16 = f16;
     pp.bias1 = c1->d_bias_tc; pp.bias2 = c2->d_bias_tc;
     pp.x_hi = a_hi; pp.x_lo = x3 ? a_lo : nullptr;
-    pp.w1_hi = c1->d_wb_hi; pp.w1_lo = c1->d_wb_lo; pp.w2_hi = c2->d_wb_hi; pp.w2_lo = c2->d_wb_lo;
+    pp.w1_hi = w1h; pp.w1_lo = c1->d_wb_lo; pp.w2_hi = w2h; pp.w2_lo = c2->d_wb_lo;
     pp.y_hi = y_hi; pp.y_lo = x3 ? y_lo : nullptr;
+    if (mrf_sum) { pp.mrf_hi = s_hi; pp.mrf_lo = x3 ? s_lo : nullptr; pp.out_scale = out_scale; }
     PairLaunch pl;
     const bool can_fuse = c1->cin_pad == c1->cout_tc && c1->k == c2->k && c2->dil == 1 && pair_supported(pp) &&
                           plan_conv_pair(&pl, pp, e->sm_count) == HFG_OK;
@@ -1211,24 +1325,26 @@ int hfg_run_pair(hfg_engine* e, int32_t resblock, int32_t m, const float* x, int
             const Layer* lay = which ? c2 : c1;
             UmmaConvParams p;
             memset(&p, 0, sizeof p);
-            p.g = geom_tc(*lay, B, L); p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1;
+            p.g = geom_tc(*lay, B, L); p.cin_pad = lay->cin_pad; p.kc = lay->kc; p.npass = x3 ? 3 : 1; p.f16 = f16;
             p.bias = lay->d_bias_tc;
             if (which) { p.res_hi = a_hi; p.res_lo = x3 ? a_lo : nullptr; }
+            if (which && mrf_sum) { p.mrf_hi = s_hi; p.mrf_lo = x3 ? s_lo : nullptr; p.out_scale = out_scale; }
             p.y_act = which ? y_hi : t_hi; p.y_act_lo = x3 ? (which ? y_lo : t_lo) : nullptr;
             const __nv_bfloat16* in_hi = which ? t_hi : a_hi;
             const __nv_bfloat16* in_lo = which ? t_lo : a_lo;
             Umma2Launch u2;
-            if (umma2_supported(p) && plan_conv_umma2(&u2, p, in_hi, in_lo, lay->d_wb_hi, lay->d_wb_lo, e->sm_count) == HFG_OK) {
+            const __nv_bfloat16* wh = which ? w2h : w1h;
+            if (umma2_supported(p) && plan_conv_umma2(&u2, p, in_hi, in_lo, wh, lay->d_wb_lo, e->sm_count) == HFG_OK) {
                 CK(launch_conv_umma2(u2, st));
             } else {
                 UmmaLaunch ul;
-                RET(plan_conv_umma(&ul, p, in_hi, in_lo, lay->d_wb_hi, lay->d_wb_lo));
+                RET(plan_conv_umma(&ul, p, in_hi, in_lo, wh, lay->d_wb_lo));
                 CK(launch_conv_umma(ul, st));
             }
         }
         e->launches += 2;
     }
-    CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, (size_t)B * L, Cp, C, st));
+    CK(launch_planes_to_raw(y_hi, x3 ? y_lo : nullptr, y_cl, (size_t)B * L, Cp, C, f16, st));
     CK(launch_transpose_cl_to_cf(y_cl, x_cf, B, C, L, st));
     e->launches += 3;
     CK(cudaMemcpyAsync(y, x_cf, n_raw * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1244,7 +1360,7 @@ int hfg_get_tap(hfg_engine* e, const char* name, float* out, size_t* n) {
     const size_t cnt = (size_t)t.B * t.C * t.L;
     if (!out) { *n = cnt; return HFG_OK; }
     if (*n < cnt) return fail(HFG_ERR_INVALID, "hfg_get_tap: buffer too small");
-    CK(cudaSetDevice(e->device));
+    GUARD(e);
     float* tmp = nullptr;
     CK(cudaMalloc(&tmp, cnt * sizeof(float)));
     cudaError_t err = t.C == 1 ? cudaMemcpyAsync(tmp, t.dev, cnt * sizeof(float), cudaMemcpyDeviceToDevice, e->stream)

@@ -69,9 +69,10 @@ cudaError_t launch_conv_post_bf16(const __nv_bfloat16* x_hi, const __nv_bfloat16
 // [B][C][L] <-> [B][L][C] fp32
 cudaError_t launch_transpose_cf_to_cl(const float* in, float* out, int B, int C, int L, cudaStream_t s);
 cudaError_t launch_transpose_cl_to_cf(const float* in, float* out, int B, int C, int L, cudaStream_t s);
-// [B][C][L] fp32 -> channels-last bf16 [B][L][Cpad] (zero padded channels), hi (+ lo) planes, optional lrelu
+// [B][C][L] fp32 -> channels-last 16-bit planes [B][L][Cpad] (zero padded channels), hi (+ lo) bf16 planes or one fp16 plane
+// (f16; the pointer type stays __nv_bfloat16* for every 16-bit plane), optional lrelu
 cudaError_t launch_mel_to_cl_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int L, int Cpad,
-                                  int apply_lrelu, cudaStream_t s);
+                                  int apply_lrelu, int f16, cudaStream_t s);
 // xs = (first ? r : xs + r) ; if div > 0: xs /= div   (MRF sum, hifigan_pretrained.py:133-137)
 cudaError_t launch_accum_fp32(float* xs, const float* r, size_t n, int first, float div, cudaStream_t s);
 // act planes from an fp32 tensor: hi = bf16(lrelu(x)), lo = bf16(lrelu(x) - hi)
@@ -86,11 +87,17 @@ struct UmmaConvParams {
     ConvGeom g;
     int cin_pad;          // channels per row of the A tensor (multiple of kc)
     int kc;               // K elements per chunk: 64 (128-byte rows) or 32 (64-byte rows)
-    int npass;            // 1: bf16 ; 3: bf16x3 (hi*hi + lo*hi + hi*lo)
+    int npass;            // 1: bf16 / fp16 ; 3: bf16x3 (hi*hi + lo*hi + hi*lo)
+    int f16;              // single-plane mode with fp16 operand planes and weights (HFG_PREC_FP16) instead of bf16
     const float* bias;
     const float* res;     // fp32 [B][Lout][Cout] or nullptr
     const __nv_bfloat16* res_hi;   // residual given as ACTIVATED planes (x recovered by inverting lrelu) or nullptr
     const __nv_bfloat16* res_lo;
+    // MRF sum folded into the last convs2 of a branch (hifigan_pretrained.py:133-137): v = (acc + bias + x + s_prev) * out_scale,
+    // s_prev = inverse-lrelu of these planes (the running sum of the previous branches' outputs); needs res_hi
+    const __nv_bfloat16* mrf_hi;
+    const __nv_bfloat16* mrf_lo;
+    float out_scale;      // used with mrf_hi only: 1, or 1 / num_kernels on the last branch
     float* y_raw;         // fp32 or nullptr
     __nv_bfloat16* y_act; // activated (lrelu) output plane or nullptr
     __nv_bfloat16* y_act_lo;
@@ -138,8 +145,11 @@ struct PairParams {
     int B, L, C;          // planes are [B][L][C] bf16, C = 32 or 64 (already channel-padded)
     int k1, k2, d;        // c1: k1 taps, dilation d ; c2: k2 taps, dilation 1 ; both 'same'-padded (k1 = k2 for a reference ResBlock;
                           // they differ for the time-folded narrow stages, engine.cu)
-    int npass;            // 1: bf16 ; 3: bf16x3
+    int npass;            // 1: bf16 / fp16 ; 3: bf16x3
+    int f16;              // fp16 operand planes (npass == 1 only)
     int reverse;
+    const __nv_bfloat16 *mrf_hi, *mrf_lo;   // running MRF sum added in epilogue 2 (see UmmaConvParams), or nullptr
+    float out_scale;
     const float* bias1;
     const float* bias2;
     const __nv_bfloat16 *x_hi, *x_lo;
@@ -158,13 +168,14 @@ cudaError_t launch_conv_pair(const PairLaunch& L, cudaStream_t s);
 
 // raw fp32 [rows][C] = inverse-lrelu(hi (+ lo)) of planes [rows][C_tc], C <= C_tc   (taps; drops padding channels)
 cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t rows, int C_tc, int C,
-                                 cudaStream_t s);
+                                 int f16, cudaStream_t s);
 // MRF combine (hifigan_pretrained.py:133-137) on planes: v = ((x0 + x1) + x2 ...) / nk with x_j = inverse-lrelu(plane j);
 // writes planes of lrelu(v) and/or raw fp32 v.
 struct MrfArgs {
     const __nv_bfloat16* hi[HFG_MAX_KERNELS];
     const __nv_bfloat16* lo[HFG_MAX_KERNELS];   // all nullptr in single-plane mode
     int nk;
+    int f16;              // planes are fp16 (single-plane mode)
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     float* out_raw;

@@ -270,7 +270,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 // mel [B][C][L] fp32 -> [B][L][Cpad] bf16 hi (+ lo) planes, channels >= C zero.
 __global__ void mel_to_cl_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                      __nv_bfloat16* __restrict__ lo, int C, int L, int Cpad, int apply_lrelu) {
+                                      __nv_bfloat16* __restrict__ lo, int C, int L, int Cpad, int apply_lrelu, int f16) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
@@ -285,8 +285,12 @@ __global__ void mel_to_cl_bf16_kernel(const float* __restrict__ in, __nv_bfloat1
         if (l < L && c < Cpad) {
             float v = tile[threadIdx.x][i];
             if (apply_lrelu) v = lrelu(v);
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const size_t o = ((size_t)b * L + l) * Cpad + c;
+            if (f16) {   // one fp16 plane in the same 16-bit storage
+                reinterpret_cast<unsigned short*>(hi)[o] = (unsigned short)(ptx::pack_f16(v, 0.f) & 0xffffu);
+                continue;
+            }
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
             hi[o] = h;
             if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
         }
@@ -320,9 +324,14 @@ __global__ void act_split_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 
 __device__ __forceinline__ float inv_lrelu(float p) { return p > 0.f ? p : p * (1.0f / kLreluSlope); }
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i8, float (&f)[8]) {
+__device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i8, float (&f)[8], int f16 = 0) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(hi) + i8);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    if (f16) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) ptx::unpack2<true>(w[t], f[2 * t], f[2 * t + 1]);
+        return;
+    }
 #pragma unroll
     for (int t = 0; t < 4; ++t) { f[2 * t] = __uint_as_float(w[t] << 16); f[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u); }
     if (lo) {
@@ -336,7 +345,7 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat
 // MRF sum of NK branch planes at 8 consecutive channels: every plane's 16-byte load is issued before the first use
 // (the generic loop over a runtime nk serialises one DRAM latency per branch).  Arithmetic: ((x0 + x1) + x2 ...) as in
 // hifigan_pretrained.py:133-136, x_j = inverse-lrelu(plane j).
-template <int NK, bool LO>
+template <int NK, bool LO, bool F16 = false>
 __device__ __forceinline__ void mrf_sum8(const MrfArgs& a, size_t i8, float (&v)[8]) {
     using namespace ptx;
     uint4 h[NK], l[NK];
@@ -352,7 +361,7 @@ __device__ __forceinline__ void mrf_sum8(const MrfArgs& a, size_t i8, float (&v)
         const uint32_t wl[4] = {LO ? l[j].x : 0u, LO ? l[j].y : 0u, LO ? l[j].z : 0u, LO ? l[j].w : 0u};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            f2 f = f2_from_bf16x2(w[t]);
+            f2 f = f2_from_h2<F16>(w[t]);
             if (LO) f = f2_add(f, f2_from_bf16x2(wl[t]));
             f = f2_inv_lrelu(f);
             acc[t] = j == 0 ? f : f2_add(acc[t], f);
@@ -363,20 +372,20 @@ __device__ __forceinline__ void mrf_sum8(const MrfArgs& a, size_t i8, float (&v)
 }
 // runtime nk -> the specialised sum (nk = 3 is every shipped config); false: caller runs the generic loop
 __device__ __forceinline__ bool mrf_sum8_dispatch(const MrfArgs& a, size_t i8, float (&v)[8]) {
-    if (a.nk == 3) { if (a.lo[0]) mrf_sum8<3, true>(a, i8, v); else mrf_sum8<3, false>(a, i8, v); return true; }
-    if (a.nk == 2) { if (a.lo[0]) mrf_sum8<2, true>(a, i8, v); else mrf_sum8<2, false>(a, i8, v); return true; }
+    if (a.nk == 3) { if (a.lo[0]) mrf_sum8<3, true>(a, i8, v); else if (a.f16) mrf_sum8<3, false, true>(a, i8, v); else mrf_sum8<3, false>(a, i8, v); return true; }
+    if (a.nk == 2) { if (a.lo[0]) mrf_sum8<2, true>(a, i8, v); else if (a.f16) mrf_sum8<2, false, true>(a, i8, v); else mrf_sum8<2, false>(a, i8, v); return true; }
     return false;
 }
 
 // [rows][C_tc] planes -> [rows][C] fp32 (C <= C_tc: drops the zero padding channels of narrow stages)
 __global__ void planes_to_raw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ raw,
-                                     size_t rows, int c8_tc, int c8) {
+                                     size_t rows, int c8_tc, int c8, int f16) {
     const size_t n8 = rows * (size_t)c8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / c8;
         const int c = (int)(i - r * c8);
         float f[8];
-        load8(hi, lo, r * c8_tc + c, f);
+        load8(hi, lo, r * c8_tc + c, f, f16);
         float4 a = make_float4(inv_lrelu(f[0]), inv_lrelu(f[1]), inv_lrelu(f[2]), inv_lrelu(f[3]));
         float4 b = make_float4(inv_lrelu(f[4]), inv_lrelu(f[5]), inv_lrelu(f[6]), inv_lrelu(f[7]));
         reinterpret_cast<float4*>(raw)[2 * i] = a;
@@ -388,12 +397,12 @@ __global__ void mrf_combine_kernel(const MrfArgs a, size_t n8) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         float v[8];
         if (!mrf_sum8_dispatch(a, i, v)) {
-            load8(a.hi[0], a.lo[0], i, v);
+            load8(a.hi[0], a.lo[0], i, v, a.f16);
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[t] = inv_lrelu(v[t]);
             for (int j = 1; j < a.nk; ++j) {
                 float f[8];
-                load8(a.hi[j], a.lo[j], i, f);
+                load8(a.hi[j], a.lo[j], i, f, a.f16);
 #pragma unroll
                 for (int t = 0; t < 8; ++t) v[t] = v[t] + inv_lrelu(f[t]);
             }
@@ -406,7 +415,12 @@ __global__ void mrf_combine_kernel(const MrfArgs a, size_t n8) {
             reinterpret_cast<float4*>(a.out_raw)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
             reinterpret_cast<float4*>(a.out_raw)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
         }
-        if (a.out_hi) {
+        if (a.out_hi && a.f16) {
+            uint4 h;
+            h.x = ptx::pack_f16(lrelu(v[0]), lrelu(v[1])); h.y = ptx::pack_f16(lrelu(v[2]), lrelu(v[3]));
+            h.z = ptx::pack_f16(lrelu(v[4]), lrelu(v[5])); h.w = ptx::pack_f16(lrelu(v[6]), lrelu(v[7]));
+            reinterpret_cast<uint4*>(a.out_hi)[i] = h;
+        } else if (a.out_hi) {
             __nv_bfloat162 h[4];
             float l[8];
 #pragma unroll
@@ -454,14 +468,14 @@ __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfAr
         if (t >= 0 && t < L) {
             const size_t i8 = base8 + (size_t)t * c8n + c8;
             const bool summed = a.nk > 1 && mrf_sum8_dispatch(a, i8, v);
-            if (!summed) load8(a.hi[0], a.lo[0], i8, v);
+            if (!summed) load8(a.hi[0], a.lo[0], i8, v, a.f16);
             if (a.nk > 1) {
                 if (!summed) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] = inv_lrelu(v[q]);
                     for (int j = 1; j < a.nk; ++j) {
                         float f[8];
-                        load8(a.hi[j], a.lo[j], i8, f);
+                        load8(a.hi[j], a.lo[j], i8, f, a.f16);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) v[q] = v[q] + inv_lrelu(f[q]);
                     }
@@ -469,6 +483,7 @@ __global__ void __launch_bounds__(kPostMrfTile) conv_post_mrf_kernel(const MrfAr
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float x = lrelu(v[q] * rinv);
+                    if (a.f16) { v[q] = __half2float(__float2half_rn(x)); continue; }
                     const float h = __bfloat162float(__float2bfloat16_rn(x));   // what the operand plane(s) would hold
                     v[q] = a.lo[0] ? h + __bfloat162float(__float2bfloat16_rn(x - h)) : h;
                 }
@@ -564,10 +579,10 @@ cudaError_t launch_transpose_cl_to_cf(const float* in, float* out, int B, int C,
 }
 
 cudaError_t launch_mel_to_cl_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int L, int Cpad,
-                                  int apply_lrelu, cudaStream_t s) {
+                                  int apply_lrelu, int f16, cudaStream_t s) {
     dim3 grid((L + 31) / 32, (Cpad + 31) / 32, B);
     dim3 block(32, 8);
-    mel_to_cl_bf16_kernel<<<grid, block, 0, s>>>(in, hi, lo, C, L, Cpad, apply_lrelu);
+    mel_to_cl_bf16_kernel<<<grid, block, 0, s>>>(in, hi, f16 ? nullptr : lo, C, L, Cpad, apply_lrelu, f16);
     return cudaGetLastError();
 }
 
@@ -580,11 +595,11 @@ cudaError_t launch_accum_fp32(float* xs, const float* r, size_t n, int first, fl
 }
 
 cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* raw, size_t rows, int C_tc, int C,
-                                 cudaStream_t s) {
+                                 int f16, cudaStream_t s) {
     if (C % 8 != 0 || C_tc % 8 != 0 || C > C_tc) return cudaErrorInvalidValue;
     const size_t n8 = rows * (size_t)(C / 8);
     const int blocks = (int)std::min<size_t>((n8 + 255) / 256, 148 * 16);
-    planes_to_raw_kernel<<<blocks, 256, 0, s>>>(hi, lo, raw, rows, C_tc / 8, C / 8);
+    planes_to_raw_kernel<<<blocks, 256, 0, s>>>(hi, lo, raw, rows, C_tc / 8, C / 8, f16);
     return cudaGetLastError();
 }
 

@@ -53,6 +53,11 @@ struct PairArgs {
     int n_x, n_t, n_o;
     int n_w2;                    // 0: c2's weights resident like c1's ; > 0: streamed per tile through a ring of n_w2 tap tiles
     int concat, acc_n, paired, reverse;
+    int f16;                     // fp16 operand planes (single-plane mode)
+    int has_mrf;                 // epilogue 2 also adds the running MRF sum of the previous branches (an R-row tile per tile of work,
+                                 // double-buffered, loaded by warp 3) and scales by out_scale  (hifigan_pretrained.py:133-137)
+    float out_scale;
+    uint32_t m_plane_bytes, off_m;
     int dbg;                     // HFG_PAIR_DBG (timing experiments only): 1 = epilogue 2 idle, 2 = no MMAs, 3 = epilogue 1 idle, 4 = no TMA stores
     uint32_t x_plane_bytes, t_plane_bytes, w_plane_bytes, o_plane_bytes;
     uint32_t off_w, off_t, off_o;
@@ -61,10 +66,10 @@ struct PairArgs {
 };
 
 // hi (and lo = v - hi) planes of 8 consecutive channels (4 pairs) -> 16-byte chunks
-template <int kPlanes>
+template <int kPlanes, bool kF16>
 __device__ __forceinline__ void store_planes8(const f2* v, uint32_t addr, uint32_t plane_bytes) {
     uint4 hi;
-    hi.x = f2_to_bf16x2(v[0]); hi.y = f2_to_bf16x2(v[1]); hi.z = f2_to_bf16x2(v[2]); hi.w = f2_to_bf16x2(v[3]);
+    hi.x = f2_to_h2<kF16>(v[0]); hi.y = f2_to_h2<kF16>(v[1]); hi.z = f2_to_h2<kF16>(v[2]); hi.w = f2_to_h2<kF16>(v[3]);
     sts128(addr, hi);
     if (kPlanes > 1) {
         uint4 lo;
@@ -101,15 +106,16 @@ __device__ __forceinline__ void issue_taps(bool leader, int k, uint32_t d0, uint
     }
 }
 
-template <int kPlanes>
+template <int kPlanes, bool kF16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                  const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
                  const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                  const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
-                 const __grid_constant__ CUtensorMap map_yt_hi, const __grid_constant__ CUtensorMap map_yt_lo, const PairArgs a) {
+                 const __grid_constant__ CUtensorMap map_yt_hi, const __grid_constant__ CUtensorMap map_yt_lo,
+                 const __grid_constant__ CUtensorMap map_m_hi, const __grid_constant__ CUtensorMap map_m_lo, const PairArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kMaxX + 2 * kMaxW2 + 17];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxX + 2 * kMaxW2 + 21];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float bias_s[2][64];
 
@@ -129,6 +135,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     const uint32_t smem_w = smem_base + a.off_w;
     const uint32_t smem_t = smem_base + a.off_t;
     const uint32_t smem_o = smem_base + a.off_o;
+    const uint32_t smem_m = smem_base + a.off_m;
+    const uint32_t m_stage = a.m_plane_bytes * planes;
 
     uint32_t bp = smem_u32(&bars[0]);
     const uint32_t bar_x_full = bp;   bp += 8 * kMaxX;
@@ -141,7 +149,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
     const uint32_t bar_a2_empty = bp; bp += 16;
     const uint32_t bar_w = bp;        bp += 8;
     const uint32_t bar_w2_full = bp;  bp += 8 * kMaxW2;
-    const uint32_t bar_w2_empty = bp;
+    const uint32_t bar_w2_empty = bp; bp += 8 * kMaxW2;
+    const uint32_t bar_m_full = bp;   bp += 16;
+    const uint32_t bar_m_empty = bp;
 
     if (threadIdx.x < 2 * a.N) {
         const int which = threadIdx.x / a.N, i = threadIdx.x % a.N;
@@ -161,6 +171,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         }
         mbar_init(bar_w, 1);
         for (int i = 0; i < a.n_w2; ++i) { mbar_init(bar_w2_full + 8 * i, 1); mbar_init(bar_w2_empty + 8 * i, nmma); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_m_full + 8 * i, 1); mbar_init(bar_m_empty + 8 * i, 4); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -219,6 +230,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 }
         }
         __syncwarp();
+    } else if (warp == 3) {
+        // ===== MRF-sum tiles (only the last step of the second and later branches of a stage): R rows from output row o0 =====
+        if (lane == 0 && a.has_mrf) {
+            pdl_wait();
+            for (int it = 0; it < n_my; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+                const int b = tl / a.tiles_per_item;
+                const int o0 = (tl - b * a.tiles_per_item) * a.V;
+                const int buf = it & 1;
+                mbar_wait(bar_m_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(bar_m_full + 8 * buf, (uint32_t)a.R * row_bytes * planes);
+                for (int pl = 0; pl < planes; ++pl)
+                    tma_load_3d(smem_m + buf * m_stage + pl * a.m_plane_bytes, pl ? &map_m_lo : &map_m_hi, bar_m_full + 8 * buf, 0, o0, b);
+            }
+        }
+        __syncwarp();
     } else if (warp >= 4 && warp < 8) {
         // ===== MMA issuers: warp 4 + cv*MT + ms issues conv cv (0: c1, 1: c2) of subtile ms =====
         // One thread cannot issue small-N MMAs at the tensor pipe's rate, and c1 of tile i+1 must overlap the
@@ -227,8 +255,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         const int cv = role / a.mt, ms = role % a.mt;
         if (cv < 2) {
             const bool leader = elect_one();
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * a.N) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = make_idesc((uint32_t)a.N, kF16);
+            const uint32_t idesc2 = make_idesc((uint32_t)(2 * a.N), kF16);
             const bool concat = a.concat != 0;
             const uint32_t id0 = concat ? idesc2 : idesc;
             const uint32_t dhi = desc_hi(row_bytes);
@@ -362,7 +390,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                     }
 #pragma unroll
                     for (int c = 0; c < CW / 8; ++c)
-                        store_planes8<kPlanes>(&v[c * 4], dst + ((((uint32_t)(h * (CW / 8) + c)) ^ sx) << 4), a.t_plane_bytes);
+                        store_planes8<kPlanes, kF16>(&v[c * 4], dst + ((((uint32_t)(h * (CW / 8) + c)) ^ sx) << 4), a.t_plane_bytes);
                 }
             }
             tc_fence_before();      // this warp has read the last of acc1[buf]
@@ -393,8 +421,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             const int buf = it & 1;
             mbar_wait(bar_a2_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
             mbar_wait(bar_x_full + 8 * sx, px);      // completed long ago (c1 consumed it); orders this thread's reads after the TMA writes
+            if (a.has_mrf) mbar_wait(bar_m_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
             const uint32_t x_slot = smem_x + sx * x_stage;
+            const uint32_t m_slot = smem_m + buf * m_stage;
+            const f2 scale2 = f2_pack(a.out_scale, a.out_scale);
             for (int ms = 0; ms < (a.dbg == 1 ? 0 : a.mt); ++ms) {
                 const int rs = ms * 128 + q * 32;                    // first tile row of this warp's box
                 int nvalid = min(32, a.V - rs);
@@ -402,6 +433,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 const uint32_t row_x = (uint32_t)(rs + lane + a.h1 + a.h2);
                 const uint32_t xsrc = x_slot + row_x * row_bytes;
                 const uint32_t xsw = swz(row_x, row_bytes);
+                const uint32_t msrc = m_slot + (uint32_t)(rs + lane) * row_bytes;
+                const uint32_t msw = swz((uint32_t)(rs + lane), row_bytes);
                 const uint32_t slot = smem_o + (uint32_t)((grp * 4 + q) * a.n_o + so) * o_slot;
                 if (lane == 0) { if (a.n_o == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the store that last used this slot has read it
                 __syncwarp();
@@ -423,7 +456,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                             for (int i = 0; i < 4; ++i) res[c * 4 + i] = f2_inv_lrelu(f2_add(f2_from_bf16x2(wh[i]), f2_from_bf16x2(wl[i])));
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) res[c * 4 + i] = f2_inv_lrelu(f2_from_bf16x2(wh[i]));
+                            for (int i = 0; i < 4; ++i) res[c * 4 + i] = f2_inv_lrelu(f2_from_h2<kF16>(wh[i]));
                         }
                     }
                     tmem_wait_ld();
@@ -440,10 +473,31 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                         for (int i = 0; i < CW / 2; ++i) v[i] = f2_add(v[i], f2_bits(r[2 * i], r[2 * i + 1]));
                     }
 #pragma unroll
-                    for (int i = 0; i < CW / 2; ++i) v[i] = f2_lrelu(f2_add(v[i], res[i]));
+                    for (int i = 0; i < CW / 2; ++i) v[i] = f2_add(v[i], res[i]);
+                    if (a.has_mrf) {   // + running sum of the previous branches' outputs, then the 1/nk of the last branch
+#pragma unroll
+                        for (int c = 0; c < CW / 8; ++c) {
+                            const uint32_t ma = msrc + ((((uint32_t)(h * (CW / 8) + c)) ^ msw) << 4);
+                            const uint4 ph = lds128(ma);
+                            const uint32_t wh[4] = {ph.x, ph.y, ph.z, ph.w};
+                            if (planes > 1) {
+                                const uint4 pl = lds128(ma + a.m_plane_bytes);
+                                const uint32_t wl[4] = {pl.x, pl.y, pl.z, pl.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    v[c * 4 + i] = f2_mul(f2_add(v[c * 4 + i], f2_inv_lrelu(f2_add(f2_from_bf16x2(wh[i]), f2_from_bf16x2(wl[i])))), scale2);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    v[c * 4 + i] = f2_mul(f2_add(v[c * 4 + i], f2_inv_lrelu(f2_from_h2<kF16>(wh[i]))), scale2);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < CW / 2; ++i) v[i] = f2_lrelu(v[i]);
 #pragma unroll
                     for (int c = 0; c < CW / 8; ++c)
-                        store_planes8<kPlanes>(&v[c * 4], slot + o_row_off + (((o_chunk0 + (uint32_t)(h * (CW / 8) + c)) ^ o_sx) << 4), a.o_plane_bytes);
+                        store_planes8<kPlanes, kF16>(&v[c * 4], slot + o_row_off + (((o_chunk0 + (uint32_t)(h * (CW / 8) + c)) ^ o_sx) << 4), a.o_plane_bytes);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -460,7 +514,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             }
             tc_fence_before();   // this warp has read the last of acc2[buf] and of the x slot
             __syncwarp();
-            if (lane == 0) { mbar_arrive(bar_a2_empty + 8 * buf); mbar_arrive(bar_x_empty + 8 * sx); }
+            if (lane == 0) { mbar_arrive(bar_a2_empty + 8 * buf); mbar_arrive(bar_x_empty + 8 * sx); if (a.has_mrf) mbar_arrive(bar_m_empty + 8 * buf); }
         }
         if (lane == 0) bulk_wait_read<0>();
     }
@@ -521,7 +575,7 @@ uint32_t rup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 struct PairLaunch::Impl {
     PairArgs a;
-    alignas(64) CUtensorMap map_x[2], map_w1[2], map_w2[2], map_y[2], map_yt[2];
+    alignas(64) CUtensorMap map_x[2], map_w1[2], map_w2[2], map_y[2], map_yt[2], map_m[2];
     int grid;
     size_t smem;
 };
@@ -531,6 +585,7 @@ bool pair_supported(const PairParams& p) {
     if (p.C != 32 && p.C != 64) return false;
     if (p.k1 < 1 || p.k1 > 31 || p.k1 % 2 == 0 || p.k2 < 1 || p.k2 > 15 || p.k2 % 2 == 0 || p.d < 1) return false;
     if (p.npass != 1 && p.npass != 3) return false;
+    if (p.f16 && p.npass != 1) return false;
     const int maxc = penv(p.npass == 3 ? "HFG_PAIR_MAXC_X3" : "HFG_PAIR_MAXC", 64);
     const int maxk = penv(p.npass == 3 ? "HFG_PAIR_MAXK_X3" : "HFG_PAIR_MAXK", 31);
     if (p.C > maxc || std::max(p.k1, p.k2) > maxk) return false;
@@ -553,6 +608,9 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     a.acc_n = a.concat ? 2 * N : N;
     a.paired = (N == 32 && p.L % 2 == 0 && penv("HFG_PAIR_PAIRED", 1)) ? 1 : 0;
     a.reverse = p.reverse;
+    a.f16 = p.f16 ? 1 : 0;
+    a.has_mrf = p.mrf_hi ? 1 : 0;
+    a.out_scale = a.has_mrf ? p.out_scale : 1.0f;
     a.dbg = penv("HFG_PAIR_DBG", 0);
     a.bias1 = p.bias1; a.bias2 = p.bias2;
     a.w_plane_bytes = rup((uint32_t)N * row_bytes, 1024);
@@ -595,8 +653,10 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
         const int box_rows = ((rows_need + pieces - 1) / pieces + 7) / 8 * 8;
         const uint32_t x_plane = rup((uint32_t)(pieces * box_rows) * row_bytes, 1024);
         const uint32_t t_plane = rup((uint32_t)((R + 2 * a.h2 + 7) / 8 * 8) * row_bytes, 1024);
+        const uint32_t m_plane = rup((uint32_t)R * row_bytes, 1024);
+        const uint32_t m_all = a.has_mrf ? 2u * m_plane * planes : 0u;
         const double t_mma = (double)mt * (p.k1 + p.k2) * ksteps * step_clk + (n_w2 ? p.k2 * 80.0 : 0.0);
-        const double t_hbm = ((double)rows_need + V) * row_bytes * planes / 20.0;
+        const double t_hbm = ((double)rows_need + V + (a.has_mrf ? R : 0)) * row_bytes * planes / 20.0;
         const double t_epi = (double)mt * (N / 32) * (planes > 1 ? 1100.0 : 600.0);   // both epilogues share an SM sub-partition
         const double t_int = std::max({t_mma, t_hbm, t_epi}) + 300.0;
         for (int n_t = 2; n_t >= (n_w2 ? 2 : 1); --n_t) {
@@ -604,7 +664,7 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
             // each epilogue-2 warp meets one of its slots again two tiles later (the groups alternate tiles): mt slots suffice
             for (int n_o = std::min(mt, 2); n_o >= 1; --n_o) {
                 if (f_no && n_o != f_no) continue;
-                const uint32_t fixed = w_all + (uint32_t)n_t * t_plane * planes + 8u * n_o * a.o_plane_bytes * planes;
+                const uint32_t fixed = w_all + (uint32_t)n_t * t_plane * planes + 8u * n_o * a.o_plane_bytes * planes + m_all;
                 if (fixed + 3 * x_plane * planes > budget) continue;
                 const int n_x_max = (int)std::min<uint32_t>((budget - fixed) / (x_plane * planes), (uint32_t)kMaxX);
                 for (int n_x = n_x_max; n_x >= 3; --n_x) {
@@ -626,8 +686,10 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
                         a.off_w = (uint32_t)n_x * x_plane * planes;
                         a.off_t = a.off_w + w_all;
                         a.off_o = a.off_t + (uint32_t)n_t * t_plane * planes;
+                        a.off_m = a.off_o + 8u * n_o * a.o_plane_bytes * planes;
+                        a.m_plane_bytes = m_plane;
                         // > half an SM, so exactly one CTA (512 TMEM columns) lives on an SM
-                        I->smem = std::max<size_t>((size_t)a.off_o + 8u * n_o * a.o_plane_bytes * planes + 1024, 120u * 1024u);
+                        I->smem = std::max<size_t>((size_t)a.off_m + m_all + 1024, 120u * 1024u);
                     }
                 }
             }
@@ -652,6 +714,11 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
         const uint32_t box[3] = {(uint32_t)N, (uint32_t)a.x_box_rows, 1};
         if (!pair_encode(&I->map_x[0], p.x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
         if (!pair_encode(&I->map_x[1], planes > 1 ? p.x_lo : p.x_hi, 3, dims3, str3, box, row_bytes)) return HFG_ERR_CUDA;
+        const uint32_t mbox[3] = {(uint32_t)N, (uint32_t)a.R, 1};
+        const void* m0p = a.has_mrf ? (const void*)p.mrf_hi : (const void*)p.x_hi;
+        const void* m1p = (a.has_mrf && planes > 1) ? (const void*)p.mrf_lo : m0p;
+        if (!pair_encode(&I->map_m[0], m0p, 3, dims3, str3, mbox, row_bytes)) return HFG_ERR_CUDA;
+        if (!pair_encode(&I->map_m[1], m1p, 3, dims3, str3, mbox, row_bytes)) return HFG_ERR_CUDA;
     }
     {
         const uint64_t dims1[2] = {(uint64_t)N, (uint64_t)p.k1 * N};
@@ -686,8 +753,9 @@ cudaError_t launch_conv_pair(const PairLaunch& L, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev % 64]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
         if (e != cudaSuccess) return e;
         configured[dev % 64] = true;
     }
@@ -701,12 +769,13 @@ cudaError_t launch_conv_pair(const PairLaunch& L, cudaStream_t s) {
     static const int use_pdl = penv("HFG_PDL", 1);
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
     cudaError_t e;
-    if (I.a.planes == 2)
-        e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<2>, I.map_x[0], I.map_x[1], I.map_w1[0], I.map_w1[1], I.map_w2[0], I.map_w2[1],
-                               I.map_y[0], I.map_y[1], I.map_yt[0], I.map_yt[1], I.a);
-    else
-        e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<1>, I.map_x[0], I.map_x[1], I.map_w1[0], I.map_w1[1], I.map_w2[0], I.map_w2[1],
-                               I.map_y[0], I.map_y[1], I.map_yt[0], I.map_yt[1], I.a);
+#define HFG_PAIR_LAUNCH(P, F)                                                                                                        \
+    e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<P, F>, I.map_x[0], I.map_x[1], I.map_w1[0], I.map_w1[1], I.map_w2[0], I.map_w2[1], \
+                           I.map_y[0], I.map_y[1], I.map_yt[0], I.map_yt[1], I.map_m[0], I.map_m[1], I.a)
+    if (I.a.planes == 2) HFG_PAIR_LAUNCH(2, false);
+    else if (I.a.f16) HFG_PAIR_LAUNCH(1, true);
+    else HFG_PAIR_LAUNCH(1, false);
+#undef HFG_PAIR_LAUNCH
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

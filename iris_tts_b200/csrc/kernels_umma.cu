@@ -55,6 +55,10 @@ struct KArgs {
     const float* res;
     const __nv_bfloat16* res_hi;
     const __nv_bfloat16* res_lo;
+    const __nv_bfloat16* mrf_hi;
+    const __nv_bfloat16* mrf_lo;
+    float out_scale;
+    int f16;
     float* y_raw;
     __nv_bfloat16* y_act;
     __nv_bfloat16* y_act_lo;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         {
             const bool leader = elect_one();
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = make_idesc((uint32_t)a.n_tile, a.f16 != 0);
             const uint32_t dhi = desc_hi(row_bytes);
             const uint32_t sub_step = (128u * row_bytes) >> 4;
             const uint32_t a_pl_step = a.a_plane_bytes >> 4, w_pl_step = a.w_plane_bytes >> 4;
@@ -242,22 +246,35 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
                         v[4 * i + 0] += rv.x; v[4 * i + 1] += rv.y; v[4 * i + 2] += rv.z; v[4 * i + 3] += rv.w;
                     }
                 }
-                if (a.res_hi) {   // residual carried as activated planes: x = inverse-lrelu(hi (+ lo))
+                // residual (and the running MRF sum of the previous branches) carried as activated planes: x = inverse-lrelu(hi (+ lo))
+                for (int src = 0; src < 2; ++src) {
+                    const __nv_bfloat16* ph = src ? a.mrf_hi : a.res_hi;
+                    const __nv_bfloat16* pl = src ? a.mrf_lo : a.res_lo;
+                    if (!ph) continue;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const uint4 u = *(reinterpret_cast<const uint4*>(a.res_hi + off) + i);
+                        const uint4 u = *(reinterpret_cast<const uint4*>(ph + off) + i);
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
                         float f[8];
+                        if (a.f16) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) { f[2 * t] = __uint_as_float(w[t] << 16); f[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u); }
-                        if (a.res_lo) {
-                            const uint4 ul = *(reinterpret_cast<const uint4*>(a.res_lo + off) + i);
+                            for (int t = 0; t < 4; ++t) unpack2<true>(w[t], f[2 * t], f[2 * t + 1]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) unpack2<false>(w[t], f[2 * t], f[2 * t + 1]);
+                        }
+                        if (pl) {
+                            const uint4 ul = *(reinterpret_cast<const uint4*>(pl + off) + i);
                             const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
 #pragma unroll
                             for (int t = 0; t < 4; ++t) { f[2 * t] += __uint_as_float(wl[t] << 16); f[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u); }
                         }
 #pragma unroll
                         for (int t = 0; t < 8; ++t) v[8 * i + t] += f[t] > 0.f ? f[t] : f[t] * (1.0f / kLreluSlope);
+                    }
+                    if (src) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= a.out_scale;
                     }
                 }
                 if (a.y_raw) {
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) hi[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+                    for (int i = 0; i < 16; ++i) hi[i] = a.f16 ? pack_f16(v[2 * i], v[2 * i + 1]) : pack_bf16(v[2 * i], v[2 * i + 1]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *(reinterpret_cast<uint4*>(a.y_act + off) + i) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
@@ -487,6 +504,10 @@ cudaError_t launch_conv_umma(const UmmaLaunch& L, cudaStream_t s) {
     a.res = p.res;
     a.res_hi = p.res_hi;
     a.res_lo = p.res_lo;
+    a.mrf_hi = p.mrf_hi;
+    a.mrf_lo = p.mrf_lo;
+    a.out_scale = p.mrf_hi ? p.out_scale : 1.0f;
+    a.f16 = p.f16 ? 1 : 0;
     a.y_raw = p.y_raw;
     a.y_act = p.y_act;
     a.y_act_lo = p.y_act_lo;

@@ -48,6 +48,8 @@ struct K2Args {
     int tiles_per_item, total_tiles;
     int rows_a, a_box_rows, a_pieces;
     int n_a, n_w, n_e, w_resident, has_res;
+    int has_mrf;      // the epilogue also adds a second plane set: the running MRF sum of the previous branches (hifigan_pretrained.py:133-136)
+    float out_scale;  // with has_mrf: v *= out_scale before the activation (1 / num_kernels on the last branch, :137)
     int ecols, groups;
     int ups;      // polyphase ConvTranspose1d (k = 2s, N = s*C_out <= 256): GEMM row m, column half h lands on output half-row
                   // 2m - 1 + h of [B][2*L_in][N/2]; the two column groups ARE the halves, stored through a 4-D tensor map
@@ -58,6 +60,7 @@ struct K2Args {
     int concat;   // bf16x3, 2N <= 128: pass 1 = A_hi x [W_hi ; W_lo] (one MMA of width 2N), pass 2 = A_lo x W_hi; the epilogue adds the halves
     int acc_n;    // TMEM columns of one 128-row subtile accumulator (N, or 2N when concat)
     int paired;   // C = 32: residual / output boxes address two 64-byte time rows as one 128-byte row (full-line TMA requests)
+    int f16;   // operand planes are fp16 instead of bf16 (single-plane mode only)
     int dbg;   // HFG_U2_DBG (timing experiments only): 1 = epilogue does no work, 2 = MMA warp issues no MMAs
     uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
     uint32_t off_w, off_e;
@@ -68,13 +71,11 @@ struct K2Args {
 
 __device__ __forceinline__ float inv_lrelu(float p) { return p > 0.f ? p : p * (1.0f / kLreluSlope); }
 
+template <bool F16 = false>
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
+    for (int i = 0; i < 4; ++i) unpack2<F16>(w[i], f[2 * i], f[2 * i + 1]);
 }
 
 // One K-chunk of one 128-row subtile: all taps x passes x K=16 slices.  The loop is warp-uniform and lives in uniform registers
@@ -127,11 +128,12 @@ __device__ __forceinline__ void issue_taps_streamed(bool leader, int taps, uint3
     }
 }
 
-template <int kPlanes, bool kHasRes>
+template <int kPlanes, bool kHasRes, bool kF16>
 __global__ void __launch_bounds__(threads_for(kPlanes), 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                   const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
+                  const __grid_constant__ CUtensorMap map_m_hi, const __grid_constant__ CUtensorMap map_m_lo,
                   const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo, const K2Args a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kMaxA + 2 * kMaxW + 2 * kMaxE + 5];
@@ -149,7 +151,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_stage_bytes = a.a_plane_bytes * planes;
     const uint32_t w_stage_bytes = a.w_plane_bytes * planes;
-    const uint32_t e_slot_bytes = a.e_plane_bytes * planes;
+    const uint32_t e_slot_bytes = a.e_plane_bytes * planes * (a.has_mrf ? 2u : 1u);   // [residual / output planes][MRF-sum planes]
+    const uint32_t e_mrf_off = a.e_plane_bytes * planes;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_w = smem_base + a.off_w;
     const uint32_t smem_e = smem_base + a.off_e;
@@ -168,7 +171,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bias_s[i] = a.bias[i % a.cout];   // column n of the GEMM -> bias[n % cout]
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_y_hi);
-        if (kHasRes) prefetch_tmap(&map_r_hi);
+        if (kHasRes) { prefetch_tmap(&map_r_hi); if (a.has_mrf) { prefetch_tmap(&map_m_hi); if (planes > 1) prefetch_tmap(&map_m_lo); } }
         if (planes > 1) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_lo); prefetch_tmap(&map_y_lo); if (kHasRes) prefetch_tmap(&map_r_lo); }
     }
     if (warp == 3 && lane == 0) {
@@ -243,8 +246,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int my_ms = warp - 8;
         if (my_ms < a.mt) {
             const bool leader = elect_one();
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * a.N) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = make_idesc((uint32_t)a.N, kF16);
+            const uint32_t idesc2 = make_idesc((uint32_t)(2 * a.N), kF16);
             const bool concat = a.concat != 0;
             const uint32_t id0 = concat ? idesc2 : idesc;
             const uint32_t dhi = desc_hi(row_bytes);
@@ -309,10 +312,14 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (row0 >= a.L) break;
                     for (int g = 0; g < a.groups; ++g) {
                         mbar_wait(bar_e_empty + 8 * se, pe ^ 1u);
-                        mbar_expect_tx(bar_e_full + 8 * se, a.e_plane_bytes * planes);
+                        mbar_expect_tx(bar_e_full + 8 * se, e_slot_bytes);
                         for (int pl = 0; pl < planes; ++pl)
                             tma_load_3d(smem_e + se * e_slot_bytes + pl * a.e_plane_bytes, pl ? &map_r_lo : &map_r_hi,
                                         bar_e_full + 8 * se, g * a.ecols, a.paired ? row0 >> 1 : row0, b);
+                        if (a.has_mrf)
+                            for (int pl = 0; pl < planes; ++pl)
+                                tma_load_3d(smem_e + se * e_slot_bytes + e_mrf_off + pl * a.e_plane_bytes, pl ? &map_m_lo : &map_m_hi,
+                                            bar_e_full + 8 * se, g * a.ecols, a.paired ? row0 >> 1 : row0, b);
                         if (++se == a.n_e) { se = 0; pe ^= 1u; }
                     }
                 }
@@ -389,7 +396,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 #pragma unroll
                             for (int cidx = 0; cidx < 4; ++cidx) {
                                 float f[8];
-                                unpack8(lds128(addr[cidx]), f);
+                                unpack8<kF16>(lds128(addr[cidx]), f);
                                 if (planes > 1) {
                                     float fl[8];
                                     unpack8(lds128(addr[cidx] + a.e_plane_bytes), fl);
@@ -419,16 +426,31 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         if (kHasRes) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] += res[i];
+                            if (a.has_mrf) {   // + running sum of the previous branches' outputs, then the 1/nk of the last branch
+#pragma unroll
+                                for (int cidx = 0; cidx < 4; ++cidx) {
+                                    float f[8];
+                                    unpack8<kF16>(lds128(addr[cidx] + e_mrf_off), f);
+                                    if (planes > 1) {
+                                        float fl[8];
+                                        unpack8(lds128(addr[cidx] + e_mrf_off + a.e_plane_bytes), fl);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) f[i] += fl[i];
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[cidx * 8 + i] = (v[cidx * 8 + i] + inv_lrelu(f[i])) * a.out_scale;
+                                }
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
 #pragma unroll
                         for (int cidx = 0; cidx < 4; ++cidx) {
                             uint4 hi;
-                            hi.x = pack_bf16(v[cidx * 8 + 0], v[cidx * 8 + 1]);
-                            hi.y = pack_bf16(v[cidx * 8 + 2], v[cidx * 8 + 3]);
-                            hi.z = pack_bf16(v[cidx * 8 + 4], v[cidx * 8 + 5]);
-                            hi.w = pack_bf16(v[cidx * 8 + 6], v[cidx * 8 + 7]);
+                            hi.x = pack2<kF16>(v[cidx * 8 + 0], v[cidx * 8 + 1]);
+                            hi.y = pack2<kF16>(v[cidx * 8 + 2], v[cidx * 8 + 3]);
+                            hi.z = pack2<kF16>(v[cidx * 8 + 4], v[cidx * 8 + 5]);
+                            hi.w = pack2<kF16>(v[cidx * 8 + 6], v[cidx * 8 + 7]);
                             sts128(addr[cidx], hi);
                             const bool direct = a.ups && uhalf == 0 && row0 + q * 32 == 0;   // box would start at q = -1: TMA stores fault there
                             const bool dwrite = direct && row >= 1 && row < a.L;   // GEMM rows 1 .. L_in of this box (plain stores are not clipped)
@@ -540,7 +562,7 @@ uint32_t rup(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 struct Umma2Launch::Impl {
     K2Args a;
-    alignas(64) CUtensorMap map_a[2], map_w[2], map_r[2], map_y[2];
+    alignas(64) CUtensorMap map_a[2], map_w[2], map_r[2], map_m[2], map_y[2];
     int grid;
     size_t smem;
 };
@@ -550,6 +572,8 @@ bool umma2_supported(const UmmaConvParams& p) {
     if (env_i("HFG_UMMA_V", 2) < 2) return false;
     if (p.cin_pad != g.Cin) return false;
     if (p.y_raw || p.res || p.xs || !p.y_act) return false;   // planes-only dataflow
+    if (p.mrf_hi && !p.res_hi) return false;                   // the MRF sum enters with the residual (last convs2 of a branch)
+    if (p.f16 && p.npass != 1) return false;
     if (g.ups_s == 1) {
         if (g.Np != g.Cout || g.Cout > 256 || g.Cout % 32 != 0 || g.Cin != g.Cout) return false;
     } else {   // polyphase upsampler with k = 2s (two taps, pad = s/2) whose whole N = s*C_out fits one tile
@@ -582,11 +606,14 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     const int span = std::max(g.tap_off0, last_off) - a.lo;
     a.planes = planes; a.npass = p.npass;
     a.has_res = (p.res_hi != nullptr);
+    a.has_mrf = (p.mrf_hi != nullptr) ? 1 : 0;
+    a.out_scale = a.has_mrf ? p.out_scale : 1.0f;
     a.paired = (!ups && N == 32 && g.Lin % 2 == 0 && env_i("HFG_U2_PAIRED", 1)) ? 1 : 0;
     a.bias = p.bias;
     a.y_hi = p.y_act; a.y_lo = p.y_act_lo;
     a.dbg = env_i("HFG_U2_DBG", 0);
     a.reverse = p.reverse;
+    a.f16 = p.f16 ? 1 : 0;
     // N = 32 always; N = 64 from 7 taps on (measured: k = 11 0.456 -> 0.420 ms, k = 7 0.316 -> 0.277 ms, k = 3 loses); wider layers
     // stream W, where halving MT would double that traffic.  Depends on the layer only: bits never depend on B or L.
     const int concat_maxn = env_i("HFG_U2_CONCAT_MAXN", 0);
@@ -623,7 +650,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
         if (ups && ecols != N / 2) continue;   // the two column groups are the two output half-rows
         const int groups = N / ecols;
         const uint32_t e_plane = 128u * (uint32_t)ecols * 2u;
-        const uint32_t e_slot = e_plane * planes;
+        const uint32_t e_slot = e_plane * planes * (a.has_mrf ? 2u : 1u);
         for (int mt = mt_max; mt >= 1; --mt) {
             const int rows_need = mt * 128 + span;
             const int pieces = (rows_need + 255) / 256;
@@ -632,9 +659,9 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
             const uint32_t a_stage = a_plane * planes;
             const int boxes = mt * groups;
             const double t_tile = (double)mt * nchunks * a.taps * ksteps * step_clk;
-            const double bytes = (double)pieces * box_rows * nchunks * row_bytes * planes + (a.has_res ? 2.0 : 1.0) * mt * 128.0 * N * 2.0 * planes;
+            const double bytes = (double)pieces * box_rows * nchunks * row_bytes * planes + (a.has_res ? (a.has_mrf ? 3.0 : 2.0) : 1.0) * mt * 128.0 * N * 2.0 * planes;
             // epilogue: ~(250 + 120 per residual plane) issue cycles per 32-column step and warp, 4 warps in parallel
-            const double t_epi = (double)mt * (N / 32) * (260.0 + (a.has_res ? 110.0 : 0.0) * planes + (planes > 1 ? 120.0 : 0.0)) + boxes * 150.0;
+            const double t_epi = (double)mt * (N / 32) * (260.0 + (a.has_res ? (a.has_mrf ? 220.0 : 110.0) : 0.0) * planes + (planes > 1 ? 120.0 : 0.0)) + boxes * 150.0;
             for (int resident = 1; resident >= 0; --resident) {
                 if (resident && (w_all > 140u * 1024u || n_tiles > 1)) continue;   // every column tile has its own weights
                 if (force_res >= 0 && resident != force_res) continue;
@@ -716,6 +743,10 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
         const void* r1 = (a.has_res && planes > 1) ? (const void*)p.res_lo : r0;
         if (!encode(&I->map_r[0], r0, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
         if (!encode(&I->map_r[1], r1, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
+        const void* m0p = a.has_mrf ? (const void*)p.mrf_hi : r0;
+        const void* m1p = (a.has_mrf && planes > 1) ? (const void*)p.mrf_lo : m0p;
+        if (!encode(&I->map_m[0], m0p, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
+        if (!encode(&I->map_m[1], m1p, 3, edims, estr, box, eb)) return HFG_ERR_CUDA;
         if (ups) {   // output [B][L_in * s][C_out] viewed as [B][L_in][2][N/2]: (half-row parity r, q = half-row / 2)
             const uint64_t NT = (uint64_t)g.Np;
             const uint64_t ud[4] = {NT / 2, 2, (uint64_t)g.Lin, (uint64_t)g.B};
@@ -739,10 +770,12 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev % 64]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        cudaError_t e = cudaSuccess;
+#define HFG_U2_ATTR(P, R, F) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<P, R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)
+        HFG_U2_ATTR(1, false, false); HFG_U2_ATTR(1, true, false); HFG_U2_ATTR(2, false, false); HFG_U2_ATTR(2, true, false);
+        HFG_U2_ATTR(1, false, true); HFG_U2_ATTR(1, true, true);
+#undef HFG_U2_ATTR
         if (e != cudaSuccess) return e;
         configured[dev % 64] = true;
     }
@@ -755,12 +788,13 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     static const int use_pdl = env_i("HFG_PDL", 1);
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-#define HFG_U2_LAUNCH(P, R)                                                                                              \
-    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<P, R>, I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1], \
-                           I.map_y[0], I.map_y[1], I.a)
+#define HFG_U2_LAUNCH(P, R, F)                                                                                           \
+    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<P, R, F>, I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1], \
+                           I.map_m[0], I.map_m[1], I.map_y[0], I.map_y[1], I.a)
     cudaError_t e;
-    if (I.a.planes == 2) { if (I.a.has_res) HFG_U2_LAUNCH(2, true); else HFG_U2_LAUNCH(2, false); }
-    else { if (I.a.has_res) HFG_U2_LAUNCH(1, true); else HFG_U2_LAUNCH(1, false); }
+    if (I.a.planes == 2) { if (I.a.has_res) HFG_U2_LAUNCH(2, true, false); else HFG_U2_LAUNCH(2, false, false); }
+    else if (I.a.f16) { if (I.a.has_res) HFG_U2_LAUNCH(1, true, true); else HFG_U2_LAUNCH(1, false, true); }
+    else { if (I.a.has_res) HFG_U2_LAUNCH(1, true, false); else HFG_U2_LAUNCH(1, false, false); }
     if (e != cudaSuccess) return e;
 #undef HFG_U2_LAUNCH
     return cudaGetLastError();

@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include <cstdio>
@@ -34,10 +35,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The bound is wall time on %globaltimer
+// (20 s), not a poll count: under time-slicing / MPS a healthy kernel may be descheduled for long stretches between polls, and a
+// trap is a sticky context error for the whole host process.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 24); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    for (uint32_t i = 1;; ++i) {
         if (mbar_try_wait(bar, parity)) return;
+        if ((i & 0x3fffu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) break;
+        }
+    }
     printf("hfg umma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
     __trap();
 }
@@ -189,6 +201,39 @@ __device__ __forceinline__ uint32_t f2_to_bf16x2(f2 v) {
     float a, b;
     f2_unpack(v, a, b);
     return pack_bf16(a, b);
+}
+
+// ---- 16-bit operand format of the single-plane modes: bf16 (8-bit significand) or fp16 (11-bit significand; HFG_PREC_FP16) ----
+// fp16 stores saturate to +-65504 instead of overflowing to inf (F2FP.SATFINITE): an activation that large is outside anything a
+// vocoder produces, but an inf would turn into NaN in the next MMA.
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack2(float a, float b) { return F16 ? pack_f16(a, b) : pack_bf16(a, b); }
+template <bool F16> __device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+    if (F16) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        a = f.x; b = f.y;
+    } else {
+        a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
+    }
+}
+template <bool F16> __device__ __forceinline__ f2 f2_from_h2(uint32_t w) {
+    float a, b;
+    unpack2<F16>(w, a, b);
+    return f2_pack(a, b);
+}
+template <bool F16> __device__ __forceinline__ uint32_t f2_to_h2(f2 v) {
+    float a, b;
+    f2_unpack(v, a, b);
+    return pack2<F16>(a, b);
+}
+// tcgen05 kind::f16 instruction descriptor: D = f32 (bit 4), A / B format at bits 7 / 10 (0 = f16, 1 = bf16), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n, bool f16) {
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // ---- programmatic dependent launch: the prologue (barriers, TMEM, weights) of kernel N+1 overlaps the tail of kernel N ----

@@ -97,7 +97,7 @@ V3 = GeneratorConfig(upsample_rates=(8, 8, 4), upsample_kernel_sizes=(16, 16, 8)
 
 
 def default_precision() -> str:
-    """Arithmetic mode used by the drop-in entry points.  ``IRIS_HIFIGAN_PRECISION`` = fp32 | bf16x3 | bf16."""
+    """Arithmetic mode used by the drop-in entry points.  ``IRIS_HIFIGAN_PRECISION`` = fp32 | bf16x3 | fp16 | bf16."""
     p = os.environ.get("IRIS_HIFIGAN_PRECISION", "bf16x3").lower()
     if p not in _abi.PRECISIONS:
         raise ValueError(f"IRIS_HIFIGAN_PRECISION={p!r}: expected one of {sorted(_abi.PRECISIONS)}")
@@ -260,16 +260,25 @@ class Engine:
                                            _abi.PRECISIONS[precision]))
         return y
 
-    def run_pair(self, resblock: int, m: int, x: np.ndarray, precision: str = "bf16x3"):
-        """One ResBlock step x + c2(lrelu(c1(lrelu(x)))) (hifigan_pretrained.py:66-70) in isolation; returns (y, fused)."""
+    def run_pair(self, resblock: int, m: int, x: np.ndarray, precision: str = "bf16x3", mrf_sum: Optional[np.ndarray] = None,
+                 out_scale: float = 1.0):
+        """One ResBlock step x + c2(lrelu(c1(lrelu(x)))) (hifigan_pretrained.py:66-70) in isolation; returns (y, fused).
+        With ``mrf_sum`` it is the LAST step of a branch with the MRF sum folded in (:133-137):
+        y = (x + c2(...) + mrf_sum) * out_scale."""
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 3:
             raise ValueError(f"x must be [B, C, L], got {x.shape}")
         B, _, L = x.shape
         y = np.empty_like(x)
         fused = ctypes.c_int32(0)
-        _abi.check(self._lib.hfg_run_pair(self._h, resblock, m, x.ctypes.data, B, L, y.ctypes.data, _abi.PRECISIONS[precision],
-                                          ctypes.byref(fused)))
+        mp = None
+        if mrf_sum is not None:
+            mrf_sum = np.ascontiguousarray(mrf_sum, dtype=np.float32)
+            if mrf_sum.shape != x.shape:
+                raise ValueError("mrf_sum must have the shape of x")
+            mp = mrf_sum.ctypes.data
+        _abi.check(self._lib.hfg_run_pair_mrf(self._h, resblock, m, x.ctypes.data, mp, float(out_scale), B, L, y.ctypes.data,
+                                              _abi.PRECISIONS[precision], ctypes.byref(fused)))
         return y, bool(fused.value)
 
     def get_tap(self, name: str, shape: Optional[Sequence[int]] = None) -> np.ndarray:

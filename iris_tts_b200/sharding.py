@@ -18,7 +18,35 @@ from typing import Callable, List, Optional, Tuple
 
 import numpy as np
 
-HALO_FRAMES = 16
+HALO_FRAMES = 16   # the V1 / V2 / V3-args generators (receptive field +-12.63 / +-12.6 / +-11.7 frames); see halo_frames()
+
+
+def receptive_field_frames(config) -> float:
+    """Upper bound, in mel frames per side, of the input span one output sample depends on, derived from the constructor
+    arguments (``GeneratorConfig``): conv_pre (k = 7) reaches 3 frames; a ConvTranspose1d(k, s, p = (k - s) / 2) reaches
+    ceil((k - p) / s) of ITS input samples; a ResBlock branch with kernel k and dilations d_m reaches
+    sum_m ((k - 1) / 2) * (d_m + 1) samples of its stage (convs1 dilated, convs2 not); conv_post 3 output samples.
+    Each term is divided by the number of samples per mel frame at the rate it acts on."""
+    import math
+
+    rf = 3.0
+    rate = 1.0   # samples per mel frame at the current stage input
+    for i, (u, k) in enumerate(zip(config.upsample_rates, config.upsample_kernel_sizes)):
+        p = (k - u) // 2
+        rf += math.ceil((k - p) / u) / rate
+        rate *= u
+        branch = max(sum(((kk - 1) // 2) * (d + 1) for d in dils)
+                     for kk, dils in zip(config.resblock_kernel_sizes, config.resblock_dilation_sizes))
+        rf += branch / rate
+    rf += 3.0 / rate
+    return rf
+
+
+def halo_frames(config) -> int:
+    """Halo (mel frames per inner chunk edge) that makes time-chunked synthesis exact for ``config``."""
+    import math
+
+    return int(math.ceil(receptive_field_frames(config)))
 
 
 def batch_shards(batch: int, world: int) -> List[Tuple[int, int]]:

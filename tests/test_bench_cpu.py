@@ -22,7 +22,10 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "vocoder_audio_samples_per_sec" and d["unit"] == "samples/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # baseline/_ref (the unmodified reference module, baseline/install_ref.py) is timed when present, the oracle port otherwise
+    want_kind = "reference" if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "iris", "hifigan_pretrained.py")) else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["same_config"] is True and d["config"]["batch_timed"] == 16
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 

@@ -114,3 +114,41 @@ def test_keras_surface_save_load_roundtrip(tmp_path):
         f.write(b"\x89HDF\r\n\x1a\n" + b"0" * 32)
     with pytest.raises(ValueError, match="HDF5"):
         b.load_weights(str(tmp_path / "fake.h5"))
+
+
+def test_pickled_reference_model_object_is_rebuilt_with_its_architecture():
+    """A checkpoint holding a whole model object pickled by the REFERENCE module (hifigan_pretrained.py:168-171; fixture made
+    by tests/golden/make_pickled_model.py with a NON-default architecture): torch.load rebuilds it as this repo's class, whose
+    __setstate__ must recover constructor arguments and every parameter from the pickled submodules."""
+    obj = torch.load(os.path.join(GOLD, "pickled_model.ckpt"), map_location="cpu", weights_only=False)
+    z = np.load(os.path.join(GOLD, "pickled_model_expected.npz"))
+    kw = json.loads(bytes(z["kwargs_json"]).decode())
+    sums = json.loads(bytes(z["weights_json"]).decode())
+    assert isinstance(obj, hp.HiFiGANModel)
+    assert obj.config.upsample_rates == tuple(kw["upsample_rates"])
+    assert obj.config.upsample_kernel_sizes == tuple(kw["upsample_kernel_sizes"])
+    assert obj.config.upsample_initial_channel == kw["upsample_initial_channel"]
+    assert obj.config.resblock_kernel_sizes == tuple(kw["resblock_kernel_sizes"])
+    assert obj.config.resblock_dilation_sizes == tuple(tuple(d) for d in kw["resblock_dilation_sizes"])
+    assert obj.training is False
+    sd = obj.state_dict()
+    assert set(sd) == set(sums)
+    for k, (s, a) in sums.items():
+        assert float(sd[k].double().sum()) == pytest.approx(s, rel=1e-12, abs=1e-12), k
+        assert float(sd[k].double().abs().sum()) == pytest.approx(a, rel=1e-12, abs=1e-12), k
+    # the oracle on those weights reproduces the reference's own output for the stored mel
+    ocfg = O.OracleConfig(80, tuple(kw["upsample_rates"]), tuple(kw["upsample_kernel_sizes"]), kw["upsample_initial_channel"],
+                          tuple(kw["resblock_kernel_sizes"]), tuple(tuple(d) for d in kw["resblock_dilation_sizes"]))
+    out = O.forward(sd, torch.from_numpy(z["mel"]), ocfg).numpy()
+    assert np.abs(out - z["out"]).max() <= 2e-5
+
+
+def test_our_model_object_round_trips_through_pickle(tmp_path):
+    torch.manual_seed(2)
+    m = hp.HiFiGANModel(upsample_initial_channel=128)
+    p = tmp_path / "ours.ckpt"
+    torch.save(m, p)
+    back = torch.load(p, map_location="cpu", weights_only=False)
+    assert back.config == m.config and back._engine is None
+    for k, v in m.state_dict().items():
+        assert torch.equal(back.state_dict()[k], v)

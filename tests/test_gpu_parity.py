@@ -4,9 +4,11 @@
 
 Tolerances (BASELINE.json north_star): fp32-class modes (``fp32`` CUDA-core FFMA and ``bf16x3`` split-bf16
 tcgen05) max-abs waveform error <= 1e-3 -- on the LOUD weight set too (output std 0.2; SURVEY.md section 7-1
-shows the default random-init output is too quiet to discriminate).  The ``bf16`` single-pass tensor-core mode
-is reported separately: <= 1e-3 at default init, <= 1.5e-1 on loud weights (measured 1.2e-2 .. 7.5e-2;
-its per-layer relative error is 2-3e-3, i.e. bf16 operand rounding).
+shows the default random-init output is too quiet to discriminate).  The single-pass tensor-core modes are
+reported separately, with the tolerance stated RELATIVE to the output's std (max-abs error of a tanh-bounded
+signal scales with how loud the signal is): ``bf16`` <= 0.15 std (operand rounding at 2^-9; float64 emulation of
+exactly that rounding, tools/emulate_rounding.py, gives 0.064 - 0.096 std on the loud goldens), ``fp16`` <= 0.025 std
+(rounding at 2^-12, TF32-class; emulation 0.009 - 0.010 std); both <= 1e-3 absolute at default init.
 """
 import json
 import os
@@ -22,10 +24,21 @@ pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = ["v1_default", "v1_loud", "v1_realistic_odd", "v2_loud", "v3_loud"]
-MODES = ["fp32", "bf16x3", "bf16"]
+MODES = ["fp32", "bf16x3", "fp16", "bf16"]
+TC_MODES = ["bf16x3", "fp16", "bf16"]
 # per-layer tolerance relative to max|reference output| of that layer
-LAYER_RTOL = {"fp32": 2e-5, "bf16x3": 1e-4, "bf16": 3e-2}
-E2E_TOL = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 1.5e-1}
+LAYER_RTOL = {"fp32": 2e-5, "bf16x3": 1e-4, "fp16": 4e-3, "bf16": 3e-2}
+PAIR_RTOL = {"bf16x3": 2e-4, "fp16": 6e-3, "bf16": 5e-2}
+# end to end: absolute for the fp32-class modes, relative to the reference output's std for the single-pass modes
+E2E_ABS = {"fp32": 1e-3, "bf16x3": 1e-3}
+E2E_REL_STD = {"fp16": 0.025, "bf16": 0.15}
+
+
+def e2e_tol(mode, ref):
+    """Max-abs waveform tolerance of `mode` against reference output `ref` (never below the headline 1e-3)."""
+    if mode in E2E_ABS:
+        return E2E_ABS[mode]
+    return max(1e-3, E2E_REL_STD[mode] * float(np.std(ref)))
 
 
 def _cfgs(name):
@@ -148,7 +161,7 @@ def _pair_ref(w, n, m, k, d, x):
 V1_PAIRS = [(6, 0), (6, 2), (7, 1), (7, 2), (8, 1), (9, 0), (9, 2), (10, 1), (11, 0), (11, 2), (4, 1)]
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 @pytest.mark.parametrize("n,m", V1_PAIRS)
 def test_v1_resblock_pair_parity(n, m, mode):
     eng, sd = _engine("v1")
@@ -159,14 +172,14 @@ def test_v1_resblock_pair_parity(n, m, mode):
     x = torch.randn(2, C, 777)                     # ragged: not a multiple of any tile height
     ref = _pair_ref(w, n, m, k, d, x)
     y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
-    if (C == 32 and not (mode == "bf16x3" and k == 11 and d == 5)) or (C == 64 and mode == "bf16" and k <= 7):
+    if (C == 32 and not (mode == "bf16x3" and k == 11 and d == 5)) or (C == 64 and mode != "bf16x3" and k <= 7):
         assert fused, "the plan is expected to fuse this pair"
     err = np.abs(y - ref).max()
-    tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
+    tol = PAIR_RTOL[mode] * max(1.0, np.abs(ref).max())
     assert err <= tol, f"resblocks.{n} pair {m} {mode} fused={fused}: max|err| {err:.3e} (ref max {np.abs(ref).max():.3f})"
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 def test_resblock_pair_edges_and_equals_unfused(mode):
     """Tile edges of the fused kernel (V = 128*MT - (k-1) valid rows per tile), the shortest inputs, odd lengths (C = 32 falls back
     from paired 128-byte boxes to 64-byte rows) -- against the oracle and against the two-launch plan, whose bits it must
@@ -190,7 +203,7 @@ def _pair_edges(eng, w, mode):
             x = torch.randn(1, C, L)
             ref = _pair_ref(w, n, m, k, d, x)
             y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
-            tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
+            tol = PAIR_RTOL[mode] * max(1.0, np.abs(ref).max())
             assert np.abs(y - ref).max() <= tol, (n, m, L, fused)
             if fused:
                 os.environ["HFG_PAIR"] = "0"
@@ -202,7 +215,7 @@ def _pair_edges(eng, w, mode):
                 np.testing.assert_array_equal(y, y2, err_msg=f"resblocks.{n} pair {m} L={L}")
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 def test_v3_resblock_pairs_wide_dilations(mode):
     """V3-args ResBlocks: k = 3 / 5 / 7 with dilations up to 12 (x halo of 36 rows each side, two TMA pieces) at C = 64 and 32."""
     eng, sd = _engine("v3")
@@ -216,7 +229,7 @@ def test_v3_resblock_pairs_wide_dilations(mode):
             x = torch.randn(2, C, L)
             ref = _pair_ref(w, n, m, k, d, x)
             y, fused = eng.run_pair(n, m, x.numpy(), precision=mode)
-            tol = {"bf16x3": 2e-4, "bf16": 5e-2}[mode] * max(1.0, np.abs(ref).max())
+            tol = PAIR_RTOL[mode] * max(1.0, np.abs(ref).max())
             assert np.abs(y - ref).max() <= tol, (n, m, L, fused)
             if fused:
                 os.environ["HFG_PAIR"] = "0"
@@ -231,7 +244,7 @@ def test_resblock_pair_batch_items_are_independent():
     eng, _ = _engine("v1")
     torch.manual_seed(5)
     x = torch.randn(5, 32, 900).numpy()
-    for mode in ("bf16x3", "bf16"):
+    for mode in TC_MODES:
         y, fused = eng.run_pair(10, 2, x, precision=mode)
         assert fused
         for b in (0, 4):
@@ -251,9 +264,9 @@ def test_golden_end_to_end(case, mode):
     ref = z["out"][:, 0]
     assert out.shape == ref.shape and out.dtype == np.float32
     err = float(np.abs(out - ref).max())
-    tol = E2E_TOL[mode] if meta["loud"] else 1e-3
-    assert err <= tol, f"{case} {mode}: max|err| {err:.3e} > {tol} (output std {ref.std():.3f})"
-    if mode != "bf16":
+    tol = e2e_tol(mode, ref) if meta["loud"] else 1e-3
+    assert err <= tol, f"{case} {mode}: max|err| {err:.3e} > {tol:.3e} (output std {ref.std():.3f})"
+    if mode in E2E_ABS:
         # the fp32-class modes are far inside the tolerance: also bound the error relative to the signal
         assert err <= 5e-4, f"{case} {mode}: {err:.3e}"
 
@@ -290,13 +303,13 @@ def test_batched_layer_matches_single_items():
     torch.manual_seed(3)
     for name, cin, L in (("resblocks.10.convs2.1", 32, 700), ("resblocks.5.convs1.2", 128, 300)):
         x = torch.randn(5, cin, L).numpy()
-        for mode in ("bf16x3", "bf16"):
+        for mode in TC_MODES:
             y = eng.run_layer(name, x, pre_lrelu=True, precision=mode)
             for b in (0, 4):
                 np.testing.assert_array_equal(y[b], eng.run_layer(name, x[b:b + 1], pre_lrelu=True, precision=mode)[0])
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 def test_time_folded_narrow_stages_match_padded_plan(mode):
     """V2's C = 16 / 8 stages: dense planes read as [L/f][32] with folded weights (engine.cu build_folded) against the plan that
     carries them padded to 32 channels (HFG_FOLD=0).  Same products, different accumulation grouping: equal to fp32 rounding in
@@ -317,19 +330,24 @@ def test_time_folded_narrow_stages_match_padded_plan(mode):
         finally:
             del os.environ["HFG_FOLD"]
     ref = O.infer(sd, mel, O.V2)
-    assert np.abs(outs[0] - ref).max() <= E2E_TOL[mode]
-    assert np.abs(outs[0] - outs[1]).max() <= (1e-4 if mode == "bf16x3" else 2e-2)
+    assert np.abs(outs[0] - ref).max() <= e2e_tol(mode, ref)
+    assert np.abs(outs[0] - outs[1]).max() <= {"bf16x3": 1e-4, "fp16": 3e-3, "bf16": 2e-2}[mode]
 
 
-def test_fused_plan_equals_tapped_plan_bitwise():
-    """The production plan forms the MRF mean of the last stage inside conv_post; the KEEP_TAPS plan materialises every
-    intermediate.  Same kernels and arithmetic order on the data path -> identical bits."""
+def test_production_plan_against_tapped_plan():
+    """The KEEP_TAPS plan materialises every intermediate and forms the MRF mean in a separate pass over the three branch
+    outputs; the production plan folds the branch sum into the last convs2 epilogue of branches 1 and 2 (the partial sums are
+    rounded to the operand planes instead of the branch outputs): the same function to operand-plane rounding.  The fp32 family
+    has one plan shape only -> identical bits."""
     eng, _ = _engine("v1")
     mel = O.synthetic_mel(2, 40, seed=3)
-    for mode in ("fp32", "bf16x3"):
+    a = eng.forward(mel, precision="fp32")
+    b = eng.forward(mel, precision="fp32", keep_taps=True)
+    np.testing.assert_array_equal(a, b)
+    for mode, tol in (("bf16x3", 5e-5), ("fp16", 4e-3), ("bf16", 3e-2)):
         a = eng.forward(mel, precision=mode)
         b = eng.forward(mel, precision=mode, keep_taps=True)
-        np.testing.assert_array_equal(a, b)
+        assert np.abs(a - b).max() <= tol, (mode, float(np.abs(a - b).max()))
 
 
 # ---------------------------------------------------------------------------
@@ -362,6 +380,7 @@ def test_time_chunking_with_halo_equals_full_forward():
     mel = O.synthetic_mel(1, T, seed=21, realistic=True)
     full = eng.forward(mel, precision="bf16x3")[0]
     parts = []
+    assert sharding.halo_frames(eng.config) <= sharding.HALO_FRAMES
     for c in sharding.time_chunks(T, 8):
         w = eng.forward(mel[:, :, c.lo:c.hi], precision="bf16x3")[0]
         parts.append(w[c.trim_front * 256: w.size - c.trim_back * 256])
@@ -391,10 +410,10 @@ def test_ragged_and_minimal_shapes(mode):
         ref = O.infer(sd, mel, O.V2)
         out = eng.forward(mel, precision=mode)
         assert out.shape == (B, T * 256)
-        assert np.abs(out - ref).max() <= E2E_TOL[mode], (B, T)
+        assert np.abs(out - ref).max() <= e2e_tol(mode, ref), (B, T)
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 def test_v1_minimal_lengths_through_the_wide_upsamplers(mode):
     """T = 1, 2, 3 frames on V1: the 128-column-tiled upsamplers ups.0/1 see 2..25 GEMM rows (their first output box is written with
     plain stores that must stop at the end of the sequence), the pair kernels a single partial tile."""
@@ -404,7 +423,7 @@ def test_v1_minimal_lengths_through_the_wide_upsamplers(mode):
         ref = O.infer(sd, mel)
         out = eng.forward(mel, precision=mode)
         assert out.shape == (B, T * 256)
-        assert np.abs(out - ref).max() <= E2E_TOL[mode], (B, T)
+        assert np.abs(out - ref).max() <= e2e_tol(mode, ref), (B, T)
 
 
 @pytest.mark.parametrize("cfg_name", ["v1", "v2", "v3"])
@@ -424,7 +443,7 @@ def test_no_kernel_writes_outside_its_buffers(cfg_name):
             ref = O.infer(sd, mel, ocfg)
             for mode in MODES:
                 out = eng.forward(mel, precision=mode)              # raises HfgError if a canary was overwritten
-                assert np.abs(out - ref).max() <= E2E_TOL[mode], (B, T, mode)
+                assert np.abs(out - ref).max() <= e2e_tol(mode, ref), (B, T, mode)
             eng.forward(mel, precision="bf16x3", keep_taps=True)
         eng.close()
     finally:
