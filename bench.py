@@ -199,7 +199,10 @@ def run_reference(args):
     t0 = time.perf_counter()
     gen.time(B, T, 1, 0)
     t_full = time.perf_counter() - t0
-    budget_s = 240.0
+    t0 = time.perf_counter()
+    gen.time(B, T, 1, 0)                 # the second forward: oneDNN primitives are cached now
+    t_full = time.perf_counter() - t0
+    budget_s = 360.0
     n_steps = args.steps + args.warmup
     b_step = B if t_full * n_steps <= budget_s else max(1, int(B * budget_s / (t_full * n_steps)))
     r = gen.time(b_step, T, args.steps, args.warmup)
@@ -508,13 +511,25 @@ def run_ours(args):
                 "dtype": mode, "value": samples_per_step / (ms_m * 1e-3), "unit": "samples/s", "ms_per_step": ms_m,
                 "layer_roofline_ms": rl * 1e3, "layer_roofline_frac": rl * 1e3 / ms_m, "roofline": dom,
                 "roofline_other_kernels": other_rooflines(recs_m, peaks, mode, dom),
-                "tolerance": {"bf16": "max-abs <= 6e-2 vs oracle on loud weights (output std 0.23), 1.5e-1 on the loud realistic-mel golden; "
-                                      "1e-3 at default init (tests/test_gpu_parity.py)",
-                              "fp16": "max-abs <= 8e-3 vs oracle on loud weights (TF32-class; emulation 2.2e-3 at T = 64), 3e-2 on the loud "
-                                      "realistic-mel golden; 1e-3 at default init (tests/test_gpu_parity.py)"}[mode]}
+                "tolerance": {"bf16": "max-abs <= 0.15 x output std vs oracle on loud weights (measured 0.064-0.10 std: 1.5e-2 at std 0.23, "
+                                      "B=32 x 10 s), <= 1e-3 at default init (tests/test_gpu_parity.py, test_gpu_north_star.py)",
+                              "fp16": "max-abs <= 0.025 x output std vs oracle on loud weights (measured 0.006-0.012 std: 2e-3 at std 0.23; "
+                                      "TF32-class), <= 1e-3 at default init (tests/test_gpu_parity.py, test_gpu_north_star.py)"}[mode]}
         # the north-star's own target case (BASELINE.json: V1 at batch 32 x 10 s, 16-bit tensor-core mode, 1 GPU: >= 50 % of the
         # per-layer roofline); single GPU only
         if world == 1:
+            # BASELINE config 3 at N = 1: batch sweep in the bf16 tensor-core mode.  Ascending and BEFORE the long legs: the
+            # latency end of the sweep (1 ms per forward) is timed before the power cap has pulled the clocks down.
+            sweep = []
+            torch.cuda.synchronize()
+            time.sleep(0.5)
+            for b in (1, 2, 4, 8, 16, 32, 64):
+                mel_b = torch.randn(b, 80, T, device="cuda")
+                out_b = torch.empty(b, T * hop, dtype=torch.float32, device="cuda")
+                nst = 40 if b <= 2 else (16 if b <= 8 else (8 if b <= 16 else 5))
+                ms_m, rl = mode_leg("bf16", b, mel_b, out_b, nst, 3, voc.model.config)
+                sweep.append({"batch": b, "ms_per_step": ms_m, "value": b * T * hop / (ms_m * 1e-3), "layer_roofline_frac": rl * 1e3 / ms_m, "steps": nst})
+                del mel_b, out_b
             B32 = 32
             mel32 = torch.randn(B32, 80, T, device="cuda")
             out32 = torch.empty(B32, T * hop, dtype=torch.float32, device="cuda")
@@ -524,14 +539,6 @@ def run_ours(args):
                 north[mode] = {"ms_per_step": ms_m, "value": B32 * T * hop / (ms_m * 1e-3), "unit": "samples/s",
                                "layer_roofline_ms": rl * 1e3, "layer_roofline_frac": rl * 1e3 / ms_m}
             del mel32, out32
-            # BASELINE config 3 at N = 1: batch sweep in the bf16 tensor-core mode
-            sweep = []
-            for b in (1, 2, 4, 8, 16, 32, 64):
-                mel_b = torch.randn(b, 80, T, device="cuda")
-                out_b = torch.empty(b, T * hop, dtype=torch.float32, device="cuda")
-                ms_m, rl = mode_leg("bf16", b, mel_b, out_b, 8 if b <= 16 else 5, 3, voc.model.config)
-                sweep.append({"batch": b, "ms_per_step": ms_m, "value": b * T * hop / (ms_m * 1e-3), "layer_roofline_frac": rl * 1e3 / ms_m})
-                del mel_b, out_b
             # BASELINE config 5: the small generators at batch 64 (memory-bound regime)
             for name, cfg in (("v2_b64", E.V2), ("v3_b64", E.V3)):
                 torch.manual_seed(0)

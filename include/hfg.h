@@ -154,6 +154,35 @@ int hfg_run_pair_mrf(hfg_engine* e, int32_t resblock, int32_t m, const float* x,
  * Pass out == NULL to query the element count via *n. */
 int hfg_get_tap(hfg_engine* e, const char* name, float* out, size_t* n);
 
+/* ---- log-mel front-end: the step immediately before the vocoder -------------------------------------
+ *
+ *   hfg_logmel_create / _forward   compute_mel_spectrogram  src/iris/data.py:25-67, i.e.
+ *                                  librosa.feature.melspectrogram(power=1.0) (data.py:51-62; librosa 0.11.0, uv.lock:872:
+ *                                  periodic Hann, center=True with zero padding, Slaney filterbank) and
+ *                                  np.log(np.clip(mel, 1e-5, None)) (data.py:65)
+ * audio [B][N] fp32 -> mel [B][n_mels][T], T = 1 + N / hop_length: the [B, 80, T] array hfg_forward consumes. */
+typedef struct hfg_logmel_config {
+    int32_t sample_rate;   /* 22050 */
+    int32_t n_fft;         /* 1024 (a power of two in [64, 4096]) */
+    int32_t hop_length;    /* 256 */
+    int32_t win_length;    /* 1024 (<= n_fft) */
+    int32_t n_mels;        /* 80 */
+    float fmin;            /* 0 */
+    float fmax;            /* 8000; <= 0 means sample_rate / 2 */
+    float clip;            /* 1e-5 */
+    int32_t log_output;    /* 1: natural log of the clipped magnitude mel (data.py:65); 0: the magnitude mel itself */
+} hfg_logmel_config;
+
+typedef struct hfg_logmel hfg_logmel;
+
+#define HFG_LOGMEL_AUDIO_ON_DEVICE 1u
+#define HFG_LOGMEL_OUT_ON_DEVICE 2u
+
+int hfg_logmel_create(const hfg_logmel_config* cfg, int device, hfg_logmel** out);
+void hfg_logmel_destroy(hfg_logmel* h);
+int32_t hfg_logmel_frames(const hfg_logmel* h, int32_t n_samples);
+int hfg_logmel_forward(hfg_logmel* h, const float* audio, int32_t B, int32_t N, float* mel, uint32_t flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,22 @@ class HfgConfig(ctypes.Structure):
     ]
 
 
+class HfgLogmelConfig(ctypes.Structure):
+    _fields_ = [
+        ("sample_rate", c_int32),
+        ("n_fft", c_int32),
+        ("hop_length", c_int32),
+        ("win_length", c_int32),
+        ("n_mels", c_int32),
+        ("fmin", c_float),
+        ("fmax", c_float),
+        ("clip", c_float),
+        ("log_output", c_int32),
+    ]
+
+
+LOGMEL_AUDIO_ON_DEVICE, LOGMEL_OUT_ON_DEVICE = 1, 2
+
 # name -> (restype, argtypes); every symbol include/hfg.h declares
 SIGNATURES = {
     "hfg_abi_version": (c_int, []),
@@ -55,6 +71,10 @@ SIGNATURES = {
     "hfg_run_layer": (c_int, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32]),
     "hfg_run_pair": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "hfg_run_pair_mrf": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "hfg_logmel_create": (c_int, [POINTER(HfgLogmelConfig), c_int, POINTER(c_void_p)]),
+    "hfg_logmel_destroy": (None, [c_void_p]),
+    "hfg_logmel_frames": (c_int32, [c_void_p, c_int32]),
+    "hfg_logmel_forward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_uint32]),
     "hfg_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_size_t)]),
 }
 

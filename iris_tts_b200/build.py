@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhfg_b200.so")
-SOURCES = ["engine.cu", "kernels_fp32.cu", "kernels_umma.cu", "kernels_umma2.cu", "kernels_pair.cu"]
+SOURCES = ["engine.cu", "kernels_fp32.cu", "kernels_umma.cu", "kernels_umma2.cu", "kernels_pair.cu", "kernels_mel.cu"]
 HEADERS = [os.path.join(CSRC, "hfg_internal.h"), os.path.join(CSRC, "umma_ptx.cuh"), os.path.join(HERE, "..", "include", "hfg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]

@@ -537,10 +537,12 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     const int npass = x3 ? 3 : 1;
     auto wts_hi = [&](const Layer& L) { return f16 ? L.d_wh : L.d_wb_hi; };
     const int a_per_tap = env_flag("HFG_UMMA_A_PER_TAP", 0);
-    // MRF sum folded into the producers (:133-137): the last convs2 of branch j >= 1 adds the running sum of branches 0..j-1 in its
-    // epilogue, the last branch also applies 1/nk and writes the stage output -- no separate combine pass.  The tap plan keeps
-    // the separate pass (it must expose every branch output).
-    const bool mrf_fold = env_flag("HFG_MRF_FOLD", 1) != 0 && !keep_taps && c.num_kernels > 1;
+    // MRF sum folded into the producers (:133-137), HFG_MRF_FOLD=1: the last convs2 of branch j >= 1 adds the running sum of
+    // branches 0..j-1 in its epilogue, the last branch also applies 1/nk and writes the stage output -- no separate combine
+    // pass.  OFF by default: measured on B200 (profiles/r02_ab_mrf_fold_graph.md) the extra plane stream costs the consuming
+    // epilogues what the removed passes saved (bf16 B=16: 9.20 vs 9.19 ms; bf16x3: the two-plane staging slots double and the
+    // C = 64 convs2 lose 0.26-0.38 ms each).  The tap plan always keeps the separate pass (it must expose every branch output).
+    const bool mrf_fold = env_flag("HFG_MRF_FOLD", 0) != 0 && !keep_taps && c.num_kernels > 1;
     const int snake = env_flag("HFG_SNAKE", 1);   // alternate the tile direction of consecutive convs (L2 reuse)
     int n_umma2 = 0;
     const int c0 = c.upsample_initial_channel;

@@ -191,16 +191,26 @@ def test_repeated_runs_are_bitwise_identical_under_varied_pipelines(mode):
             eng = Engine(V1, 0)
             eng.load_state_dict(sd, strict=True)
             eng.finalize()
+            mine = None                                    # first output of THIS engine
             for _ in range(40):
                 out.zero_()
                 torch.cuda.synchronize()
                 eng.forward_ptr(mel.data_ptr(), 16, 862, out.data_ptr(), mode, mel_on_device=True, wave_on_device=True)
-                if first is None:
-                    first = out.clone()
-                    ref = O.infer(sd, mel[3:4].cpu().numpy())[0]
-                    assert np.abs(first[3].cpu().numpy() - ref).max() <= e2e_tol(mode, ref)
+                if mine is None:
+                    mine = out.clone()
+                    if first is None:
+                        first = mine
+                        ref = O.infer(sd, mel[3:4].cpu().numpy())[0]
+                        assert np.abs(first[3].cpu().numpy() - ref).max() <= e2e_tol(mode, ref)
+                    elif not torch.equal(mine, first):
+                        # A forced depth that a layer cannot be planned with sends that layer to the first-generation kernel, whose
+                        # K-chunk order differs in bf16x3 (64- vs 32-channel chunks): the same sums in another fp32 order (after ~80
+                        # layers the waveforms differ at the mode's own error level, measured 3e-5), not a race.
+                        d = float((mine - first).abs().max())
+                        print(f"[stress] {mode} overrides {ov}: plan differs from the default one, max|diff| {d:.2e}")
+                        assert mode == "bf16x3" and d <= 1e-4, (mode, ov, d)
                 else:
-                    assert torch.equal(out, first), f"run {runs} differs from run 0 (overrides {ov})"
+                    assert torch.equal(out, mine), f"run {runs} differs from the first run of its engine (overrides {ov})"
                 runs += 1
             eng.close()
         finally:

@@ -1,0 +1,59 @@
+"""The log-mel oracle (oracle/logmel_oracle.py: float64 restatement of librosa 0.11.0's melspectrogram(power=1) + log clip,
+which is what src/iris/data.py:25-67 computes) pinned against INDEPENDENT implementations available in this image: librosa
+itself is not installable, so the pin is transformers.audio_utils (documents itself as matching librosa for these options) and
+scipy.signal.get_window -- a cross-implementation pin, stated as such in DESIGN.md."""
+import numpy as np
+import pytest
+
+from oracle import logmel_oracle as LO
+
+
+def test_window_is_scipys_periodic_hann():
+    scipy_signal = pytest.importorskip("scipy.signal")
+    for n in (1024, 800, 64):
+        np.testing.assert_allclose(LO.hann_periodic(n), scipy_signal.get_window("hann", n, fftbins=True), atol=1e-15)
+
+
+def test_slaney_filterbank_matches_transformers_audio_utils():
+    au = pytest.importorskip("transformers.audio_utils")
+    for sr, n_fft, n_mels, fmin, fmax in ((22050, 1024, 80, 0.0, 8000.0), (16000, 512, 40, 50.0, None), (22050, 2048, 128, 0.0, None)):
+        fb = LO.mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
+        ref = au.mel_filter_bank(1 + n_fft // 2, n_mels, fmin, fmax if fmax else sr / 2, sr, norm="slaney", mel_scale="slaney").T
+        assert fb.shape == ref.shape == (n_mels, 1 + n_fft // 2)
+        np.testing.assert_allclose(fb, ref, atol=1e-12)
+    # known answers of the Slaney scale (librosa docs): 1000 Hz = 15 mel, linear below, 6.4x per 27 mel above
+    assert LO.hz_to_mel(1000.0) == pytest.approx(15.0)
+    assert LO.hz_to_mel(6400.0) == pytest.approx(42.0)
+    assert LO.mel_to_hz(LO.hz_to_mel(np.array([60.0, 440.0, 8000.0]))) == pytest.approx([60.0, 440.0, 8000.0])
+
+
+def test_mel_spectrogram_matches_transformers_spectrogram():
+    au = pytest.importorskip("transformers.audio_utils")
+    scipy_signal = pytest.importorskip("scipy.signal")
+    rng = np.random.default_rng(0)
+    for n in (22050, 5000, 1023, 256):
+        y = rng.standard_normal(n) * 0.1
+        filt = au.mel_filter_bank(513, 80, 0.0, 8000.0, 22050, norm="slaney", mel_scale="slaney")
+        ref = au.spectrogram(y, scipy_signal.get_window("hann", 1024, fftbins=True), 1024, 256, fft_length=1024, power=1.0, center=True,
+                             pad_mode="constant", mel_filters=filt, mel_floor=1e-5, dtype=np.float64)
+        got = LO.mel_linear(y)
+        assert got.shape == ref.shape == (80, 1 + n // 256)
+        np.testing.assert_allclose(np.maximum(got, 1e-5), ref, atol=2e-7)
+        np.testing.assert_allclose(LO.compute_mel_spectrogram(y), np.log(ref), atol=2e-3)
+
+
+def test_known_answers():
+    # silence sits on the clip floor; frame count is 1 + N // hop; a tone lands in the band whose centre is nearest
+    assert np.allclose(LO.compute_mel_spectrogram(np.zeros(1024)), np.log(1e-5))
+    sr = 22050
+    t = np.arange(5000) / sr
+    mel = LO.compute_mel_spectrogram(0.5 * np.sin(2 * np.pi * 2000.0 * t))
+    assert mel.shape == (80, 20)
+    centres = LO.mel_to_hz(np.linspace(LO.hz_to_mel(0.0), LO.hz_to_mel(8000.0), 82))[1:-1]
+    assert int(np.argmax(mel[:, 10])) == int(np.argmin(np.abs(centres - 2000.0)))
+    # a unit impulse at a frame centre has a flat magnitude spectrum equal to the window's centre value (1.0): every mel band
+    # then sums its own weights
+    y = np.zeros(4096)
+    y[2048] = 1.0
+    lin = LO.mel_linear(y)
+    np.testing.assert_allclose(lin[:, 8], LO.mel_filterbank().sum(axis=1), rtol=1e-12)

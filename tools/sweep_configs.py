@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--batches", default="1,2,4,8,16,32,64")
     ap.add_argument("--modes", default="bf16,bf16x3")
     ap.add_argument("--frames", type=int, default=862)
+    ap.add_argument("--v1-only", action="store_true")
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
     import torch
 
@@ -59,7 +61,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         rl = work.layer_roofline_seconds(cfg, B, T, 2, P, BW) * 1e3
-        print(json.dumps({"model": name, "batch": B, "frames": T, "mode": mode, "ms": round(ms, 4),
+        print(json.dumps({"tag": a.tag, "model": name, "batch": B, "frames": T, "mode": mode, "ms": round(ms, 4),
                           "samples_per_s": round(B * T * eng.hop / (ms * 1e-3)), "x_realtime": round(B * T * eng.hop / (ms * 1e-3) / 22050, 1),
                           "layer_roofline_bf16_ms": round(rl, 4), "frac_of_bf16_layer_roofline": round(rl / ms, 4),
                           "workspace_gb": round(eng.workspace_bytes(B, T, mode) / 2**30, 2)}), flush=True)
@@ -69,6 +71,8 @@ def main():
         for B in [int(x) for x in a.batches.split(",")]:
             run("V1", E.V1, m1, B, mode)
     del m1
+    if a.v1_only:
+        return
     for name, cfg in (("V2", E.V2), ("V3-args", E.V3)):
         m = model_for(cfg)
         for mode in a.modes.split(","):
