@@ -132,23 +132,38 @@ class HiFiGANGenerator:
         self._dirty = True
 
     def save_weights(self, weights_path: str) -> None:
-        """Writes a NumPy ``.npz`` archive keyed ``<layer>/kernel`` and ``<layer>/bias`` (Keras layouts)."""
+        """Writes a NumPy ``.npz`` archive keyed ``<layer>/kernel`` and ``<layer>/bias`` (Keras layouts).  Writing HDF5 is
+        not offered: nothing in this image can check that a hand-rolled HDF5 writer produces files libhdf5 accepts."""
+        if str(weights_path).endswith((".h5", ".hdf5", ".keras")):
+            raise ValueError(f"{weights_path}: this build writes the NumPy archive only (use a .npz path); Keras .weights.h5 / "
+                             ".keras files can be READ by load_weights")
         with open(weights_path, "wb") as f:
             np.savez(f, **self.weights)
 
     def load_weights(self, weights_path: str) -> None:
+        """``.npz`` written by save_weights, or a Keras 3 weight file: ``*.weights.h5`` (HDF5) / ``*.keras`` (zip archive holding
+        ``model.weights.h5``), which is what the reference's ``keras.Model.load_weights`` reads (vocoder.py:167-170)."""
         path = str(weights_path)
         with open(path, "rb") as f:
             magic = f.read(8)
+        if magic.startswith(b"PK") and not path.endswith(".npz"):          # .keras archive
+            import tempfile
+            import zipfile
+
+            with zipfile.ZipFile(path) as zf, tempfile.TemporaryDirectory() as d:
+                zf.extract("model.weights.h5", d)
+                return self.load_weights(str(Path(d) / "model.weights.h5"))
         if magic.startswith(b"\x89HDF"):
-            raise ValueError(
-                f"{path} is an HDF5 Keras weight file; this build reads the NumPy archive written by save_weights "
-                "(h5py is not available). Convert with keras: np.savez(path, **{v.path: v.numpy() for v in model.weights})."
-            )
-        z = np.load(path)
+            from iris_tts_b200.h5lite import H5File
+
+            z = keras_h5_to_weights(H5File(path).datasets(), self.config)
+            files = set(z)
+        else:
+            z = np.load(path)
+            files = set(z.files)
         new = dict(self.weights)
         for k in self.weights:
-            if k not in z.files:
+            if k not in files:
                 raise ValueError(f"{path}: missing array {k}")
             a = np.asarray(z[k], dtype=np.float32)
             if a.shape != self.weights[k].shape:
@@ -166,6 +181,52 @@ class HiFiGANGenerator:
             "resblock_kernel_sizes": self.resblock_kernel_sizes,
             "resblock_dilations": self.resblock_dilations,
         }
+
+
+_KERAS_WRAPPERS = {"layers", "_layer_checkpoint_dependencies", "model", "generator"}
+
+
+def _suffix_index(name: str) -> int:
+    """Keras names the saveables of a list attribute by class: ``conv1d``, ``conv1d_1``, ``conv1d_2`` ... -> 0, 1, 2."""
+    import re
+
+    m = re.search(r"_(\d+)$", name)
+    return int(m.group(1)) if m else 0
+
+
+def keras_h5_to_weights(datasets: Dict[str, np.ndarray], config) -> Dict[str, np.ndarray]:
+    """Map the dataset paths of a Keras 3 ``.weights.h5`` of the reference's ``HiFiGANGenerator`` (vocoder.py:52-101) onto
+    ``<layer>/kernel`` / ``<layer>/bias``.
+
+    Keras 3's ``saving_lib`` stores a layer's variables as ``<attribute path>/vars/<i>`` (0 = kernel, 1 = bias); the members of a
+    list attribute are named by snake-cased class with a running suffix.  For the reference model that gives
+    ``conv_pre/vars/0``, ``ups/conv1d_transpose_2/vars/1``, ``resblocks/res_block_7/convs1/conv1d_1/vars/0``, ``conv_post/...``
+    (optionally below a wrapper group such as ``layers/``).  Keras is not installable here, so this layout is taken from
+    saving_lib as published (keras 3.12, the reference's pin uv.lock:823) and is **not pinned by a file Keras wrote**."""
+    out: Dict[str, np.ndarray] = {}
+    for path, arr in datasets.items():
+        if isinstance(arr, Exception):
+            continue
+        parts = [p for p in path.split("/") if p]
+        if len(parts) < 3 or parts[-2] != "vars" or not parts[-1].isdigit():
+            continue
+        which = {0: "kernel", 1: "bias"}.get(int(parts[-1]))
+        owner = [p for p in parts[:-2] if p not in _KERAS_WRAPPERS]
+        if which is None or not owner:
+            continue
+        name = None
+        if owner[-1] in ("conv_pre", "conv_post") and len(owner) == 1:
+            name = owner[-1]
+        elif len(owner) == 2 and owner[0] == "ups":
+            name = f"ups.{_suffix_index(owner[1])}"
+        elif len(owner) == 4 and owner[0] == "resblocks" and owner[2] in ("convs1", "convs2"):
+            name = f"resblocks.{_suffix_index(owner[1])}.{owner[2]}.{_suffix_index(owner[3])}"
+        if name is None:
+            continue
+        out[f"{name}/{which}"] = np.asarray(arr, dtype=np.float32)
+    if not out:
+        raise ValueError("no Keras layer variables (<layer>/vars/<i>) found in the HDF5 file: " + ", ".join(sorted(datasets)[:8]))
+    return out
 
 
 class HiFiGANVocoder:

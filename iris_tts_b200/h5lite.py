@@ -11,7 +11,6 @@ test data, tests/test_h5lite_cpu.py).  Read-only: nothing here can write HDF5.
 """
 from __future__ import annotations
 
-import struct
 from typing import Dict, Iterator, List, Tuple, Union
 
 import numpy as np
@@ -151,16 +150,25 @@ class H5File:
                 raise H5Unsupported("filtered (compressed) dataset")
             elif mtype == 0x08:                 # data layout
                 ver = self.buf[body]
-                if ver != 3:
-                    raise H5Unsupported(f"data layout message version {ver}")
-                lclass = self.buf[body + 1]
-                if lclass == 0:                 # compact
-                    n = self._u(body + 2, 2)
-                    data = (body + 4, n)
-                elif lclass == 1:               # contiguous
-                    data = (self._addr(body + 2), self._u(body + 2 + self.so, self.sl))
+                if ver == 3:
+                    lclass = self.buf[body + 1]
+                    if lclass == 0:             # compact: size, then the raw data inside the header
+                        data = (body + 4, self._u(body + 2, 2))
+                    elif lclass == 1:           # contiguous: address, size
+                        data = (self._addr(body + 2), self._u(body + 2 + self.so, self.sl))
+                    else:
+                        raise H5Unsupported("chunked dataset layout")
+                elif ver in (1, 2):             # older writers: version, rank, class, 5 reserved, [address], rank x 4-byte dims, ...
+                    rank, lclass = self.buf[body + 1], self.buf[body + 2]
+                    if lclass == 1:
+                        data = (self._addr(body + 8), None)
+                    elif lclass == 0:
+                        p2 = body + 8 + 4 * rank
+                        data = (p2 + 4, self._u(p2, 4))
+                    else:
+                        raise H5Unsupported("chunked dataset layout")
                 else:
-                    raise H5Unsupported("chunked dataset layout")
+                    raise H5Unsupported(f"data layout message version {ver}")
         if dims is None or dtype is None or data is None:
             raise ValueError("object is not a dataset")
         count = int(np.prod(dims)) if dims else 1

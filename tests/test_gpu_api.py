@@ -124,6 +124,31 @@ def test_variable_length_batches_are_exact(loud_ckpt):
             np.testing.assert_array_equal(o, gen(m))        # identical to running the utterance alone
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
+def test_ragged_batch_by_buckets_and_tails_equals_per_utterance_forwards(loud_ckpt, mode):
+    """f4: 12 utterances of 12 distinct lengths (33 .. 400 frames) in a handful of dense calls -- a zero-padded body pass per
+    length bucket plus ONE tail pass over every utterance's last 32 frames -- bit-identical to twelve batch-1 forwards."""
+    import iris.hifigan_pretrained as hp
+    from iris_tts_b200 import sharding
+    from iris_tts_b200.batching import synthesize_variable
+    gen = hp.get_pretrained_hifigan(loud_ckpt)
+    old = gen.model.precision
+    gen.model.precision = mode
+    try:
+        assert sharding.halo_frames(gen.model.config) <= sharding.HALO_FRAMES
+        lengths = (400, 33, 371, 64, 390, 127, 350, 32, 398, 129, 65, 301)
+        mels = [O.synthetic_mel(1, t, seed=50 + i, realistic=(i % 2 == 0))[0] for i, t in enumerate(lengths)]
+        stats = {}
+        outs = synthesize_variable(gen, mels, stats=stats)
+        assert stats["distinct_lengths"] == 12 and stats["calls"] <= 7, stats
+        for m, o in zip(mels, outs):
+            np.testing.assert_array_equal(o, gen(m))
+        ref = O.infer(O.random_state_dict(O.V1, seed=0, loud=True), mels[5])
+        assert np.abs(outs[5] - ref).max() <= (1e-3 if mode == "bf16x3" else 0.025 * ref.std())
+    finally:
+        gen.model.precision = old
+
+
 def test_cli_end_to_end(loud_ckpt, tmp_path):
     spec = importlib.util.spec_from_file_location("synthesize_cli", os.path.join(ROOT, "scripts", "synthesize.py"))
     cli = importlib.util.module_from_spec(spec)

@@ -130,3 +130,62 @@ def test_world_size_2_gloo_longform_gather_and_batch_shards():
     fullb = O.forward(sd, torch.from_numpy(O.synthetic_mel(3, 20, seed=12)), O.V2).numpy()
     assert (r0, r1) == ((0, 2), (2, 3))
     assert np.abs(np.concatenate([part0, part1]) - fullb).max() <= 5e-6
+
+
+# ---------------------------------------------------------------------------
+# ragged batches: length buckets + one tail pass (iris_tts_b200/batching.py), with the oracle standing in for the engine
+# ---------------------------------------------------------------------------
+
+def test_halo_derived_from_the_constructor_arguments_covers_the_receptive_field():
+    from iris_tts_b200.engine import V1, V2, V3
+    for cfg in (V1, V2, V3):
+        assert 12 <= sharding.halo_frames(cfg) <= sharding.HALO_FRAMES
+    # empirically: perturbing the mel `halo` frames away does not change a sample, one frame inside the bound it may
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    mel = torch.from_numpy(O.synthetic_mel(1, 80, seed=4))
+    base = O.forward(sd, mel, O.V2).reshape(-1)
+    h = sharding.halo_frames(V2)
+    bumped = mel.clone()
+    bumped[:, :, 40 + h:] += 1.0
+    out = O.forward(sd, bumped, O.V2).reshape(-1)
+    assert torch.equal(out[: 40 * 256], base[: 40 * 256])
+    assert not torch.equal(out[: (40 + h) * 256], base[: (40 + h) * 256])
+
+
+def test_length_buckets_bound_the_padding():
+    from iris_tts_b200.batching import length_buckets
+    lengths = [400, 33, 371, 64, 390, 127, 350, 32, 398, 129, 65, 301]
+    b = length_buckets(lengths, max_pad=0.15)
+    assert sorted(i for g in b for i in g) == list(range(len(lengths)))
+    for g in b:
+        top = max(lengths[i] for i in g)
+        assert all(lengths[i] >= 0.85 * top for i in g)
+    assert len(b) < len(lengths)
+    assert all(len(g) <= 2 for g in length_buckets(lengths, max_pad=0.15, max_batch=2))
+    assert length_buckets([], 0.1) == []
+
+
+def test_ragged_batch_scheme_is_exact_against_per_utterance_forwards():
+    from iris_tts_b200.batching import synthesize_variable
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    calls = []
+
+    def vocoder(batch):
+        calls.append(batch.shape)
+        return O.infer(sd, batch, O.V2)
+
+    lengths = (90, 33, 84, 64, 7, 70, 32, 7, 0, 31)
+    mels = [O.synthetic_mel(1, t, seed=20 + i)[0] if t else np.zeros((80, 0), np.float32) for i, t in enumerate(lengths)]
+    stats = {}
+    outs = synthesize_variable(vocoder, mels, stats=stats)
+    n_calls = len(calls)
+    assert stats["calls"] == n_calls < len(set(lengths))
+    for m, o, t in zip(mels, outs, lengths):
+        assert o.shape == (t * 256,) and o.dtype == np.float32
+        if t:
+            np.testing.assert_allclose(o, O.infer(sd, m[None], O.V2)[0], atol=2e-6)
+    # a halo smaller than the receptive field is NOT exact (the scheme depends on it)
+    bad = synthesize_variable(vocoder, mels[:1], halo=4)
+    assert np.abs(bad[0] - O.infer(sd, mels[0][None], O.V2)[0]).max() > 1e-4
+    with pytest.raises(ValueError):
+        synthesize_variable(vocoder, [np.zeros((1, 80, 5), np.float32)])
