@@ -65,7 +65,9 @@ typedef enum hfg_precision {
 #define HFG_MEL_ON_DEVICE 1u    /* mel is a device pointer (default: host)   */
 #define HFG_WAVE_ON_DEVICE 2u   /* wave is a device pointer (default: host)  */
 #define HFG_KEEP_TAPS 4u        /* keep copies of intermediate activations for hfg_get_tap */
-#define HFG_NO_SYNC 8u          /* device pointers only: enqueue and return; call hfg_sync */
+#define HFG_NO_SYNC 8u          /* enqueue and return; call hfg_sync before reading the result.  Host pointers are allowed if
+                                   they are PAGE-LOCKED and stay valid until hfg_sync: the waveform then reaches the host on a
+                                   second stream, so the D2H copy of forward i overlaps the kernels of forward i+1 */
 
 /* The six constructor arguments of the reference generator
  * (hifigan_pretrained.py:77-85 / vocoder.py:59-68). */

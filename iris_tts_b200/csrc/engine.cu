@@ -162,6 +162,14 @@ struct hfg_engine {
     // run_layer scratch
     uint8_t* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // asynchronous host output (HFG_NO_SYNC with a page-locked host wave pointer): the waveform is parked in one of two device
+    // staging buffers and copied to the host on a second stream, so the D2H of forward i overlaps the kernels of forward i+1
+    cudaStream_t copy_stream = nullptr;
+    float* wave_stage[2] = {nullptr, nullptr};
+    size_t wave_stage_bytes[2] = {0, 0};
+    cudaEvent_t ev_plan_done[2] = {nullptr, nullptr}, ev_d2h_done[2] = {nullptr, nullptr};
+    bool d2h_pending[2] = {false, false};
+    uint64_t async_count = 0;
 };
 
 namespace hfg {
@@ -991,6 +999,11 @@ int hfg_create(const hfg_config* cfg, int device, hfg_engine** out) {
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&e->ev_plan_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_d2h_done[i], cudaEventDisableTiming));
+    }
     build_layers(e.get());
     if (const char* nl = getenv("HFG_NCU_LAYERS")) {   // profiling aid: ncu --profile-from-start off captures only these
         std::string cur;
@@ -1007,7 +1020,14 @@ void hfg_destroy(hfg_engine* e) {
     if (!e) return;
     DeviceGuard guard(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     e->plans.clear();
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(e->wave_stage[i]);
+        if (e->ev_plan_done[i]) cudaEventDestroy(e->ev_plan_done[i]);
+        if (e->ev_d2h_done[i]) cudaEventDestroy(e->ev_d2h_done[i]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (auto& L : e->layers) free_layer_dev(L);
     for (auto& kv : e->folded) free_layer_dev(kv.second);
     for (auto& kv : e->taps) cudaFree(kv.second.dev);
@@ -1126,6 +1146,8 @@ int hfg_sync(hfg_engine* e) {
     if (!e) return fail(HFG_ERR_INVALID, "hfg_sync: null engine");
     GUARD(e);
     CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->copy_stream));
+    e->d2h_pending[0] = e->d2h_pending[1] = false;
     return HFG_OK;
 }
 
@@ -1136,7 +1158,10 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     if (!e->finalized) return fail(HFG_ERR_STATE, "hfg_forward: call hfg_finalize first");
     const bool mel_dev = flags & HFG_MEL_ON_DEVICE, wave_dev = flags & HFG_WAVE_ON_DEVICE;
     const bool keep = flags & HFG_KEEP_TAPS;
-    if ((flags & HFG_NO_SYNC) && !(mel_dev && wave_dev)) return fail(HFG_ERR_INVALID, "hfg_forward: HFG_NO_SYNC needs device pointers");
+    // HFG_NO_SYNC with HOST pointers: both must be page-locked and stay valid until hfg_sync (the copies are asynchronous);
+    // not combined with taps or the canary mode, which read results back inside the call
+    const bool async_host = (flags & HFG_NO_SYNC) && !(mel_dev && wave_dev);
+    if (async_host && (keep || env_flag("HFG_GUARD", 0))) return fail(HFG_ERR_INVALID, "hfg_forward: HFG_NO_SYNC with host pointers excludes HFG_KEEP_TAPS / HFG_GUARD");
     GUARD(e);
 
     const auto key = std::make_tuple((int)B, (int)T, (int)precision, keep ? 1 : 0);
@@ -1179,6 +1204,26 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
                     return fail(HFG_ERR_CUDA, buf);
                 }
         }
+    }
+    if (async_host && !wave_dev) {
+        const int k = (int)(e->async_count++ & 1);
+        if (e->wave_stage_bytes[k] < wave_bytes) {
+            CK(cudaStreamSynchronize(e->copy_stream));
+            CK(cudaStreamSynchronize(e->stream));
+            cudaFree(e->wave_stage[k]);
+            e->wave_stage[k] = nullptr; e->wave_stage_bytes[k] = 0;
+            CK(cudaMalloc(&e->wave_stage[k], wave_bytes));
+            e->wave_stage_bytes[k] = wave_bytes;
+            e->d2h_pending[k] = false;
+        }
+        if (e->d2h_pending[k]) CK(cudaStreamWaitEvent(e->stream, e->ev_d2h_done[k], 0));   // staging buffer k is free again
+        CK(cudaMemcpyAsync(e->wave_stage[k], plan->wave_dev, wave_bytes, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaEventRecord(e->ev_plan_done[k], e->stream));
+        CK(cudaStreamWaitEvent(e->copy_stream, e->ev_plan_done[k], 0));
+        CK(cudaMemcpyAsync(wave, e->wave_stage[k], wave_bytes, cudaMemcpyDeviceToHost, e->copy_stream));
+        CK(cudaEventRecord(e->ev_d2h_done[k], e->copy_stream));
+        e->d2h_pending[k] = true;
+        return HFG_OK;
     }
     CK(cudaMemcpyAsync(wave, plan->wave_dev, wave_bytes, wave_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     if (!(flags & HFG_NO_SYNC)) CK(cudaStreamSynchronize(e->stream));

@@ -229,9 +229,25 @@ class Engine:
             if self._pin_in is None or self._pin_in.numel() < mel.size:
                 self._pin_in = torch.empty(mel.size, dtype=torch.float32, pin_memory=True)
             stage = self._pin_in[: mel.size].view(B, mel.shape[1], T)
-            np.copyto(stage.numpy(), mel, casting="unsafe")
+            # torch's caching host allocator hands the same page-locked block back once the previous result array is dropped:
+            # no cudaHostAlloc per call in steady state
             out_t = torch.empty((B, T * self.hop), dtype=torch.float32, pin_memory=True)
-            self.forward_ptr(stage.data_ptr(), B, T, out_t.data_ptr(), precision, keep_taps=keep_taps)
+            if keep_taps or B < 4 or B * T < 4000:
+                np.copyto(stage.numpy(), mel, casting="unsafe")
+                self.forward_ptr(stage.data_ptr(), B, T, out_t.data_ptr(), precision, keep_taps=keep_taps)
+                return out_t.numpy()
+            # Two half-batches, enqueued without waiting (utterances are independent: the halves reproduce the whole batch's
+            # bits).  The host converts / stages the second half while the GPU runs the first, and the first half's waveform
+            # travels to the host on the copy stream while the second half computes: only the first stage-in and the last D2H
+            # are exposed (hifigan_pretrained.py:228-235 does H2D, forward, D2H strictly in sequence).
+            b0 = (B + 1) // 2
+            try:
+                np.copyto(stage[:b0].numpy(), mel[:b0], casting="unsafe")
+                self.forward_ptr(stage[:b0].data_ptr(), b0, T, out_t[:b0].data_ptr(), precision, sync=False)
+                np.copyto(stage[b0:].numpy(), mel[b0:], casting="unsafe")
+                self.forward_ptr(stage[b0:].data_ptr(), B - b0, T, out_t[b0:].data_ptr(), precision, sync=False)
+            finally:
+                self.sync()        # nothing may still be writing into the page-locked buffers when this frame unwinds
             return out_t.numpy()
         m = np.ascontiguousarray(mel, dtype=np.float32)
         out = np.empty((B, T * self.hop), dtype=np.float32)

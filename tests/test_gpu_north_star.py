@@ -140,6 +140,25 @@ def test_graph_launch_equals_direct_launch(mode):
     eng.close()
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_pipelined_host_path_equals_the_synchronous_one(mode):
+    """Engine.forward on a large enough batch runs two half-batches back to back without waiting (HFG_NO_SYNC with page-locked
+    host pointers): the second half is staged on the host while the first computes, and the first half's waveform is copied out
+    on the copy stream while the second computes.  Same bits as the synchronous whole-batch call, call after call."""
+    eng, sd = _engine("v1")
+    for B, T in ((16, 300), (5, 1000), (4, 1001)):
+        mel = O.synthetic_mel(B, T, seed=B + T)
+        want = eng.forward(mel, precision=mode, pinned=False)          # pageable buffers: one synchronous whole-batch forward
+        for _ in range(3):
+            got = eng.forward(mel, precision=mode)                       # pipelined halves
+            np.testing.assert_array_equal(got, want)
+        other = eng.forward(O.synthetic_mel(B, T, seed=1), precision=mode)   # staging buffers are reused across calls, results are not
+        assert not np.array_equal(other, want)
+        np.testing.assert_array_equal(eng.forward(mel, precision=mode), want)
+    ref = O.infer(sd, mel[1:2])[0]
+    assert np.abs(want[1] - ref).max() <= e2e_tol(mode, ref)
+
+
 def test_caller_device_is_left_alone():
     """Every ABI call runs on the engine's device and restores the caller's current device."""
     if torch.cuda.device_count() < 2:
