@@ -121,6 +121,8 @@ size_t hfg_workspace_bytes(const hfg_engine* e, int32_t B, int32_t T, int32_t pr
 void* hfg_stream(hfg_engine* e);
 /* Kernels launched by this handle since creation (bench "gpu_launches"). */
 uint64_t hfg_launch_count(const hfg_engine* e);
+/* Plans whose launches were captured into a CUDA graph / whose capture failed (those keep launching kernel by kernel). */
+int hfg_graph_stats(const hfg_engine* e, int32_t* captured, int32_t* failed);
 
 /* Per-launch device timing for roofline reports (bench.py): when enabled, every kernel launch
  * of the following hfg_forward calls is bracketed by CUDA events on the engine's stream.  Records

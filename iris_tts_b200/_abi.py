@@ -64,6 +64,7 @@ SIGNATURES = {
     "hfg_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32, c_int32]),
     "hfg_stream": (c_void_p, [c_void_p]),
     "hfg_launch_count": (c_uint64, [c_void_p]),
+    "hfg_graph_stats": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32)]),
     "hfg_profile_enable": (c_int, [c_void_p, c_int]),
     "hfg_profile_count": (c_int, [c_void_p]),
     "hfg_profile_get": (c_int, [c_void_p, c_int, c_char_p, c_size_t, c_char_p, c_size_t, POINTER(c_float),

@@ -80,7 +80,8 @@ struct Layer {
     __nv_bfloat16* d_wh = nullptr;     // same layout, fp16 values (HFG_PREC_FP16); 16-bit storage shares the pointer type
 };
 
-enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_PAIR, S_POST32, S_ACCUM, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP };
+enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_PAIR, S_POST32, S_ACCUM, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP,
+                S_FORK, S_JOIN };   // the branch lanes of a stage start after / end before this point (no kernel)
 
 struct Step {
     StepKind kind;
@@ -100,6 +101,7 @@ struct Step {
     const float* bias = nullptr;
     int B = 0, L = 0, C = 0, k = 0, cpad = 0;
     int flag0 = 0, flag1 = 0, f16 = 0;
+    int lane = 0;   // 0: the engine's stream; j > 0: ResBlock branch j of a stage whose branches run concurrently (small inputs)
     float fval = 0.f;
     size_t n = 0;
     std::string tap_name;
@@ -164,12 +166,18 @@ struct hfg_engine {
     size_t scratch_bytes = 0;
     // asynchronous host output (HFG_NO_SYNC with a page-locked host wave pointer): the waveform is parked in one of two device
     // staging buffers and copied to the host on a second stream, so the D2H of forward i overlaps the kernels of forward i+1
+    // The nk ResBlock branches of a stage are independent (hifigan_pretrained.py:131-136).  When one kernel cannot fill the GPU
+    // (batch 1-2, long-form chunks) branches 1.. run on these streams, forked after the upsampler and joined before the MRF mean;
+    // under graph capture they become parallel branches of the plan's graph.
+    cudaStream_t lane_stream[HFG_MAX_KERNELS] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[HFG_MAX_KERNELS] = {};
     cudaStream_t copy_stream = nullptr;
     float* wave_stage[2] = {nullptr, nullptr};
     size_t wave_stage_bytes[2] = {0, 0};
     cudaEvent_t ev_plan_done[2] = {nullptr, nullptr}, ev_d2h_done[2] = {nullptr, nullptr};
     bool d2h_pending[2] = {false, false};
     uint64_t async_count = 0;
+    int graphs_captured = 0, graphs_failed = 0;
 };
 
 namespace hfg {
@@ -599,7 +607,27 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     // tensor-core operand planes
     struct Planes { bf* hi = nullptr; bf* lo = nullptr; };
     auto take_planes = [&](size_t n) { Planes p; p.hi = bump.take<bf>(n); if (x3) p.lo = bump.take<bf>(n); return p; };
+    // Concurrent branch lanes for stages one kernel cannot fill: fewer than HFG_BRANCH_PAR_TILES (default 4) x SM-count 128-row
+    // tiles.  HFG_BRANCH_PAR = 0: never, 1: every stage, default -1: by that size rule.
+    const int par_mode = env_flag("HFG_BRANCH_PAR", -1);
+    const double par_tiles = (double)env_flag("HFG_BRANCH_PAR_TILES", 4) * e->sm_count;
+    bool par_stage[HFG_MAX_UPSAMPLES] = {};
+    bool par_any = false;
+    size_t par_elems = 0;
+    {
+        size_t Ls = (size_t)T;
+        for (int i = 0; i < NU; ++i) {
+            Ls *= c.upsample_rates[i];
+            const double tiles = (double)B * (double)Ls / 128.0;
+            par_stage[i] = any_tc && i < n_tc && nk > 1 && !keep_taps && !mrf_fold && par_mode != 0 && (par_mode == 1 || tiles < par_tiles);
+            if (par_stage[i]) {
+                par_any = true;
+                par_elems = std::max(par_elems, (size_t)B * Ls * std::max(32, c0 >> (i + 1)));
+            }
+        }
+    }
     Planes mel_p, x0_p, u_p, xt_p, pp[2], s_p, r_p[HFG_MAX_KERNELS];
+    Planes xt_b[HFG_MAX_KERNELS], pp_b[HFG_MAX_KERNELS][2];   // per-branch temporaries of the concurrent lanes (branch 0 uses xt_p / pp)
     if (any_tc) {
         mel_p = take_planes((size_t)B * T * pre.cin_pad);
         x0_p = take_planes(n_pre);
@@ -607,8 +635,13 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
             u_p = take_planes(smax_tc); xt_p = take_planes(smax_tc); pp[0] = take_planes(smax_tc); pp[1] = take_planes(smax_tc);
             s_p = take_planes(smax_tc);
             for (int j = 0; j < nk; ++j) r_p[j] = take_planes(smax_tc);
+            xt_b[0] = xt_p; pp_b[0][0] = pp[0]; pp_b[0][1] = pp[1];
+            for (int j = 1; j < nk && par_any; ++j) {
+                xt_b[j] = take_planes(par_elems); pp_b[j][0] = take_planes(par_elems); pp_b[j][1] = take_planes(par_elems);
+            }
         }
     }
+    int cur_lane = 0;   // lane of the steps being emitted
 
     // F_l = 2*Cin*Cout*k*L (L = L_out for Conv1d, L_in for ConvTranspose1d); Q_l = activations in + out + weights
     auto work = [&](Step& s, const Layer& L, int Lin, int act_bytes) {
@@ -639,6 +672,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
             s.kind = S_UMMA;
             RET(plan_conv_umma(&s.ul, p, x.hi, x.lo, wts_hi(L), L.d_wb_lo));
         }
+        s.lane = cur_lane;
         plan->steps.push_back(std::move(s));
         return HFG_OK;
     };
@@ -670,6 +704,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         const double act_b = x3 ? 4.0 : 2.0;
         s.kind = S_PAIR; s.label = label; s.flops += w2.flops;
         s.bytes = 2.0 * r1.cin * (double)rL * B * act_b + 2.0 * (double)r1.cin * r1.cout * r1.k * act_b;
+        s.lane = cur_lane;
         plan->steps.push_back(std::move(s));
         return true;
     };
@@ -734,9 +769,14 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
             snprintf(nm, sizeof nm, "ups.%d", i);
             tap_planes(nm, u_p, ch, L, fold);
             const int rows = L / f;
+            const bool par = par_stage[i];
+            if (par) { Step s{}; s.kind = S_FORK; s.flag0 = nk; push(std::move(s)); }
             for (int j = 0; j < nk; ++j, ++n) {
                 Planes xin = u_p;
                 const int nd = c.num_dilations[j];
+                cur_lane = par ? j : 0;
+                const Planes xt_use = par ? xt_b[j] : xt_p;
+                const Planes pp_use[2] = {par ? pp_b[j][0] : pp[0], par ? pp_b[j][1] : pp[1]};
                 for (int m = 0; m < nd; ++m) {
                     const Layer& o1 = layer("resblocks.%d.convs1.%d", n, m);
                     const Layer& o2 = layer("resblocks.%d.convs2.%d", n, m);
@@ -747,19 +787,21 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
                     // the stage output s_p = sum / nk
                     const bool fold_in = mrf_fold && last_m && j > 0;
                     const bool fold_out = mrf_fold && last_m && j == nk - 1;
-                    Planes xout = fold_out ? s_p : (last_m ? r_p[j] : pp[m & 1]);
+                    Planes xout = fold_out ? s_p : (last_m ? r_p[j] : pp_use[m & 1]);
                     const Planes mrf_in = fold_in ? r_p[j - 1] : Planes();
                     const float osc = fold_out ? 1.0f / (float)nk : 1.0f;
                     snprintf(nm, sizeof nm, "resblocks.%d.pair.%d", n, m);
                     if (!pair(c1, c2, rows, xin, xout, nm, fold ? &o1 : nullptr, fold ? &o2 : nullptr, L, mrf_in, osc)) {
-                        RET(umma(c1, rows, xin, Planes(), nullptr, xt_p, fold ? &o1 : nullptr, L));   // :66-67 (+ :68 in the epilogue)
-                        RET(umma(c2, rows, xt_p, xin, nullptr, xout, fold ? &o2 : nullptr, L, mrf_in, osc));   // :69-70 (+ :133-137)
+                        RET(umma(c1, rows, xin, Planes(), nullptr, xt_use, fold ? &o1 : nullptr, L));   // :66-67 (+ :68 in the epilogue)
+                        RET(umma(c2, rows, xt_use, xin, nullptr, xout, fold ? &o2 : nullptr, L, mrf_in, osc));   // :69-70 (+ :133-137)
                     }
                     xin = xout;
                 }
                 snprintf(nm, sizeof nm, "resblocks.%d", n);
                 tap_planes(nm, r_p[j], ch, L, fold);
             }
+            cur_lane = 0;
+            if (par) { Step s{}; s.kind = S_JOIN; s.flag0 = nk; push(std::move(s)); }
             const bool fuse_post = last_stage && !keep_taps;   // the MRF mean of the last stage is computed inside conv_post
             if (!fuse_post && !mrf_fold) {   // xs = sum_j r_j ; x = xs / nk  (:133-137)
                 Step s{}; s.kind = S_MRF; s.n = ne;
@@ -864,6 +906,7 @@ const char* kind_label(StepKind k) {
 }
 
 int run_plan(hfg_engine* e, Plan* plan);
+inline bool is_kernel_step(StepKind k) { return k != S_TAP && k != S_FORK && k != S_JOIN; }
 
 // Launches the plan's kernels: as ONE CUDA graph once the plan has run before (production path: no per-launch driver work
 // on the host, which is what bounds short inputs), directly otherwise (first forward of a shape, profiling, taps, canaries, ncu).
@@ -883,9 +926,13 @@ int launch_plan(hfg_engine* e, Plan* plan) {
         if (g) cudaGraphDestroy(g);
         e->launches = l0;   // capture enqueued nothing
         if (err != cudaSuccess) {   // not fatal: keep launching kernel by kernel
+            if (env_flag("HFG_GRAPH_VERBOSE", 0)) fprintf(stderr, "hfg: graph capture failed (%s); launching directly\n", cudaGetErrorString(err));
             cudaGetLastError();
             plan->graph = nullptr;
             plan->graph_failed = true;
+            ++e->graphs_failed;
+        } else {
+            ++e->graphs_captured;
         }
     }
     ++plan->runs;
@@ -898,6 +945,8 @@ int launch_plan(hfg_engine* e, Plan* plan) {
 }
 
 int run_plan(hfg_engine* e, Plan* plan) {
+    // per-launch profiling and ncu bracketing serialise everything on the engine's stream; otherwise branch lanes are honoured
+    const bool lanes = !e->profiling && e->ncu_layers.empty();
     cudaStream_t st = e->stream;
     size_t nev = e->prof_used;
     if (e->profiling) {
@@ -909,6 +958,20 @@ int run_plan(hfg_engine* e, Plan* plan) {
         CK(cudaEventRecord(e->prof_events[nev++], st));
     }
     for (const Step& s : plan->steps) {
+        if (s.kind == S_FORK || s.kind == S_JOIN) {
+            if (!lanes) continue;
+            for (int l = 1; l < s.flag0; ++l) {
+                if (s.kind == S_FORK) {
+                    if (l == 1) CK(cudaEventRecord(e->ev_fork, e->stream));
+                    CK(cudaStreamWaitEvent(e->lane_stream[l], e->ev_fork, 0));
+                } else {
+                    CK(cudaEventRecord(e->ev_join[l], e->lane_stream[l]));
+                    CK(cudaStreamWaitEvent(e->stream, e->ev_join[l], 0));
+                }
+            }
+            continue;
+        }
+        st = (lanes && s.lane > 0) ? e->lane_stream[s.lane] : e->stream;
         const bool ncu = !e->ncu_layers.empty() && s.kind != S_TAP &&
                          (e->ncu_layers[0] == "*" || std::find(e->ncu_layers.begin(), e->ncu_layers.end(), s.label) != e->ncu_layers.end());
         if (ncu) cudaProfilerStart();
@@ -925,6 +988,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_MEL_CL32: CK(launch_transpose_cf_to_cl(s.f_in, s.f_out, s.B, s.C, s.L, st)); break;
             case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, 0, s.f16, st)); break;
             case S_TAP: RET(store_tap(e, s)); break;   // a copy, not one of our kernels
+            case S_FORK: case S_JOIN: break;
         }
         if (ncu) cudaProfilerStop();
         if (s.kind != S_TAP) ++e->launches;
@@ -1000,6 +1064,11 @@ int hfg_create(const hfg_config* cfg, int device, hfg_engine** out) {
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    for (int i = 1; i < cfg->num_kernels; ++i) {
+        CK(cudaStreamCreateWithFlags(&e->lane_stream[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&e->ev_plan_done[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->ev_d2h_done[i], cudaEventDisableTiming));
@@ -1028,6 +1097,11 @@ void hfg_destroy(hfg_engine* e) {
         if (e->ev_d2h_done[i]) cudaEventDestroy(e->ev_d2h_done[i]);
     }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (int i = 1; i < HFG_MAX_KERNELS; ++i) {
+        if (e->lane_stream[i]) { cudaStreamSynchronize(e->lane_stream[i]); cudaStreamDestroy(e->lane_stream[i]); }
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
     for (auto& L : e->layers) free_layer_dev(L);
     for (auto& kv : e->folded) free_layer_dev(kv.second);
     for (auto& kv : e->taps) cudaFree(kv.second.dev);
@@ -1116,6 +1190,13 @@ size_t hfg_workspace_bytes(const hfg_engine* e, int32_t B, int32_t T, int32_t pr
 void* hfg_stream(hfg_engine* e) { return e ? (void*)e->stream : nullptr; }
 uint64_t hfg_launch_count(const hfg_engine* e) { return e ? e->launches : 0; }
 
+int hfg_graph_stats(const hfg_engine* e, int32_t* captured, int32_t* failed) {
+    if (!e) return fail(HFG_ERR_INVALID, "hfg_graph_stats: null engine");
+    if (captured) *captured = e->graphs_captured;
+    if (failed) *failed = e->graphs_failed;
+    return HFG_OK;
+}
+
 int hfg_profile_enable(hfg_engine* e, int on) {
     if (!e) return fail(HFG_ERR_INVALID, "hfg_profile_enable: null engine");
     // (re)enabling starts a fresh record list; disabling keeps the records readable
@@ -1178,7 +1259,7 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
         plan->bytes = bytes;
         // All plans share the arena from offset 0: they run one after another on one stream.
         RET(build_plan(e, B, T, precision, keep, e->arena, plan.get(), nullptr));
-        for (const Step& st : plan->steps) plan->kernels += st.kind != S_TAP;
+        for (const Step& st : plan->steps) plan->kernels += is_kernel_step(st.kind);
         it = e->plans.emplace(key, std::move(plan)).first;
     }
     Plan* plan = it->second.get();

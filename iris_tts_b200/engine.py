@@ -232,7 +232,7 @@ class Engine:
             # torch's caching host allocator hands the same page-locked block back once the previous result array is dropped:
             # no cudaHostAlloc per call in steady state
             out_t = torch.empty((B, T * self.hop), dtype=torch.float32, pin_memory=True)
-            if keep_taps or B < 4 or B * T < 4000:
+            if keep_taps or B < 4 or B * T < 4000 or os.environ.get("HFG_PIPELINE", "1") == "0":
                 np.copyto(stage.numpy(), mel, casting="unsafe")
                 self.forward_ptr(stage.data_ptr(), B, T, out_t.data_ptr(), precision, keep_taps=keep_taps)
                 return out_t.numpy()
@@ -328,6 +328,13 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.hfg_launch_count(self._h))
+
+    @property
+    def graph_stats(self) -> Tuple[int, int]:
+        """(plans captured into a CUDA graph, plans whose capture failed and that launch kernel by kernel)."""
+        a, b = ctypes.c_int32(0), ctypes.c_int32(0)
+        _abi.check(self._lib.hfg_graph_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
 
     def workspace_bytes(self, B: int, T: int, precision: str = "fp32") -> int:
         return int(self._lib.hfg_workspace_bytes(self._h, B, T, _abi.PRECISIONS[precision]))

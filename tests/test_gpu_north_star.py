@@ -134,6 +134,7 @@ def test_graph_launch_equals_direct_launch(mode):
     for _ in range(4):                                 # graph (captured on the second call)
         np.testing.assert_array_equal(eng.forward(mel, precision=mode), first)
     assert n0 > 0 and eng.launch_count == 5 * n0      # the launch counter keeps counting kernels under graph launch
+    assert eng.graph_stats == (1, 0)                   # B = 3 x 45 frames: captured WITH the concurrent branch lanes of its stages
     other = O.synthetic_mel(3, 45, seed=18)            # a graph replays the plan, not the data
     ref = O.infer(sd, other)
     assert np.abs(eng.forward(other, precision=mode) - ref).max() <= e2e_tol(mode, ref)
@@ -157,6 +158,38 @@ def test_pipelined_host_path_equals_the_synchronous_one(mode):
         np.testing.assert_array_equal(eng.forward(mel, precision=mode), want)
     ref = O.infer(sd, mel[1:2])[0]
     assert np.abs(want[1] - ref).max() <= e2e_tol(mode, ref)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_concurrent_branch_lanes_equal_the_serial_plan(mode):
+    """Small inputs run the three ResBlock branches of a stage on three streams (parallel branches of the plan's graph).  Same
+    kernels on the same data in per-branch buffers: identical bits to the serial plan (HFG_BRANCH_PAR=0), also when forced on for
+    a batch that fills the GPU, also kernel by kernel without a graph."""
+    from iris_tts_b200 import Engine
+    from iris_tts_b200.engine import V1
+    sd = O.random_state_dict(O.V1, seed=0, loud=True)
+    outs = {}
+    for par in ("0", "1"):
+        os.environ["HFG_BRANCH_PAR"] = par
+        try:
+            eng = Engine(V1, 0)
+            eng.load_state_dict(sd, strict=True)
+            eng.finalize()
+            for B, T in ((1, 862), (2, 97), (8, 300)):
+                mel = O.synthetic_mel(B, T, seed=B * 7 + T)
+                first = eng.forward(mel, precision=mode)                 # direct launches (lanes as plain streams)
+                for _ in range(3):
+                    np.testing.assert_array_equal(eng.forward(mel, precision=mode), first)   # graph
+                outs.setdefault((B, T), []).append(first)
+            assert eng.graph_stats[1] == 0
+            eng.close()
+        finally:
+            del os.environ["HFG_BRANCH_PAR"]
+    for key, (serial, parallel) in outs.items():
+        np.testing.assert_array_equal(serial, parallel, err_msg=str(key))
+    mel = O.synthetic_mel(1, 862, seed=1 * 7 + 862)
+    ref = O.infer(sd, mel)
+    assert np.abs(outs[(1, 862)][1] - ref).max() <= e2e_tol(mode, ref)
 
 
 def test_caller_device_is_left_alone():

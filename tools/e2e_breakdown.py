@@ -37,7 +37,20 @@ def main():
     print("empty pinned    %.3f ms" % t(lambda: torch.empty((B, T * eng.hop), dtype=torch.float32, pin_memory=True)))
     print("device forward  %.3f ms" % t(lambda: (eng.forward_ptr(mel_dev.data_ptr(), B, T, out_dev.data_ptr(), mode, mel_on_device=True, wave_on_device=True, sync=False), eng.sync())))
     print("pinned forward  %.3f ms" % t(lambda: eng.forward_ptr(pin_in.data_ptr(), B, T, out_pin.data_ptr(), mode)))
-    print("engine.forward  %.3f ms" % t(lambda: eng.forward(mel, mode)))
+    print("engine.forward  %.3f ms (pipelined halves)" % t(lambda: eng.forward(mel, mode)))
+    os.environ["HFG_PIPELINE"] = "0"
+    print("engine.forward  %.3f ms (HFG_PIPELINE=0: one synchronous call)" % t(lambda: eng.forward(mel, mode)))
+    del os.environ["HFG_PIPELINE"]
+    h = B // 2
+    mel_h = mel_dev[:h].contiguous()
+    out_h = torch.empty(h, T * eng.hop, device="cuda")
+    print("device fwd B/2  %.3f ms" % t(lambda: (eng.forward_ptr(mel_h.data_ptr(), h, T, out_h.data_ptr(), mode, mel_on_device=True, wave_on_device=True, sync=False), eng.sync())))
+    print("2 halves, each synchronous, pinned   %.3f ms" % t(lambda: (eng.forward_ptr(pin_in[:h].data_ptr(), h, T, out_pin[:h].data_ptr(), mode),
+                                                                     eng.forward_ptr(pin_in[h:].data_ptr(), B - h, T, out_pin[h:].data_ptr(), mode))))
+    print("2 halves, NO_SYNC + one sync, pinned %.3f ms" % t(lambda: (eng.forward_ptr(pin_in[:h].data_ptr(), h, T, out_pin[:h].data_ptr(), mode, sync=False),
+                                                                     eng.forward_ptr(pin_in[h:].data_ptr(), B - h, T, out_pin[h:].data_ptr(), mode, sync=False),
+                                                                     eng.sync())))
+    print("1 whole, NO_SYNC + sync, pinned      %.3f ms" % t(lambda: (eng.forward_ptr(pin_in.data_ptr(), B, T, out_pin.data_ptr(), mode, sync=False), eng.sync())))
     out_np = np.empty((B, T * eng.hop), np.float32)
     print("pageable fwd    %.3f ms" % t(lambda: eng.forward_ptr(mel.ctypes.data, B, T, out_np.ctypes.data, mode)))
     s = torch.cuda.Stream()

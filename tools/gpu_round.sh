@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: GPU tests, smoke, per-layer times, bench, ncu launch list, ncu full capture of selected layers.
 # Usage (from the repo root on the GPU box): bash tools/gpu_round.sh [tag]
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L > $OUT/smi.txt
