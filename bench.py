@@ -415,9 +415,15 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this engine has no CPU path)")
     torch.cuda.set_device(local_rank)
+    affinity = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # one process per GPU: run on (and allocate page-locked staging from) the GPU's own NUMA node
+        from iris_tts_b200 import numa
+
+        if os.environ.get("HFG_BIND_NUMA", "1") != "0":
+            affinity = numa.bind_process_to_gpu(local_rank)
 
     def barrier():
         if world > 1:
@@ -610,7 +616,8 @@ def run_ours(args):
         "config": {"workload": f"HiFiGAN V1 random-init (seed 0) via infer_hifigan path, {B} x {T}-frame (10 s) mels per GPU, "
                                f"{args.precision}", "batch_per_gpu": B, "frames": T, "global_batch": B * world, "sharding": f"batch x{world}, no collective",
                    "l2": "no flush: each step streams ~3 GB of stage activations (452 MB per tensor) >> 126 MB L2",
-                   "timed_path": "production: one CUDA graph per forward, programmatic dependent launch, no events inside the timed region"},
+                   "timed_path": "production: one CUDA graph per forward, programmatic dependent launch, no events inside the timed region",
+                   "rank0_cpu_affinity": (f"{len(affinity)} CPUs local to the GPU (NVML)" if affinity else "unchanged")},
         "clocks": clocks,
         "per_rank_ms": {"min": min(ms_all) / args.steps, "median": statistics.median(ms_all) / args.steps, "max": max(ms_all) / args.steps,
                         "all": [m / args.steps for m in ms_all],

@@ -232,7 +232,10 @@ class Engine:
             # torch's caching host allocator hands the same page-locked block back once the previous result array is dropped:
             # no cudaHostAlloc per call in steady state
             out_t = torch.empty((B, T * self.hop), dtype=torch.float32, pin_memory=True)
-            if keep_taps or B < 4 or B * T < 4000 or os.environ.get("HFG_PIPELINE", "1") == "0":
+            # HFG_PIPELINE=1 splits the batch into two halves enqueued without waiting (below).  OFF by default: measured on B200
+            # (profiles/r02_e2e_breakdown.md) two half-batch plans cost 0.6-0.7 ms more on the device than one whole-batch plan at
+            # 16 x 862 frames, which is more than the 0.3-0.5 ms of copies and staging the overlap hides.
+            if keep_taps or B < 4 or B * T < 4000 or os.environ.get("HFG_PIPELINE", "0") != "1":
                 np.copyto(stage.numpy(), mel, casting="unsafe")
                 self.forward_ptr(stage.data_ptr(), B, T, out_t.data_ptr(), precision, keep_taps=keep_taps)
                 return out_t.numpy()

@@ -53,6 +53,8 @@ def build_parser() -> argparse.ArgumentParser:
     src = p.add_mutually_exclusive_group(required=True)
     src.add_argument("--mel", type=str, help=".npy mel-spectrogram [n_mels, T] or [B, n_mels, T] (log magnitudes)")
     src.add_argument("--synthetic_frames", type=int, help="use a seeded synthetic mel of this many frames instead of a file")
+    src.add_argument("--audio_wav", type=str, help="copy-synthesis (demo_vocoder.py:28-65): 16-bit mono WAV -> log-mel on the GPU "
+                                                   "(compute_mel_spectrogram, src/iris/data.py:25-67) -> vocoder")
     p.add_argument("--output_wav", type=str, default="outputs/sample.wav")
     p.add_argument("--n_mels", type=int, default=80)
     p.add_argument("--sample_rate", type=int, default=22050)
@@ -68,6 +70,16 @@ def build_parser() -> argparse.ArgumentParser:
 def load_mel(args) -> np.ndarray:
     if args.mel:
         mel = np.load(args.mel)
+    elif args.audio_wav:
+        from iris_tts_b200.mel import compute_mel_spectrogram
+
+        with wave.open(args.audio_wav, "rb") as w:
+            if w.getsampwidth() != 2 or w.getnchannels() != 1:
+                raise ValueError("--audio_wav expects 16-bit mono PCM")
+            if w.getframerate() != args.sample_rate:
+                raise ValueError(f"--audio_wav is {w.getframerate()} Hz, expected --sample_rate {args.sample_rate} (no resampler here)")
+            audio = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768.0
+        mel = compute_mel_spectrogram(audio, sample_rate=args.sample_rate, hop_length=args.hop_length, n_mels=args.n_mels)
     else:
         rng = np.random.default_rng(args.seed)
         mel = (rng.standard_normal((args.n_mels, args.synthetic_frames)) * 2.0 - 5.0).astype(np.float32)

@@ -189,3 +189,12 @@ def test_ragged_batch_scheme_is_exact_against_per_utterance_forwards():
     assert np.abs(bad[0] - O.infer(sd, mels[0][None], O.V2)[0]).max() > 1e-4
     with pytest.raises(ValueError):
         synthesize_variable(vocoder, [np.zeros((1, 80, 5), np.float32)])
+
+
+def test_numa_binding_is_a_no_op_without_nvml_or_gpu():
+    from iris_tts_b200 import numa
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert numa.gpu_local_cpus(0) is None and numa.bind_process_to_gpu(0) is None
+    assert numa.bind_process_to_gpu(10 ** 6) is None          # no such GPU
+    assert os.sched_getaffinity(0) == before
