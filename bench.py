@@ -360,6 +360,31 @@ def measure_tf32_peak(seconds=1.5):
         return None
 
 
+def logmel_leg(batch, samples, peaks, reps=20):
+    """the log-mel front-end kernel (hfg_logmel_*, csrc/kernels_mel.cu) on `batch` waveforms of `samples` samples,
+    device-resident in and out; HBM-bound: algorithmic bytes = 4 B per audio sample read + the [B, 80, T] mel written."""
+    import torch
+
+    from iris_tts_b200.mel import LogMel
+
+    fe = LogMel()
+    audio = torch.randn(batch, samples, device="cuda") * 0.1
+    T = fe.frames(samples)
+    out = torch.empty(batch, 80, T, device="cuda")
+    for _ in range(3):
+        fe.forward_ptr(audio.data_ptr(), batch, samples, out.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fe.forward_ptr(audio.data_ptr(), batch, samples, out.data_ptr())     # each call synchronises its stream
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    nbytes = batch * samples * 4 + out.numel() * 4
+    fe.close()
+    return {"workload": f"log-mel of {batch} x {samples} samples (n_fft 1024, hop 256, 80 mels), device-resident, wall clock per synchronous call",
+            "ms": ms, "value": batch * samples / (ms * 1e-3), "unit": "audio samples/s", "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9,
+            "hbm_peak_gbs": peaks["gbs"], "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["gbs"], "frames": T}
+
+
 def longform_leg(model, precision, world, rank, reps=5):
     """BASELINE config 4: one 120 s mel (10,336 frames).  N > 1: chunks of T/N frames + halo per rank, ONE NCCL gather to rank 0
     (iris_tts_b200.sharding.synthesize_longform); N = 1: the unchunked forward.  Device-timed, max over ranks."""
@@ -505,6 +530,7 @@ def run_ours(args):
     longform = None
     strong = None
     tf32_peak = None
+    logmel = None
     if not args.no_secondary:
         # the single-pass tensor-core modes on the headline workload (BASELINE config 3's mode), reported separately
         for mode in ("bf16", "fp16"):
@@ -567,6 +593,7 @@ def run_ours(args):
                 del mel_b, out_b
                 e2.close()
             tf32_peak = measure_tf32_peak()
+            logmel = logmel_leg(B, T * hop, peaks)
         else:
             # BASELINE config 3 at N > 1: a FIXED global batch of 64 utterances sharded over the N GPUs (strong scaling)
             from iris_tts_b200 import sharding
@@ -652,6 +679,8 @@ def run_ours(args):
         line["strong_scaling_b64"] = strong
     if longform:
         line["longform_120s"] = longform
+    if logmel:
+        line["logmel_frontend"] = logmel
     if world == 1 and not args.no_cpu_baseline:
         gen = CpuGenerator()
         r = gen.time(1, T, 3, 2)
