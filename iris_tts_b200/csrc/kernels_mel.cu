@@ -7,10 +7,11 @@
 // n_fft/2 ZEROS on both sides (pad_mode='constant'), T = 1 + N / hop frames, |rfft|, Slaney mel filterbank with
 // area normalisation (oracle/logmel_oracle.py restates each function and is what the -m gpu tests compare against).
 //
-// One CTA transforms kFramesPerCta consecutive frames of one utterance: windowed frame -> shared memory (bit-reversed),
-// radix-2 FFT in shared memory (fp32, twiddles from a table computed in fp64 on the host), magnitudes of the n_fft/2+1
-// bins, sparse triangular mel filters (each band touches a contiguous run of bins), log(max(., clip)), and the frames
-// of a CTA leave as runs of kFramesPerCta consecutive floats per mel band.  The op is 0.3 % of the vocoder's FLOPs and is
+// One CTA transforms kFramesPerCta consecutive frames of one utterance, two at a time (two real frames ride one complex
+// FFT): windowed frames -> shared memory (bit-reversed), radix-2 FFT in shared memory (fp32, twiddles from a table computed
+// in fp64 on the host), the two spectra separated by conjugate symmetry, magnitudes of the n_fft/2+1 bins, sparse
+// triangular mel filters (a warp per band, lanes over its contiguous run of bins), log(max(., clip)), and the frames of a
+// CTA leave as runs of kFramesPerCta consecutive floats per mel band.  The op is 0.3 % of the vocoder's FLOPs and is
 // bound by reading 4 bytes per sample once (frames overlap 4x: the re-reads hit L2) -- CUDA-core fp32 is the right tool.
 #include <math.h>
 #include <string.h>
@@ -48,25 +49,31 @@ __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
     float* im = re + a.n_fft;                 // [n_fft]
     float2* tw = reinterpret_cast<float2*>(im + a.n_fft);   // [n_fft/2]
     float* win = reinterpret_cast<float*>(tw + a.n_fft / 2);   // [n_fft]
-    float* mel_s = win + a.n_fft;             // [n_mels][kFramesPerCta]
-    const int tid = threadIdx.x;
+    const int nbins = a.n_fft / 2 + 1;
+    float* mag_a = win + a.n_fft;             // [nbins]  |X| of the pair's first frame
+    float* mag_b = mag_a + nbins;             // [nbins]  ... second frame
+    float* mel_s = mag_b + nbins;             // [n_mels][kFramesPerCta]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kFramesPerCta;
     const float* x = a.audio + (size_t)b * a.N;
     for (int i = tid; i < a.n_fft / 2; i += kMelThreads) tw[i] = a.twiddle[i];
     for (int i = tid; i < a.n_fft; i += kMelThreads) win[i] = a.window[i];
-    const int nbins = a.n_fft / 2 + 1;
-    for (int f = 0; f < kFramesPerCta; ++f) {
-        const int t = t0 + f;
-        if (t >= a.T) break;                  // uniform across the CTA
-        __syncthreads();                      // tables loaded / previous frame's magnitudes consumed
-        const int s0 = t * a.hop - a.n_fft / 2;
+    // Two real frames per complex FFT: z = x_a + i x_b, and X_a[k] = (Z[k] + conj Z[N-k]) / 2, X_b[k] = (Z[k] - conj Z[N-k]) / 2i.
+    for (int f = 0; f < kFramesPerCta; f += 2) {
+        const int ta = t0 + f, tb = ta + 1;
+        if (ta >= a.T) break;                 // uniform across the CTA
+        const bool has_b = tb < a.T;
+        __syncthreads();                      // tables loaded / previous pair's magnitudes consumed
+        const int sa = ta * a.hop - a.n_fft / 2, sb = sa + a.hop;
         for (int i = tid; i < a.n_fft; i += kMelThreads) {
-            const int s = s0 + i;
-            const float v = (s >= 0 && s < a.N) ? __ldg(x + s) * win[i] : 0.f;
+            const int ia = sa + i, ib = sb + i;
+            const float w = win[i];
+            const float va = (ia >= 0 && ia < a.N) ? __ldg(x + ia) * w : 0.f;
+            const float vb = (has_b && ib >= 0 && ib < a.N) ? __ldg(x + ib) * w : 0.f;
             const int j = (int)(__brev((unsigned)i) >> (32 - a.log2n));
-            re[j] = v;
-            im[j] = 0.f;
+            re[j] = va;
+            im[j] = vb;
         }
         for (int st = 1; st <= a.log2n; ++st) {
             __syncthreads();
@@ -86,14 +93,34 @@ __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
             }
         }
         __syncthreads();
-        for (int i = tid; i < nbins; i += kMelThreads) re[i] = sqrtf(re[i] * re[i] + im[i] * im[i]);   // |X_k| in place (bin i only reads itself)
+        for (int k = tid; k < nbins; k += kMelThreads) {
+            const int nk = (a.n_fft - k) & (a.n_fft - 1);
+            const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+            const float ar = 0.5f * (zr + yr), ai = 0.5f * (zi - yi);      // X_a[k]
+            const float br = 0.5f * (zi + yi), bi = -0.5f * (zr - yr);     // X_b[k]
+            mag_a[k] = sqrtf(ar * ar + ai * ai);
+            mag_b[k] = sqrtf(br * br + bi * bi);
+        }
         __syncthreads();
-        for (int m = tid; m < a.n_mels; m += kMelThreads) {
+        // one warp per mel band, lanes over the band's bins (a contiguous run), both frames of the pair at once
+        for (int m = warp; m < a.n_mels; m += kMelThreads / 32) {
             const int s = a.band_start[m], c = a.band_count[m];
             const float* w = a.weights + a.band_off[m];
-            float acc = 0.f;
-            for (int i = 0; i < c; ++i) acc = fmaf(__ldg(w + i), re[s + i], acc);
-            mel_s[m * kFramesPerCta + f] = a.log_output ? logf(fmaxf(acc, a.clip)) : acc;
+            float acc_a = 0.f, acc_b = 0.f;
+            for (int i = lane; i < c; i += 32) {
+                const float wi = __ldg(w + i);
+                acc_a = fmaf(wi, mag_a[s + i], acc_a);
+                acc_b = fmaf(wi, mag_b[s + i], acc_b);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                acc_a += __shfl_xor_sync(0xffffffffu, acc_a, d);
+                acc_b += __shfl_xor_sync(0xffffffffu, acc_b, d);
+            }
+            if (lane == 0) {
+                mel_s[m * kFramesPerCta + f] = a.log_output ? logf(fmaxf(acc_a, a.clip)) : acc_a;
+                mel_s[m * kFramesPerCta + f + 1] = a.log_output ? logf(fmaxf(acc_b, a.clip)) : acc_b;
+            }
         }
     }
     __syncthreads();
@@ -215,7 +242,7 @@ int hfg_logmel_create(const hfg_logmel_config* cfg, int device, hfg_logmel** out
     MCK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     MCK(cudaMemcpy(h->d_band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice));
     MCK(cudaMemcpy(h->d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice));
-    h->smem = (size_t)(2 * n + n + n + c.n_mels * kFramesPerCta) * sizeof(float);
+    h->smem = (size_t)(2 * n + n + n + 2 * nbins + c.n_mels * kFramesPerCta) * sizeof(float);
     if (h->smem > 48 * 1024) MCK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     *out = h.release();
     return HFG_OK;

@@ -1,0 +1,14 @@
+import sys, time
+sys.path.insert(0, '.')
+import torch
+from iris_tts_b200.mel import LogMel
+for B, N in ((16, 220672), (1, 220672), (64, 220672)):
+    fe = LogMel()
+    audio = torch.randn(B, N, device="cuda") * 0.1
+    T = fe.frames(N)
+    out = torch.empty(B, 80, T, device="cuda")
+    for _ in range(3): fe.forward_ptr(audio.data_ptr(), B, N, out.data_ptr())
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(20): fe.forward_ptr(audio.data_ptr(), B, N, out.data_ptr())
+    ms = 1e3 * (time.perf_counter() - t0) / 20
+    print(B, N, f"{ms:.4f} ms", f"{(B*N*4 + out.numel()*4)/ms/1e6:.1f} GB/s algorithmic")
