@@ -385,6 +385,40 @@ def logmel_leg(batch, samples, peaks, reps=20):
             "hbm_peak_gbs": peaks["gbs"], "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["gbs"], "frames": T}
 
 
+def ragged_leg(voc, max_frames, n_utt=32, reps=3):
+    """32 utterances of 32 DISTINCT lengths (300 .. max_frames frames) end to end (numpy in, numpy out) in the
+    bf16 mode: exact length-bucketed batching (iris_tts_b200.batching.synthesize_variable: a padded body pass per bucket + one
+    tail pass) against the reference's only option, one batch-1 call per utterance.  Both produce the same bits."""
+    import numpy as np
+
+    from iris_tts_b200.batching import synthesize_variable
+
+    old = voc.model.precision
+    voc.model.precision = "bf16"
+    rng = np.random.default_rng(7)
+    lengths = sorted(set(int(x) for x in np.linspace(300, max_frames, n_utt)))
+    mels = [rng.standard_normal((80, t)).astype(np.float32) for t in lengths]
+    stats = {}
+    a = synthesize_variable(voc, mels, stats=stats, length_quantum=64)      # builds the plans
+    b = [voc(m) for m in mels]
+    same = all(np.array_equal(x, y) for x, y in zip(a, b))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        synthesize_variable(voc, mels, length_quantum=64)
+    ms_b = 1e3 * (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for m in mels:
+            voc(m)
+    ms_u = 1e3 * (time.perf_counter() - t0) / reps
+    voc.model.precision = old
+    samples = sum(lengths) * 256
+    return {"workload": f"{len(lengths)} utterances, {len(lengths)} distinct lengths {lengths[0]}..{lengths[-1]} frames, bf16, numpy in -> numpy out",
+            "bucketed_ms": ms_b, "bucketed_value": samples / (ms_b * 1e-3), "per_utterance_calls_ms": ms_u,
+            "per_utterance_value": samples / (ms_u * 1e-3), "unit": "samples/s", "speedup": ms_u / ms_b, "dense_calls": stats["calls"],
+            "frames_real": stats["frames_real"], "frames_run": stats["frames_run"], "bit_identical_to_per_utterance": bool(same)}
+
+
 def longform_leg(model, precision, world, rank, reps=5):
     """BASELINE config 4: one 120 s mel (10,336 frames).  N > 1: chunks of T/N frames + halo per rank, ONE NCCL gather to rank 0
     (iris_tts_b200.sharding.synthesize_longform); N = 1: the unchunked forward.  Device-timed, max over ranks."""
@@ -531,6 +565,7 @@ def run_ours(args):
     strong = None
     tf32_peak = None
     logmel = None
+    ragged = None
     if not args.no_secondary:
         # the single-pass tensor-core modes on the headline workload (BASELINE config 3's mode), reported separately
         for mode in ("bf16", "fp16"):
@@ -594,6 +629,8 @@ def run_ours(args):
                 e2.close()
             tf32_peak = measure_tf32_peak()
             logmel = logmel_leg(B, T * hop, peaks)
+            ragged = ragged_leg(voc, T)
+            voc.model.precision = args.precision
         else:
             # BASELINE config 3 at N > 1: a FIXED global batch of 64 utterances sharded over the N GPUs (strong scaling)
             from iris_tts_b200 import sharding
@@ -681,6 +718,8 @@ def run_ours(args):
         line["longform_120s"] = longform
     if logmel:
         line["logmel_frontend"] = logmel
+    if ragged:
+        line["ragged_batch"] = ragged
     if world == 1 and not args.no_cpu_baseline:
         gen = CpuGenerator()
         r = gen.time(1, T, 3, 2)

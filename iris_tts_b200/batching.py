@@ -53,11 +53,13 @@ def length_buckets(lengths: Sequence[int], max_pad: float = 0.15, max_batch: Opt
 
 def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Sequence[np.ndarray], hop: int = 256,
                         halo: int = HALO_FRAMES, max_pad: float = 0.15, max_batch: Optional[int] = None,
-                        stats: Optional[dict] = None) -> List[np.ndarray]:
+                        stats: Optional[dict] = None, length_quantum: int = 1) -> List[np.ndarray]:
     """``mels``: list of [n_mels, T_i] arrays -> list of [T_i * hop] float32 waveforms (same order), each equal to what
     ``vocoder(mel_i[None])[0]`` returns.  ``vocoder`` maps [B, n_mels, T] -> [B, T * hop] (e.g. ``get_pretrained_hifigan(...)``);
     ``halo`` must cover the generator's receptive field (``sharding.halo_frames(config)``).  ``stats`` (optional dict) receives
-    the number of dense calls and the padded / real frame counts."""
+    the number of dense calls and the padded / real frame counts.  ``length_quantum`` > 1 rounds every bucket's padded length up
+    to a multiple of it: a serving loop then meets a handful of (batch, frames) shapes again and again, and the engine's per-shape
+    launch plans and CUDA graphs are reused instead of rebuilt (the padding is exact for the same reason the bucket padding is)."""
     for m in mels:
         if m.ndim != 2:
             raise ValueError(f"each mel must be [n_mels, T], got {m.shape}")
@@ -90,6 +92,8 @@ def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Seque
         for bucket in length_buckets([lengths[i] for i in long_idx], max_pad, max_batch):
             ids = [long_idx[j] for j in bucket]
             tb = max(lengths[i] for i in ids)
+            if length_quantum > 1:
+                tb = -(-tb // length_quantum) * length_quantum
             batch = np.zeros((len(ids), n_mels, tb), dtype=np.float32)
             for j, i in enumerate(ids):
                 batch[j, :, : lengths[i]] = mels[i]

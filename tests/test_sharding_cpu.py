@@ -184,6 +184,12 @@ def test_ragged_batch_scheme_is_exact_against_per_utterance_forwards():
         assert o.shape == (t * 256,) and o.dtype == np.float32
         if t:
             np.testing.assert_allclose(o, O.infer(sd, m[None], O.V2)[0], atol=2e-6)
+    # padded lengths quantised to multiples of 64 frames (plan reuse in a serving loop): still exact
+    calls.clear()
+    outs_q = synthesize_variable(vocoder, mels, length_quantum=64)
+    assert all(shape[2] % 64 == 0 for shape in calls if shape[2] > 32 and shape[2] != 2 * 16)
+    for a, b_ in zip(outs, outs_q):
+        np.testing.assert_allclose(a, b_, atol=2e-6)
     # a halo smaller than the receptive field is NOT exact (the scheme depends on it)
     bad = synthesize_variable(vocoder, mels[:1], halo=4)
     assert np.abs(bad[0] - O.infer(sd, mels[0][None], O.V2)[0]).max() > 1e-4
