@@ -5,7 +5,7 @@ Runs the generator forward in float64 with the roundings a mode applies to (a) t
 and (b) the residual stream (what `x = xt + x`, hifigan_pretrained.py:70, is rebuilt from), and reports max-abs waveform error
 against the unrounded float64 forward.  Used to choose between schemes before spending GPU time (DESIGN.md "precision schemes").
 
-    python tools/emulate_rounding.py [--frames 128] [--realistic] [--cfg v1]
+    python tests/dev/emulate_rounding.py [--frames 128] [--realistic] [--cfg v1]
 """
 from __future__ import annotations
 
@@ -16,8 +16,8 @@ import sys
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import hifigan_oracle as O  # noqa: E402  (test infrastructure; this tool is not product code)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import hifigan_oracle as O  # noqa: E402  (this file lives under tests/: it may use the oracle)
 
 
 def rnd(x, fmt):

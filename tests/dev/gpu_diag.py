@@ -4,8 +4,8 @@ Development tool (not a test, not the product): prints a table instead of assert
 mode in its own subprocess so a trapped kernel in one mode cannot poison the CUDA context of the
 next.  Uses oracle/ as the checker, like tests/ do.
 
-    python tools/gpu_diag.py                 # all modes
-    python tools/gpu_diag.py --one bf16x3    # one mode, in-process
+    python tests/dev/gpu_diag.py                 # all modes
+    python tests/dev/gpu_diag.py --one bf16x3    # one mode, in-process
 """
 import argparse
 import json
@@ -15,7 +15,7 @@ import sys
 import time
 import zlib
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402

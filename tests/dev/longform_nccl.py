@@ -1,7 +1,7 @@
 """BASELINE config 4 on real GPUs: one long mel split along time across the ranks (16-frame halo), ONE NCCL gather.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
-        tools/longform_nccl.py [--frames 10336] [--precision bf16x3]
+        tests/dev/longform_nccl.py [--frames 10336] [--precision bf16x3]
 
 Rank 0 checks the stitched waveform against the unchunked forward on its own GPU (<= 2e-5) and, for the first
 4 s, against the CPU oracle (<= 1e-3), and prints one JSON line with device-timed (max over ranks) throughput.
@@ -11,7 +11,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -1,16 +1,16 @@
 """A tiny forward in every mode for compute-sanitizer runs (tools: memcheck, racecheck, synccheck, initcheck).
-    compute-sanitizer --tool memcheck python tools/sanitize_probe.py
+    compute-sanitizer --tool memcheck python tests/dev/sanitize_probe.py
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 
 from iris_tts_b200 import Engine
 from iris_tts_b200.engine import V1, V2
-from oracle import hifigan_oracle as O   # test infrastructure: this probe is a test driver, not product code
+from oracle import hifigan_oracle as O   # this file lives under tests/: it may use the oracle
 
 for cfg, ocfg, shapes in ((V1, O.V1, ((1, 9), (2, 33))), (V2, O.V2, ((3, 17),))):
     sd = O.random_state_dict(ocfg, seed=0, loud=True)

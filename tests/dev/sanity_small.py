@@ -1,8 +1,8 @@
-"""Tiny forward in every mode and config (for compute-sanitizer memcheck runs): python tools/sanity_small.py"""
+"""Tiny forward in every mode and config (for compute-sanitizer memcheck runs): python tests/dev/sanity_small.py"""
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

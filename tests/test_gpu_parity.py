@@ -7,7 +7,7 @@ tcgen05) max-abs waveform error <= 1e-3 -- on the LOUD weight set too (output st
 shows the default random-init output is too quiet to discriminate).  The single-pass tensor-core modes are
 reported separately, with the tolerance stated RELATIVE to the output's std (max-abs error of a tanh-bounded
 signal scales with how loud the signal is): ``bf16`` <= 0.15 std (operand rounding at 2^-9; float64 emulation of
-exactly that rounding, tools/emulate_rounding.py, gives 0.064 - 0.096 std on the loud goldens), ``fp16`` <= 0.025 std
+exactly that rounding, tests/dev/emulate_rounding.py, gives 0.064 - 0.096 std on the loud goldens), ``fp16`` <= 0.025 std
 (rounding at 2^-12, TF32-class; emulation 0.009 - 0.010 std); both <= 1e-3 absolute at default init.
 """
 import json
