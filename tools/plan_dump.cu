@@ -1,6 +1,7 @@
 // Offline view of the conv_umma2 planner's choices (no GPU needed: the plan is printed before the tensor maps are encoded).
 //   nvcc -o /tmp/plan_dump tools/plan_dump.cu iris_tts_b200/build/*.o -Iiris_tts_b200/csrc && HFG_U2_VERBOSE=1 /tmp/plan_dump
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "hfg_internal.h"
@@ -8,7 +9,7 @@
 using namespace hfg;
 
 int main() {
-    const int B = 16;
+    const int B = getenv("PD_B") ? atoi(getenv("PD_B")) : 16;
     struct Case { int C, k, d, L; } cases[] = {{256, 3, 1, 6896}, {256, 11, 5, 6896}, {128, 3, 1, 55168}, {128, 7, 3, 55168}, {128, 11, 5, 55168},
                                                {64, 3, 1, 110336}, {64, 7, 3, 110336}, {64, 11, 5, 110336}, {32, 3, 1, 220672}, {32, 11, 5, 220672}};
     for (int planes = 1; planes <= 2; ++planes)
