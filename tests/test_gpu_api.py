@@ -161,3 +161,80 @@ def test_cli_end_to_end(loud_ckpt, tmp_path):
         pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32767.0
     ref = O.infer(O.random_state_dict(O.V1, seed=0, loud=True), mel)
     assert pcm.shape == ref.shape and np.abs(pcm - ref).max() <= 1e-3 + 1.0 / 32767.0
+
+
+def test_pickled_reference_model_checkpoint_runs_on_the_engine():
+    """A checkpoint that holds a whole model object pickled by the REFERENCE (hifigan_pretrained.py:168-171), non-default
+    architecture: loaded through HiFiGANGenerator and run on the GPU, against the output the reference itself produced."""
+    import iris.hifigan_pretrained as hp
+    gen = hp.HiFiGANGenerator(os.path.join(GOLD, "pickled_model.ckpt"))
+    z = np.load(os.path.join(GOLD, "pickled_model_expected.npz"))
+    out = gen(z["mel"])
+    want = z["out"][:, 0]
+    assert out.shape == want.shape and out.dtype == np.float32
+    assert np.abs(out - want).max() <= 1e-3
+
+
+def test_keras_weights_h5_and_keras_archive_through_the_keras_surface(tmp_path):
+    """create_vocoder(weights_path='x.weights.h5') (demo_vocoder.py:83; reference vocoder.py:161-170): the HDF5 file is read by
+    the pure-Python reader, the kernels are permuted to the torch layout, and the waveform equals the oracle's on those weights."""
+    import zipfile
+
+    import _h5write
+    import iris.vocoder as kv
+    from test_h5lite_cpu import _keras_tree
+    src = kv.HiFiGANGenerator(seed=11)
+    rng = np.random.default_rng(0)
+    for k in src.weights:
+        if k.endswith("/bias"):
+            src.weights[k] = (rng.standard_normal(src.weights[k].shape) * 0.05).astype(np.float32)
+    p = tmp_path / "gen.weights.h5"
+    _h5write.write_h5(p, _keras_tree(src, "layers"))
+    voc = kv.create_vocoder(weights_path=str(p))
+    sd = {}
+    for name, *_ in src.config.layer_specs():
+        sd[f"{name}.weight"] = torch.from_numpy(np.ascontiguousarray(np.transpose(src.weights[f"{name}/kernel"], (2, 1, 0))))
+        sd[f"{name}.bias"] = torch.from_numpy(src.weights[f"{name}/bias"])
+    mel = O.synthetic_mel(2, 21, seed=9)
+    ref = O.infer(sd, mel)
+    out = voc.infer(mel)
+    assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-3
+    z = tmp_path / "gen.keras"
+    with zipfile.ZipFile(z, "w") as zf:
+        zf.write(p, "model.weights.h5")
+    np.testing.assert_array_equal(kv.create_vocoder(weights_path=str(z)).infer(mel), out)
+
+
+def test_fp16_mode_saturates_instead_of_overflowing():
+    """HFG_PREC_FP16 stores activations with cvt.rn.satfinite: inputs that drive activations past 65504 give a finite waveform
+    (clipped arithmetic), never NaN; the bf16 mode, with fp32's exponent range, handles the same input without clipping."""
+    from iris_tts_b200 import Engine
+    from iris_tts_b200.engine import V2
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+    eng = Engine(V2, 0)
+    eng.load_state_dict(sd, strict=True)
+    eng.finalize()
+    mel = O.synthetic_mel(1, 12, seed=3) * 3.0e5
+    big = eng.forward(mel, precision="fp16")
+    assert np.isfinite(big).all() and np.abs(big).max() <= 1.0
+    ref = O.infer(sd, mel, O.V2)
+    assert np.abs(eng.forward(mel, precision="bf16x3") - ref).max() <= 1e-2          # saturated tanh output either way
+    eng.close()
+
+
+def test_cli_copy_synthesis_from_a_wav(loud_ckpt, tmp_path):
+    """--audio_wav: waveform -> log-mel on the GPU (src/iris/data.py:25-67) -> vocoder -> wav of the frame-aligned length
+    (demo_vocoder.py's copy-synthesis)."""
+    spec = importlib.util.spec_from_file_location("synthesize_cli", os.path.join(ROOT, "scripts", "synthesize.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    n = 22050
+    t = np.arange(n) / 22050.0
+    pcm = (0.3 * np.sin(2 * np.pi * 440.0 * t) * 32767).astype("<i2")
+    src = tmp_path / "in.wav"
+    with wave.open(str(src), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(22050); w.writeframes(pcm.tobytes())
+    out = tmp_path / "copy.wav"
+    assert cli.main(["--audio_wav", str(src), "--output_wav", str(out), "--checkpoint", str(loud_ckpt)]) == 0
+    with wave.open(str(out)) as w:
+        assert w.getframerate() == 22050 and w.getnframes() == (1 + n // 256) * 256
