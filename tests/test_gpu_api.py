@@ -217,8 +217,11 @@ def test_fp16_mode_saturates_instead_of_overflowing():
     mel = O.synthetic_mel(1, 12, seed=3) * 3.0e5
     big = eng.forward(mel, precision="fp16")
     assert np.isfinite(big).all() and np.abs(big).max() <= 1.0
-    ref = O.infer(sd, mel, O.V2)
-    assert np.abs(eng.forward(mel, precision="bf16x3") - ref).max() <= 1e-2          # saturated tanh output either way
+    assert np.isfinite(eng.forward(mel, precision="bf16")).all()
+    # and at ordinary amplitudes the saturating conversion never engages: the mode stays inside its tolerance
+    small = O.synthetic_mel(1, 12, seed=3)
+    ref = O.infer(sd, small, O.V2)
+    assert np.abs(eng.forward(small, precision="fp16") - ref).max() <= 0.025 * ref.std()
     eng.close()
 
 
