@@ -546,6 +546,30 @@ def run_ours(args):
     e2e_ms, e2e_all = timer.max_over_ranks(e2e_ms)
     e2e_value = samples_per_step * args.steps / (e2e_ms * 1e-3)
 
+    # what the host side of that call costs on THIS box (boxes of the pool differ: the same code has shown 1 ms and 7 ms of gap):
+    # raw page-locked copies of the step's buffers and the staging copy, each timed alone
+    pin_out = torch.empty((B, T * hop), dtype=torch.float32, pin_memory=True)
+    pin_in = torch.empty((B, 80, T), dtype=torch.float32, pin_memory=True)
+    cs = torch.cuda.Stream()
+    host_io = {}
+    with torch.cuda.stream(cs):
+        for name, fn, nbytes in (("d2h_gbs", lambda: pin_out.copy_(out_dev, non_blocking=True), pin_out.numel() * 4),
+                                 ("h2d_gbs", lambda: mel_dev.copy_(pin_in, non_blocking=True), pin_in.numel() * 4)):
+            fn()
+            cs.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(cs)
+            for _ in range(5):
+                fn()
+            c1.record(cs)
+            cs.synchronize()
+            host_io[name] = nbytes * 5 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    t0 = time.perf_counter()
+    for _ in range(5):
+        np.copyto(pin_in.numpy(), mel_host, casting="unsafe")
+    host_io["staging_copy_gbs"] = mel_host.nbytes * 5 / (time.perf_counter() - t0) / 1e9
+    del pin_out, pin_in
+
     # ---- per-launch records for the roofline: a separate profiled pass (events around every launch, no graph) ----
     prof_steps = max(1, min(args.steps, 5))
     ms_prof, _, recs = timer.run(mel_dev, out_dev, B, T, args.precision, prof_steps, 1, profile=True)
@@ -688,7 +712,7 @@ def run_ours(args):
                         "e2e_all": [m / args.steps for m in e2e_all]},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(B * 80 * T * 4),
                 "d2h_bytes_per_step": int(B * T * hop * 4), "api": "iris.hifigan_pretrained.HiFiGANGenerator.__call__(np.ndarray)",
-                "gap_vs_device": e2e_ms / ms - 1.0},
+                "gap_vs_device": e2e_ms / ms - 1.0, "host_io_rank0": host_io},
         "gpu_launches": int(launches),
         "roofline": dom,
         "roofline_other_kernels": other_rooflines(recs, peaks, args.precision, dom),
