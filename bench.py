@@ -533,6 +533,9 @@ def run_ours(args):
     barrier()
     torch.cuda.synchronize()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler2 = ClockSampler(local_rank) if rank == 0 else None
+    if sampler2:
+        sampler2.start()
     s0.record(stream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -540,6 +543,7 @@ def run_ours(args):
     wall_ms = 1e3 * (time.perf_counter() - t0)
     s1.record(stream)
     torch.cuda.synchronize()
+    e2e_clocks = sampler2.stop() if sampler2 else None
     barrier()
     e2e_ms = max(s0.elapsed_time(s1), wall_ms)
     assert wav.shape == (B, T * hop) and wav.dtype == np.float32
@@ -712,7 +716,7 @@ def run_ours(args):
                         "e2e_all": [m / args.steps for m in e2e_all]},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(B * 80 * T * 4),
                 "d2h_bytes_per_step": int(B * T * hop * 4), "api": "iris.hifigan_pretrained.HiFiGANGenerator.__call__(np.ndarray)",
-                "gap_vs_device": e2e_ms / ms - 1.0, "host_io_rank0": host_io},
+                "gap_vs_device": e2e_ms / ms - 1.0, "host_io_rank0": host_io, "clocks": e2e_clocks},
         "gpu_launches": int(launches),
         "roofline": dom,
         "roofline_other_kernels": other_rooflines(recs, peaks, args.precision, dom),
