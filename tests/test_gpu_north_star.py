@@ -273,3 +273,50 @@ def test_repeated_runs_are_bitwise_identical_under_varied_pipelines(mode):
             for k in ov:
                 del os.environ[k]
     assert runs == 200
+
+
+# ---------------------------------------------------------------------------
+# generator architectures nobody hand-picked
+# ---------------------------------------------------------------------------
+
+def _random_config(rng):
+    from iris_tts_b200.engine import GeneratorConfig
+    nu = int(rng.integers(2, 5))
+    rates = [int(rng.choice([2, 4, 8])) for _ in range(nu)]
+    while int(np.prod(rates)) > 512:
+        rates[int(np.argmax(rates))] //= 2
+    c_last = int(rng.choice([8, 16, 32, 64]))
+    c0 = c_last << nu
+    if c0 > 512:
+        c0, c_last = 512, 512 >> nu
+    nk = int(rng.integers(1, 4))
+    ks = [int(rng.choice([3, 5, 7, 9, 11])) for _ in range(nk)]
+    nd = int(rng.integers(1, 4))
+    dils = tuple(tuple(int(rng.integers(1, 7)) for _ in range(nd)) for _ in range(nk))
+    return GeneratorConfig(80, tuple(rates), tuple(2 * r for r in rates), c0, tuple(ks), dils)
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_architectures_match_the_oracle(seed):
+    """Ten seeded random generator configurations (2-4 upsamplers of rate 2/4/8, 1-3 ResBlock kernels of size 3-11, 1-3 dilations
+    of 1-6, 8-64 final channels): every arithmetic mode against the oracle on loud weights, at a ragged length.  Exercises planner
+    paths no named configuration reaches (single-branch MRF, one-dilation blocks, time-folded stages behind every rate mix)."""
+    from iris_tts_b200 import Engine
+    rng = np.random.default_rng(1000 + seed)
+    cfg = _random_config(rng)
+    ocfg = O.OracleConfig(cfg.in_channels, cfg.upsample_rates, cfg.upsample_kernel_sizes, cfg.upsample_initial_channel,
+                          cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes)
+    sd = O.random_state_dict(ocfg, seed=seed, loud=True)
+    eng = Engine(cfg, 0)
+    eng.load_state_dict(sd, strict=True)
+    eng.finalize()
+    for B, T in ((2, 37), (1, 130)):
+        mel = O.synthetic_mel(B, T, seed=seed * 10 + T)
+        ref = O.infer(sd, mel, ocfg)
+        for mode in ("fp32", "bf16x3", "fp16", "bf16"):
+            for _ in range(2):                      # direct launches, then the graph
+                out = eng.forward(mel, precision=mode)
+            assert out.shape == ref.shape
+            err = float(np.abs(out - ref).max())
+            assert err <= e2e_tol(mode, ref), f"{cfg} B={B} T={T} {mode}: {err:.3e} > {e2e_tol(mode, ref):.3e} (std {ref.std():.3f})"
+    eng.close()
