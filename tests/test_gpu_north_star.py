@@ -18,13 +18,13 @@ from test_gpu_parity import PAIR_RTOL, TC_MODES, _cfgs, _engine, _pair_ref, e2e_
 pytestmark = pytest.mark.gpu
 
 
-def _check_items(eng, sd, ocfg, mel, mode, items, label):
+def _check_items(eng, sd, ocfg, mel, mode, items, label, abs_tol=None):
     out = eng.forward(mel, precision=mode)
     assert out.shape == (mel.shape[0], mel.shape[2] * 256) and np.isfinite(out).all()
     for b in items:
         ref = O.infer(sd, mel[b:b + 1], ocfg)[0]
         err = float(np.abs(out[b] - ref).max())
-        tol = e2e_tol(mode, ref)
+        tol = abs_tol if abs_tol is not None else e2e_tol(mode, ref)
         print(f"[parity] {label} {mode} item {b}: max|err| {err:.3e} = {err / ref.std():.3e} std (tol {tol:.3e}, output std {ref.std():.4f})")
         assert err <= tol, f"{label} {mode} item {b}: {err:.3e} > {tol:.3e}"
     return out
@@ -37,7 +37,8 @@ def test_north_star_shape_b32_x_10s(mode, loud):
     three items against the oracle (a full-batch oracle pass would take minutes on the host)."""
     eng, sd = _engine("v1", loud=loud)
     mel = O.synthetic_mel(32, 862, seed=1234)
-    out = _check_items(eng, sd, O.V1, mel, mode, (0, 13, 31), f"v1 B=32 T=862 {'loud' if loud else 'default'}")
+    out = _check_items(eng, sd, O.V1, mel, mode, (0, 13, 31), f"v1 B=32 T=862 {'loud' if loud else 'default'}",
+                       abs_tol=None if loud else 1e-3)        # default init: the headline 1e-3, every mode
     if not loud:
         return
     # batch independence at this size: an item run alone reproduces its bits

@@ -5,8 +5,8 @@
 Tolerances (BASELINE.json north_star): fp32-class modes (``fp32`` CUDA-core FFMA and ``bf16x3`` split-bf16
 tcgen05) max-abs waveform error <= 1e-3 -- on the LOUD weight set too (output std 0.2; SURVEY.md section 7-1
 shows the default random-init output is too quiet to discriminate).  The single-pass tensor-core modes are
-reported separately, with the tolerance stated RELATIVE to the output's std (max-abs error of a tanh-bounded
-signal scales with how loud the signal is): ``bf16`` <= 0.15 std (operand rounding at 2^-9; float64 emulation of
+reported separately, with the tolerance stated RELATIVE to the output's RMS level (= its std for the zero-mean
+loud outputs; max-abs error of a tanh-bounded signal scales with how loud the signal is): ``bf16`` <= 0.15 std (operand rounding at 2^-9; float64 emulation of
 exactly that rounding, tests/dev/emulate_rounding.py, gives 0.064 - 0.096 std on the loud goldens), ``fp16`` <= 0.025 std
 (rounding at 2^-12, TF32-class; emulation 0.009 - 0.010 std); both <= 1e-3 absolute at default init.
 """
@@ -35,10 +35,12 @@ E2E_REL_STD = {"fp16": 0.025, "bf16": 0.15}
 
 
 def e2e_tol(mode, ref):
-    """Max-abs waveform tolerance of `mode` against reference output `ref` (never below the headline 1e-3)."""
+    """Max-abs waveform tolerance of `mode` against reference output `ref` (never below the headline 1e-3).  The single-pass modes'
+    tolerance scales with the signal's RMS level -- its std for the zero-mean outputs of the named configurations; a generator whose
+    output rides on a DC offset (random architectures) rounds relative to that level, not to the ripple on top of it."""
     if mode in E2E_ABS:
         return E2E_ABS[mode]
-    return max(1e-3, E2E_REL_STD[mode] * float(np.std(ref)))
+    return max(1e-3, E2E_REL_STD[mode] * float(np.sqrt(np.mean(np.square(ref, dtype=np.float64)))))
 
 
 def _cfgs(name):
