@@ -385,6 +385,34 @@ def logmel_leg(batch, samples, peaks, reps=20):
             "hbm_peak_gbs": peaks["gbs"], "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["gbs"], "frames": T}
 
 
+def griffin_lim_leg(frames, n_iter=60, reps=3):
+    """SURVEY 8(f) f3, the CLI's no-vocoder fallback (reference scripts/synthesize.py:174-194): Griffin-Lim, `n_iter` iterations on
+    one utterance of `frames` frames, host magnitudes in / host waveform out through hfg_griffin_lim (inverse STFT, envelope
+    normalisation and forward STFT + momentum phase update kernels, csrc/kernels_mel.cu).  Beside it the float64 oracle
+    (oracle/griffinlim_oracle.py, numpy FFTs) on 5 iterations, scaled to `n_iter`."""
+    import numpy as np
+
+    from iris_tts_b200.griffin_lim import griffin_lim
+    from oracle import griffinlim_oracle as G
+
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(256 * (frames - 1)) * 0.1
+    S = np.abs(G.stft(y))
+    ang = np.exp(2j * np.pi * rng.random(S.shape))
+    griffin_lim(S, n_iter=2, angles0=ang)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        wav = griffin_lim(S, n_iter=n_iter, angles0=ang)
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    G.griffinlim(S, ang, n_iter=5)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) * (n_iter + 1) / 6.0
+    inc = float(np.abs(np.abs(G.stft(wav.astype(np.float64))) - S).mean() / S.mean())
+    return {"workload": f"Griffin-Lim, {n_iter} iterations, 1 x {frames} frames (n_fft 1024, hop 256), numpy in / numpy out",
+            "ms": ms, "ms_per_iteration": ms / (n_iter + 1), "oracle_cpu_ms_scaled_from_5_iterations": cpu_ms,
+            "spectral_inconsistency": inc}
+
+
 def ragged_leg(voc, max_frames, n_utt=32, reps=3):
     """32 utterances of 32 DISTINCT lengths (300 .. max_frames frames) end to end (numpy in, numpy out) in the
     bf16 mode: exact length-bucketed batching (iris_tts_b200.batching.synthesize_variable: a padded body pass per bucket + one
@@ -597,6 +625,7 @@ def run_ours(args):
     strong = None
     tf32_peak = None
     logmel = None
+    glim = None
     ragged = None
     if not args.no_secondary:
         # the single-pass tensor-core modes on the headline workload (BASELINE config 3's mode), reported separately
@@ -662,6 +691,7 @@ def run_ours(args):
             tf32_peak = measure_tf32_peak()
             logmel = logmel_leg(B, T * hop, peaks)
             ragged = ragged_leg(voc, T)
+            glim = griffin_lim_leg(T)
             voc.model.precision = args.precision
         else:
             # BASELINE config 3 at N > 1: a FIXED global batch of 64 utterances sharded over the N GPUs (strong scaling)
@@ -750,6 +780,8 @@ def run_ours(args):
         line["longform_120s"] = longform
     if logmel:
         line["logmel_frontend"] = logmel
+    if glim:
+        line["griffin_lim_fallback"] = glim
     if ragged:
         line["ragged_batch"] = ragged
     if world == 1 and not args.no_cpu_baseline:

@@ -187,6 +187,13 @@ void hfg_logmel_destroy(hfg_logmel* h);
 int32_t hfg_logmel_frames(const hfg_logmel* h, int32_t n_samples);
 int hfg_logmel_forward(hfg_logmel* h, const float* audio, int32_t B, int32_t N, float* mel, uint32_t flags);
 
+/* Griffin-Lim, the reference's alternative vocoder: scripts/synthesize.py:193  librosa.griffinlim(S, n_iter=60, hop_length, win_length)
+ * (librosa 0.11.0: momentum 0.99, random initial phases, center=True) with the STFT geometry of the handle's configuration.
+ * mag [B][1 + n_fft/2][T] linear magnitudes (librosa layout), angles0 [B][T][1 + n_fft/2][2] initial unit phasors (cos, sin) -- drawn
+ * by the caller, so a result can be reproduced -- -> audio [B][hop_length * (T - 1)].  Host pointers. */
+int hfg_griffin_lim(hfg_logmel* h, const float* mag, const float* angles0, int32_t B, int32_t T, int32_t n_iter, float momentum,
+                    float* audio);
+
 #ifdef __cplusplus
 }
 #endif

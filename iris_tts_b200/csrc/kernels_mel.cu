@@ -43,6 +43,29 @@ struct MelArgs {
     int log_output;
 };
 
+// Radix-2 decimation-in-time stages on bit-reversed input in shared memory (forward transform, twiddles exp(-2 pi i k / n)).
+// Begins and ends with a CTA barrier.
+__device__ __forceinline__ void fft_stages(float* re, float* im, const float2* tw, int n_fft, int log2n, int tid) {
+    for (int st = 1; st <= log2n; ++st) {
+        __syncthreads();
+        const int half = 1 << (st - 1);
+        const int tstep = n_fft >> st;
+        for (int idx = tid; idx < n_fft / 2; idx += kMelThreads) {
+            const int k = idx & (half - 1);
+            const int i0 = ((idx >> (st - 1)) << st) + k;
+            const int i1 = i0 + half;
+            const float2 w = tw[k * tstep];
+            const float xr = re[i1], xi = im[i1];
+            const float tr = w.x * xr - w.y * xi;
+            const float ti = w.x * xi + w.y * xr;
+            const float ur = re[i0], ui = im[i0];
+            re[i0] = ur + tr; im[i0] = ui + ti;
+            re[i1] = ur - tr; im[i1] = ui - ti;
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* re = smem;                         // [n_fft]
@@ -75,24 +98,7 @@ __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
             re[j] = va;
             im[j] = vb;
         }
-        for (int st = 1; st <= a.log2n; ++st) {
-            __syncthreads();
-            const int half = 1 << (st - 1);
-            const int tstep = a.n_fft >> st;
-            for (int idx = tid; idx < a.n_fft / 2; idx += kMelThreads) {
-                const int k = idx & (half - 1);
-                const int i0 = ((idx >> (st - 1)) << st) + k;
-                const int i1 = i0 + half;
-                const float2 w = tw[k * tstep];
-                const float xr = re[i1], xi = im[i1];
-                const float tr = w.x * xr - w.y * xi;
-                const float ti = w.x * xi + w.y * xr;
-                const float ur = re[i0], ui = im[i0];
-                re[i0] = ur + tr; im[i0] = ui + ti;
-                re[i1] = ur - tr; im[i1] = ui - ti;
-            }
-        }
-        __syncthreads();
+        fft_stages(re, im, tw, a.n_fft, a.log2n, tid);
         for (int k = tid; k < nbins; k += kMelThreads) {
             const int nk = (a.n_fft - k) & (a.n_fft - 1);
             const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
@@ -128,6 +134,141 @@ __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
     for (int i = tid; i < a.n_mels * kFramesPerCta; i += kMelThreads) {
         const int m = i / kFramesPerCta, f = i - m * kFramesPerCta;
         if (f < nf) a.out[((size_t)b * a.n_mels + m) * a.T + t0 + f] = mel_s[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Griffin-Lim (the reference's alternative vocoder, scripts/synthesize.py:193 -> librosa.griffinlim; oracle/griffinlim_oracle.py)
+//   per iteration:  y = istft(S * angles) ;  X = stft(y) ;  angles = X - c * X_prev ;  angles /= |angles| + tiny ;  X_prev = X
+// Spectra live frame-major, [B][T][nbins] float2, so that a frame's bins are contiguous.
+// ---------------------------------------------------------------------------------------------------------------------
+struct GlArgs {
+    const float* mag;        // [B][T][nbins]   |S|
+    float2* angles;          // [B][T][nbins]   unit phasors
+    float2* prev;            // [B][T][nbins]   stft of the previous iteration
+    float* y_acc;            // [B][n_fft + hop*(T-1)]  overlap-add accumulator
+    float* y;                // [B][hop*(T-1)]
+    const float* wss;        // [n_fft + hop*(T-1)]  window sum-square
+    const float* window;
+    const float2* twiddle;
+    int T, n_fft, log2n, hop, N;   // N = hop*(T-1): samples of y
+    float mom;               // momentum / (1 + momentum), 0 in the first iteration
+};
+
+// y_acc += window * irfft(S * angles), two frames per complex FFT: Z = X_a + i X_b with both spectra Hermitian-extended, and
+// ifft(Z) = x_a + i x_b;  ifft(Z) = conj(fft(conj Z)) / n.
+__global__ void __launch_bounds__(kMelThreads) gl_istft_kernel(const GlArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* re = smem;
+    float* im = re + a.n_fft;
+    float2* tw = reinterpret_cast<float2*>(im + a.n_fft);
+    float* win = reinterpret_cast<float*>(tw + a.n_fft / 2);
+    float* ola = win + a.n_fft;               // [n_fft + (kFramesPerCta-1)*hop]  this CTA's overlap-add
+    const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kFramesPerCta;
+    const int nbins = a.n_fft / 2 + 1, half = a.n_fft / 2;
+    const int span = a.n_fft + (kFramesPerCta - 1) * a.hop;
+    for (int i = tid; i < half; i += kMelThreads) tw[i] = a.twiddle[i];
+    for (int i = tid; i < a.n_fft; i += kMelThreads) win[i] = a.window[i];
+    for (int i = tid; i < span; i += kMelThreads) ola[i] = 0.f;
+    const float inv_n = 1.0f / (float)a.n_fft;
+    for (int f = 0; f < kFramesPerCta; f += 2) {
+        const int ta = t0 + f, tb = ta + 1;
+        if (ta >= a.T) break;
+        const bool has_b = tb < a.T;
+        const size_t ba = ((size_t)b * a.T + ta) * nbins, bb = ba + nbins;
+        __syncthreads();
+        for (int k = tid; k < a.n_fft; k += kMelThreads) {
+            const int kk = k <= half ? k : a.n_fft - k;          // Hermitian extension: X[n-k] = conj X[k]
+            const float sgn = k <= half ? 1.f : -1.f;
+            const float2 ga = a.angles[ba + kk];
+            const float ma = a.mag[ba + kk];
+            float ar = ma * ga.x, ai = sgn * ma * ga.y;
+            float br = 0.f, bi = 0.f;
+            if (has_b) {
+                const float2 gb = a.angles[bb + kk];
+                const float mb = a.mag[bb + kk];
+                br = mb * gb.x; bi = sgn * mb * gb.y;
+            }
+            if (kk == 0 || kk == half) { ai = 0.f; bi = 0.f; }   // irfft ignores the imaginary part of the DC and Nyquist bins
+            // Z = X_a + i X_b ; load conj(Z) bit-reversed
+            const int j = (int)(__brev((unsigned)k) >> (32 - a.log2n));
+            re[j] = ar - bi;
+            im[j] = -(ai + br);
+        }
+        fft_stages(re, im, tw, a.n_fft, a.log2n, tid);
+        // ifft(Z) = conj(fft(conj Z)) / n:  x_a = re / n,  x_b = -im / n
+        for (int i = tid; i < a.n_fft; i += kMelThreads) {
+            const float w = win[i] * inv_n;
+            ola[f * a.hop + i] += re[i] * w;
+        }
+        __syncthreads();
+        if (has_b)
+            for (int i = tid; i < a.n_fft; i += kMelThreads) ola[(f + 1) * a.hop + i] -= im[i] * win[i] * inv_n;
+    }
+    __syncthreads();
+    const size_t ylen = (size_t)a.n_fft + (size_t)a.hop * (a.T - 1);
+    const int nf = min(kFramesPerCta, a.T - t0);
+    const int used = a.n_fft + (nf - 1) * a.hop;
+    for (int i = tid; i < used; i += kMelThreads) atomicAdd(a.y_acc + (size_t)b * ylen + (size_t)t0 * a.hop + i, ola[i]);
+}
+
+// y = y_acc / window_sumsquare (where that is not ~0), trimmed by n_fft/2 on both sides (center=True)
+__global__ void gl_norm_kernel(const GlArgs a) {
+    const size_t ylen = (size_t)a.n_fft + (size_t)a.hop * (a.T - 1);
+    const int b = blockIdx.y;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += gridDim.x * blockDim.x) {
+        const size_t j = (size_t)n + a.n_fft / 2;
+        const float w = a.wss[j];
+        const float v = a.y_acc[(size_t)b * ylen + j];
+        a.y[(size_t)b * a.N + n] = w > 1.17549435e-38f ? v / w : v;
+    }
+}
+
+// X = stft(y) (two frames per FFT) ; angles = X - mom * prev ; angles /= |angles| + tiny ; prev = X
+__global__ void __launch_bounds__(kMelThreads) gl_stft_update_kernel(const GlArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* re = smem;
+    float* im = re + a.n_fft;
+    float2* tw = reinterpret_cast<float2*>(im + a.n_fft);
+    float* win = reinterpret_cast<float*>(tw + a.n_fft / 2);
+    const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kFramesPerCta;
+    const int nbins = a.n_fft / 2 + 1;
+    const float* x = a.y + (size_t)b * a.N;
+    for (int i = tid; i < a.n_fft / 2; i += kMelThreads) tw[i] = a.twiddle[i];
+    for (int i = tid; i < a.n_fft; i += kMelThreads) win[i] = a.window[i];
+    for (int f = 0; f < kFramesPerCta; f += 2) {
+        const int ta = t0 + f, tb = ta + 1;
+        if (ta >= a.T) break;
+        const bool has_b = tb < a.T;
+        __syncthreads();
+        const int sa = ta * a.hop - a.n_fft / 2, sb = sa + a.hop;
+        for (int i = tid; i < a.n_fft; i += kMelThreads) {
+            const int ia = sa + i, ib = sb + i;
+            const float w = win[i];
+            const float va = (ia >= 0 && ia < a.N) ? __ldg(x + ia) * w : 0.f;
+            const float vb = (has_b && ib >= 0 && ib < a.N) ? __ldg(x + ib) * w : 0.f;
+            const int j = (int)(__brev((unsigned)i) >> (32 - a.log2n));
+            re[j] = va;
+            im[j] = vb;
+        }
+        fft_stages(re, im, tw, a.n_fft, a.log2n, tid);
+        for (int k = tid; k < nbins; k += kMelThreads) {
+            const int nk = (a.n_fft - k) & (a.n_fft - 1);
+            const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+            const float2 xa = make_float2(0.5f * (zr + yr), 0.5f * (zi - yi));
+            const float2 xb = make_float2(0.5f * (zi + yi), -0.5f * (zr - yr));
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                if (which && !has_b) break;
+                const size_t o = ((size_t)b * a.T + (which ? tb : ta)) * nbins + k;
+                const float2 X = which ? xb : xa;
+                const float2 p = a.prev[o];
+                float gr = X.x - a.mom * p.x, gi = X.y - a.mom * p.y;
+                const float inv = 1.0f / (sqrtf(gr * gr + gi * gi) + 1.17549435e-38f);
+                a.angles[o] = make_float2(gr * inv, gi * inv);
+                a.prev[o] = X;
+            }
+        }
     }
 }
 
@@ -302,6 +443,75 @@ int hfg_logmel_forward(hfg_logmel* h, const float* audio, int32_t B, int32_t N, 
     MCK(cudaGetLastError());
     if (!out_dev) MCK(cudaMemcpyAsync(mel, d_o, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     MCK(cudaStreamSynchronize(h->stream));
+    return HFG_OK;
+}
+
+int hfg_griffin_lim(hfg_logmel* h, const float* mag, const float* angles0, int32_t B, int32_t T, int32_t n_iter, float momentum,
+                    float* audio) {
+    if (!h || !mag || !angles0 || !audio) return mel_fail(HFG_ERR_INVALID, "hfg_griffin_lim: null argument");
+    if (B <= 0 || T < 2 || n_iter < 0 || momentum < 0.f) return mel_fail(HFG_ERR_INVALID, "hfg_griffin_lim: need B > 0, T >= 2, n_iter >= 0, momentum >= 0");
+    MelDeviceGuard guard(h->device);
+    MCK(guard.err);
+    const hfg_logmel_config& c = h->cfg;
+    const int n = c.n_fft, nbins = n / 2 + 1, hop = c.hop_length;
+    const int N = hop * (T - 1);
+    const size_t ylen = (size_t)n + (size_t)hop * (T - 1);
+    const size_t nspec = (size_t)B * T * nbins;
+    // librosa.filters.window_sumsquare: squared synthesis window overlap-added at every frame position
+    std::vector<float> wss(ylen, 0.f);
+    {
+        std::vector<double> w2((size_t)n, 0.0), acc(ylen, 0.0);
+        const int lpad = (n - c.win_length) / 2;
+        for (int i = 0; i < c.win_length; ++i) { const double w = 0.5 - 0.5 * cos(2.0 * M_PI * i / c.win_length); w2[lpad + i] = w * w; }
+        for (int t = 0; t < T; ++t)
+            for (int i = 0; i < n; ++i) acc[(size_t)t * hop + i] += w2[i];
+        for (size_t i = 0; i < ylen; ++i) wss[i] = (float)acc[i];
+    }
+    float *d_mag_cf = nullptr, *d_mag = nullptr, *d_yacc = nullptr, *d_y = nullptr, *d_wss = nullptr;
+    float2 *d_ang = nullptr, *d_prev = nullptr;
+    auto release = [&]() { cudaFree(d_mag_cf); cudaFree(d_mag); cudaFree(d_yacc); cudaFree(d_y); cudaFree(d_wss); cudaFree(d_ang); cudaFree(d_prev); };
+#define GCK(expr)                                                                                                       \
+    do {                                                                                                                \
+        cudaError_t _e = (expr);                                                                                        \
+        if (_e != cudaSuccess) { release(); return mel_fail(HFG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } \
+    } while (0)
+    GCK(cudaMalloc(&d_mag_cf, nspec * sizeof(float)));
+    GCK(cudaMalloc(&d_mag, nspec * sizeof(float)));
+    GCK(cudaMalloc(&d_ang, nspec * sizeof(float2)));
+    GCK(cudaMalloc(&d_prev, nspec * sizeof(float2)));
+    GCK(cudaMalloc(&d_yacc, (size_t)B * ylen * sizeof(float)));
+    GCK(cudaMalloc(&d_y, (size_t)B * N * sizeof(float)));
+    GCK(cudaMalloc(&d_wss, ylen * sizeof(float)));
+    cudaStream_t st = h->stream;
+    GCK(cudaMemcpyAsync(d_mag_cf, mag, nspec * sizeof(float), cudaMemcpyHostToDevice, st));
+    GCK(launch_transpose_cf_to_cl(d_mag_cf, d_mag, B, nbins, T, st));     // [B][nbins][T] (librosa layout) -> frame-major [B][T][nbins]
+    GCK(cudaMemcpyAsync(d_ang, angles0, nspec * sizeof(float2), cudaMemcpyHostToDevice, st));
+    GCK(cudaMemsetAsync(d_prev, 0, nspec * sizeof(float2), st));
+    GCK(cudaMemcpyAsync(d_wss, wss.data(), ylen * sizeof(float), cudaMemcpyHostToDevice, st));
+    GlArgs a;
+    a.mag = d_mag; a.angles = d_ang; a.prev = d_prev; a.y_acc = d_yacc; a.y = d_y; a.wss = d_wss;
+    a.window = h->d_window; a.twiddle = h->d_twiddle;
+    a.T = T; a.n_fft = n; a.log2n = h->log2n; a.hop = hop; a.N = N; a.mom = 0.f;
+    const size_t smem_i = (size_t)(4 * n + n + (kFramesPerCta - 1) * hop) * sizeof(float);
+    const size_t smem_s = (size_t)(4 * n) * sizeof(float);
+    if (smem_i > 48 * 1024) GCK(cudaFuncSetAttribute(gl_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
+    if (smem_s > 48 * 1024) GCK(cudaFuncSetAttribute(gl_stft_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    const dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
+    const dim3 ngrid((unsigned)std::min<size_t>(((size_t)N + 255) / 256, 1024), B);
+    for (int it = 0; it <= n_iter; ++it) {
+        GCK(cudaMemsetAsync(d_yacc, 0, (size_t)B * ylen * sizeof(float), st));
+        gl_istft_kernel<<<grid, kMelThreads, smem_i, st>>>(a);
+        gl_norm_kernel<<<ngrid, 256, 0, st>>>(a);
+        if (it == n_iter) break;                                            // the last inverse transform is the result
+        a.mom = it == 0 ? 0.f : momentum / (1.0f + momentum);
+        gl_stft_update_kernel<<<grid, kMelThreads, smem_s, st>>>(a);
+        GCK(cudaGetLastError());
+    }
+    GCK(cudaGetLastError());
+    GCK(cudaMemcpyAsync(audio, d_y, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    GCK(cudaStreamSynchronize(st));
+#undef GCK
+    release();
     return HFG_OK;
 }
 

@@ -1,10 +1,14 @@
 """Griffin-Lim alternative vocoder (reference: scripts/synthesize.py:174-194, which calls librosa).
 
-NOT the hot path and not a drop-in for librosa bit for bit: librosa is not installable here, so this is a restatement of
-the same steps -- exp of the clipped log-mel, mel -> linear magnitude by a non-negative least-squares-like projection
-through the pseudo-inverse of a Slaney mel filterbank (n_fft 1024, fmin 0, fmax sr/2, as src/iris/data.py:25-67 uses),
-60 Griffin-Lim iterations with hop 256 / window 1024 (Hann).  torch.stft / istft do the transforms (library FFTs, on the
-GPU when there is one).  **Parity unpinned**: there is nothing to execute it against.
+NOT the hot path.  The steps of the reference -- exp of the clipped log-mel (:180-181), ``librosa.feature.inverse.mel_to_stft``
+(:187-192), ``librosa.griffinlim(S, n_iter=60, hop_length, win_length=1024)`` (:193) -- with the iteration itself on the GPU:
+``hfg_griffin_lim`` (csrc/kernels_mel.cu: shared-memory FFT kernels for the inverse and forward STFT of every iteration, the phase
+update with momentum 0.99 fused into the forward one).  No CPU fallback.  The mel -> linear step is a pseudo-inverse-and-clip
+projection through the Slaney filterbank (librosa solves a non-negative least-squares problem there: not restated).
+
+Parity: the iteration is checked against oracle/griffinlim_oracle.py (float64 restatement of librosa 0.11.0's ``griffinlim`` /
+``istft`` / ``stft``) on identical initial phases, tests/test_gpu_logmel.py; against librosa itself it is **unpinned** (not
+installable here; its random phases are not reproducible across implementations anyway).
 """
 from __future__ import annotations
 
@@ -40,24 +44,49 @@ def mel_filterbank(sample_rate: int = 22050, n_fft: int = 1024, n_mels: int = 80
     return fb.astype(np.float32)
 
 
+def griffin_lim(mag: np.ndarray, n_iter: int = 60, hop_length: int = 256, win_length: int = 1024, n_fft: int = 1024,
+                momentum: float = 0.99, seed: int = 0, angles0: np.ndarray = None, sample_rate: int = 22050, device: int = 0) -> np.ndarray:
+    """``librosa.griffinlim``: linear magnitudes [1 + n_fft // 2, T] or [B, 1 + n_fft // 2, T] -> float32 [hop * (T - 1)] (or [B, ...]).
+    ``angles0`` (complex unit phasors of mag's shape) replaces the seeded random initial phases."""
+    import ctypes
+
+    from . import _abi
+    from .mel import LogMel
+
+    m = np.asarray(mag, dtype=np.float32)
+    squeeze = m.ndim == 2
+    if squeeze:
+        m = m[None]
+    if m.ndim != 3 or m.shape[1] != 1 + n_fft // 2:
+        raise ValueError(f"mag must be [{1 + n_fft // 2}, T] or [B, {1 + n_fft // 2}, T], got {np.shape(mag)}")
+    B, nbins, T = m.shape
+    if T < 2:
+        raise ValueError("Griffin-Lim needs at least two frames")
+    if angles0 is None:
+        rng = np.random.default_rng(seed)
+        phase = 2.0 * np.pi * rng.random((B, nbins, T))
+        angles0 = np.cos(phase) + 1j * np.sin(phase)
+    a0 = np.asarray(angles0, dtype=np.complex64)
+    if a0.ndim == 2:
+        a0 = a0[None]
+    if a0.shape != m.shape:
+        raise ValueError("angles0 must have the shape of mag")
+    a0 = np.ascontiguousarray(np.transpose(a0, (0, 2, 1)))                     # frame-major [B][T][nbins] (re, im) pairs
+    m = np.ascontiguousarray(m)
+    out = np.empty((B, hop_length * (T - 1)), dtype=np.float32)
+    fe = LogMel(sample_rate, n_fft, hop_length, win_length, device=device)
+    try:
+        _abi.check(fe._lib.hfg_griffin_lim(fe._h, m.ctypes.data, a0.ctypes.data, B, T, int(n_iter), float(momentum), out.ctypes.data))
+    finally:
+        fe.close()
+    return out[0] if squeeze else out
+
+
 def griffin_lim_from_log_mel(log_mel: np.ndarray, sample_rate: int = 22050, hop_length: int = 256, n_fft: int = 1024,
                              n_iter: int = 60, seed: int = 0) -> np.ndarray:
-    """log-mel [n_mels, T] (natural log of magnitudes) -> waveform float32 [~T * hop_length]."""
-    import torch
-
-    dev = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
-    m = np.exp(np.clip(np.asarray(log_mel, dtype=np.float64), -11.513, 2.0))          # scripts/synthesize.py:180-181
-    fb = mel_filterbank(sample_rate, n_fft, m.shape[0]).astype(np.float64)
-    mag = np.maximum(np.linalg.pinv(fb) @ m, 0.0)                                     # mel_to_stft, power = 1
-    mag_t = torch.from_numpy(mag.astype(np.float32)).to(dev)
-    win = torch.hann_window(n_fft, device=dev)
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    phase = torch.exp(2j * np.pi * torch.rand(mag_t.shape, generator=g)).to(dev)
-    length = hop_length * (mag_t.shape[1] - 1)
-    spec = mag_t * phase
-    for _ in range(n_iter):
-        wav = torch.istft(spec, n_fft, hop_length=hop_length, win_length=n_fft, window=win, length=length)
-        rebuilt = torch.stft(wav, n_fft, hop_length=hop_length, win_length=n_fft, window=win, return_complex=True)
-        spec = mag_t * torch.exp(1j * torch.angle(rebuilt))
-    wav = torch.istft(spec, n_fft, hop_length=hop_length, win_length=n_fft, window=win, length=length)
-    return wav.clamp(-1.0, 1.0).cpu().numpy().astype(np.float32)
+    """log-mel [n_mels, T] (natural log of magnitudes) -> waveform float32 [hop_length * (T - 1)] (scripts/synthesize.py:174-194)."""
+    m = np.exp(np.clip(np.asarray(log_mel, dtype=np.float64), -11.513, 2.0))          # :180-181
+    fb = mel_filterbank(sample_rate, n_fft, m.shape[0]).astype(np.float64)            # mel_to_stft's default fmax = sr / 2 (:187-192)
+    mag = np.maximum(np.linalg.pinv(fb) @ m, 0.0)                                     # power = 1
+    wav = griffin_lim(mag, n_iter=n_iter, hop_length=hop_length, win_length=n_fft, n_fft=n_fft, seed=seed, sample_rate=sample_rate)
+    return np.clip(wav, -1.0, 1.0).astype(np.float32)

@@ -57,3 +57,30 @@ def test_known_answers():
     y[2048] = 1.0
     lin = LO.mel_linear(y)
     np.testing.assert_allclose(lin[:, 8], LO.mel_filterbank().sum(axis=1), rtol=1e-12)
+
+
+def test_griffinlim_oracle_transforms_are_consistent():
+    """oracle/griffinlim_oracle.py: istft(stft(y)) reproduces y (perfect reconstruction of the periodic Hann at hop = n_fft / 4),
+    the window sum-square is the constant 1.5 away from the edges, the iteration reduces the spectral inconsistency, and its stft
+    is the same transform as the log-mel oracle's and transformers' (power = None spectrogram)."""
+    from oracle import griffinlim_oracle as G
+    au = pytest.importorskip("transformers.audio_utils")
+    scipy_signal = pytest.importorskip("scipy.signal")
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(256 * 24) * 0.1
+    X = G.stft(y)
+    assert X.shape == (513, 25)
+    ref = au.spectrogram(y, scipy_signal.get_window("hann", 1024, fftbins=True), 1024, 256, fft_length=1024, power=None, center=True,
+                         pad_mode="constant", dtype=np.float64)
+    np.testing.assert_allclose(X, ref, atol=1e-6)
+    back = G.istft(X)
+    assert back.shape == y.shape
+    np.testing.assert_allclose(back, y, atol=1e-12)
+    wss = G.window_sumsquare(25)
+    np.testing.assert_allclose(wss[1024:-1024], 1.5, atol=1e-12)
+    S = np.abs(X)
+    ang = np.exp(2j * np.pi * rng.random(S.shape))
+    err0 = np.abs(np.abs(G.stft(G.istft(S * ang))) - S).mean()
+    out = G.griffinlim(S, ang, n_iter=20)
+    assert out.shape == y.shape
+    assert np.abs(np.abs(G.stft(out)) - S).mean() < 0.35 * err0
