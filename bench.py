@@ -362,7 +362,9 @@ def measure_tf32_peak(seconds=1.5):
 
 def logmel_leg(batch, samples, peaks, reps=20):
     """the log-mel front-end kernel (hfg_logmel_*, csrc/kernels_mel.cu) on `batch` waveforms of `samples` samples,
-    device-resident in and out; HBM-bound: algorithmic bytes = 4 B per audio sample read + the [B, 80, T] mel written."""
+    device-resident in and out.  Algorithmic bytes = 4 B per audio sample read + the [B, 80, T] mel written (the kernel reads HBM
+    exactly that once: profiles/r02d_mel_ncu_summary.txt); the FFT's ~50 flop per byte puts the op on the FP32 issue rate, not on
+    HBM, so `frac` (against the HBM peak) is small by nature -- `issue_bound` says so in the line."""
     import torch
 
     from iris_tts_b200.mel import LogMel
@@ -382,7 +384,8 @@ def logmel_leg(batch, samples, peaks, reps=20):
     fe.close()
     return {"workload": f"log-mel of {batch} x {samples} samples (n_fft 1024, hop 256, 80 mels), device-resident, wall clock per synchronous call",
             "ms": ms, "value": batch * samples / (ms * 1e-3), "unit": "audio samples/s", "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9,
-            "hbm_peak_gbs": peaks["gbs"], "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["gbs"], "frames": T}
+            "hbm_peak_gbs": peaks["gbs"], "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["gbs"], "frames": T,
+            "issue_bound": "shared-memory FFT on CUDA cores: 70 % issue-active under ncu, 2 % of L2, DRAM read = the audio once"}
 
 
 def griffin_lim_leg(frames, n_iter=60, reps=3):

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "hfg_internal.h"
@@ -38,102 +39,133 @@ struct MelArgs {
     const int* band_count;   // [n_mels]
     const int* band_off;     // [n_mels]  offset of the band's weights in `weights`
     const float* weights;
+    int n_weights;
     int N, T, n_fft, log2n, hop, n_mels;
     float clip;
     int log_output;
 };
 
-// Radix-2 decimation-in-time stages on bit-reversed input in shared memory (forward transform, twiddles exp(-2 pi i k / n)).
+// Shared-memory FFT (forward transform, decimation in time on bit-reversed input), fp32.
+//  * Data live at PADDED positions fft_pad(i) = i + i / 32: the bit-reversed scatter of the load phase (a warp's 32 stores differ
+//    only in address bits >= 5, one bank without padding) and the strided butterflies of the early stages are then spread
+//    over the banks (measured: the unpadded radix-2 version spent ~9/10 of the kernel in bank conflicts).
+//  * Two radix-2 stages per pass, in registers: a thread owns the 4 points {b, b+h, b+2h, b+3h}, so n_fft = 1024 takes 5 passes
+//    (5 CTA barriers) with 256 threads; an odd log2(n_fft) ends with one radix-2 pass.
+//  * Twiddles come from a per-stage COMPACT table: entry (h - 1 + k) = exp(-2 pi i k / 2h), k < h, for h = 1, 2, 4 ...; a warp
+//    reads consecutive entries (or one, broadcast) instead of a stride of n / 2h through one table.
 // Begins and ends with a CTA barrier.
-__device__ __forceinline__ void fft_stages(float* re, float* im, const float2* tw, int n_fft, int log2n, int tid) {
-    for (int st = 1; st <= log2n; ++st) {
+__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 5); }
+__host__ __device__ constexpr int fft_padded_len(int n) { return n + n / 32; }
+
+template <int kLog2N>
+__device__ __forceinline__ void fft_stages(float* re, float* im, const float2* tws, int tid) {
+    constexpr int n_fft = 1 << kLog2N, log2n = kLog2N;     // compile-time: every shift, bound and stride below folds to an immediate
+    int st = 1;
+#pragma unroll
+    for (; st + 1 <= log2n; st += 2) {
         __syncthreads();
-        const int half = 1 << (st - 1);
-        const int tstep = n_fft >> st;
-        for (int idx = tid; idx < n_fft / 2; idx += kMelThreads) {
-            const int k = idx & (half - 1);
-            const int i0 = ((idx >> (st - 1)) << st) + k;
-            const int i1 = i0 + half;
-            const float2 w = tw[k * tstep];
-            const float xr = re[i1], xi = im[i1];
-            const float tr = w.x * xr - w.y * xi;
-            const float ti = w.x * xi + w.y * xr;
-            const float ur = re[i0], ui = im[i0];
-            re[i0] = ur + tr; im[i0] = ui + ti;
-            re[i1] = ur - tr; im[i1] = ui - ti;
+        const int h = 1 << (st - 1);
+#pragma unroll
+        for (int q = tid; q < n_fft / 4; q += kMelThreads) {
+            const int k = q & (h - 1);
+            const int base = ((q >> (st - 1)) << (st + 1)) + k;
+            const int p0 = fft_pad(base), p1 = fft_pad(base + h), p2 = fft_pad(base + 2 * h), p3 = fft_pad(base + 3 * h);
+            const float2 wa = tws[h - 1 + k];             // exp(-2 pi i k / 2h): stage st, both butterflies
+            const float2 wb = tws[2 * h - 1 + k];         // exp(-2 pi i k / 4h): stage st + 1 (the second butterfly takes wb * -i)
+            const float x0r = re[p0], x0i = im[p0], x1r = re[p1], x1i = im[p1];
+            const float x2r = re[p2], x2i = im[p2], x3r = re[p3], x3i = im[p3];
+            float tr = wa.x * x1r - wa.y * x1i, ti = wa.x * x1i + wa.y * x1r;
+            const float y0r = x0r + tr, y0i = x0i + ti, y1r = x0r - tr, y1i = x0i - ti;
+            tr = wa.x * x3r - wa.y * x3i; ti = wa.x * x3i + wa.y * x3r;
+            const float y2r = x2r + tr, y2i = x2i + ti, y3r = x2r - tr, y3i = x2i - ti;
+            tr = wb.x * y2r - wb.y * y2i; ti = wb.x * y2i + wb.y * y2r;
+            re[p0] = y0r + tr; im[p0] = y0i + ti;
+            re[p2] = y0r - tr; im[p2] = y0i - ti;
+            const float ur = wb.x * y3r - wb.y * y3i, ui = wb.x * y3i + wb.y * y3r;   // (ur + i ui) * -i = ui - i ur
+            re[p1] = y1r + ui; im[p1] = y1i - ur;
+            re[p3] = y1r - ui; im[p3] = y1i + ur;
+        }
+    }
+    if (log2n & 1) {
+        st = log2n;
+        __syncthreads();
+        const int h = 1 << (st - 1);
+#pragma unroll
+        for (int q = tid; q < n_fft / 2; q += kMelThreads) {
+            const int k = q & (h - 1);
+            const int i0 = ((q >> (st - 1)) << st) + k;
+            const int p0 = fft_pad(i0), p1 = fft_pad(i0 + h);
+            const float2 w = tws[h - 1 + k];
+            const float xr = re[p1], xi = im[p1];
+            const float tr = w.x * xr - w.y * xi, ti = w.x * xi + w.y * xr;
+            const float ur = re[p0], ui = im[p0];
+            re[p0] = ur + tr; im[p0] = ui + ti;
+            re[p1] = ur - tr; im[p1] = ui - ti;
         }
     }
     __syncthreads();
 }
 
+template <int kLog2N>
 __global__ void __launch_bounds__(kMelThreads) logmel_kernel(const MelArgs a) {
+    constexpr int kN = 1 << kLog2N;
     extern __shared__ __align__(16) float smem[];
-    float* re = smem;                         // [n_fft]
-    float* im = re + a.n_fft;                 // [n_fft]
-    float2* tw = reinterpret_cast<float2*>(im + a.n_fft);   // [n_fft/2]
-    float* win = reinterpret_cast<float*>(tw + a.n_fft / 2);   // [n_fft]
-    const int nbins = a.n_fft / 2 + 1;
-    float* mag_a = win + a.n_fft;             // [nbins]  |X| of the pair's first frame
-    float* mag_b = mag_a + nbins;             // [nbins]  ... second frame
-    float* mel_s = mag_b + nbins;             // [n_mels][kFramesPerCta]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* re = smem;                         // [n_fft] at padded positions
+    float* im = re + fft_padded_len(kN);
+    float2* tw = reinterpret_cast<float2*>(im + fft_padded_len(kN));   // [n_fft] per-stage compact twiddles
+    float* win = reinterpret_cast<float*>(tw + kN);   // [n_fft]
+    const int nbins = kN / 2 + 1;
+    float* mag = win + kN;               // [kFramesPerCta][nbins]  |X| of the CTA's frames (odd row stride: rows fall on different banks)
+    float* wts = mag + kFramesPerCta * nbins; // [n_weights]  the bands' non-zero filter weights, back to back
+    int* band = reinterpret_cast<int*>(wts + a.n_weights);   // start | count | offset, n_mels each
+    const int tid = threadIdx.x;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kFramesPerCta;
     const float* x = a.audio + (size_t)b * a.N;
-    for (int i = tid; i < a.n_fft / 2; i += kMelThreads) tw[i] = a.twiddle[i];
-    for (int i = tid; i < a.n_fft; i += kMelThreads) win[i] = a.window[i];
+    for (int i = tid; i < kN; i += kMelThreads) { tw[i] = a.twiddle[i]; win[i] = a.window[i]; }
+    for (int i = tid; i < a.n_weights; i += kMelThreads) wts[i] = a.weights[i];
+    for (int i = tid; i < 3 * a.n_mels; i += kMelThreads) band[i] = a.band_start[i];   // the three tables are one allocation
     // Two real frames per complex FFT: z = x_a + i x_b, and X_a[k] = (Z[k] + conj Z[N-k]) / 2, X_b[k] = (Z[k] - conj Z[N-k]) / 2i.
     for (int f = 0; f < kFramesPerCta; f += 2) {
         const int ta = t0 + f, tb = ta + 1;
         if (ta >= a.T) break;                 // uniform across the CTA
         const bool has_b = tb < a.T;
-        __syncthreads();                      // tables loaded / previous pair's magnitudes consumed
-        const int sa = ta * a.hop - a.n_fft / 2, sb = sa + a.hop;
-        for (int i = tid; i < a.n_fft; i += kMelThreads) {
+        __syncthreads();                      // tables loaded / previous pair's spectrum consumed
+        const int sa = ta * a.hop - kN / 2, sb = sa + a.hop;
+        for (int i = tid; i < kN; i += kMelThreads) {
             const int ia = sa + i, ib = sb + i;
             const float w = win[i];
             const float va = (ia >= 0 && ia < a.N) ? __ldg(x + ia) * w : 0.f;
             const float vb = (has_b && ib >= 0 && ib < a.N) ? __ldg(x + ib) * w : 0.f;
-            const int j = (int)(__brev((unsigned)i) >> (32 - a.log2n));
+            const int j = fft_pad((int)(__brev((unsigned)i) >> (32 - kLog2N)));
             re[j] = va;
             im[j] = vb;
         }
-        fft_stages(re, im, tw, a.n_fft, a.log2n, tid);
+        fft_stages<kLog2N>(re, im, tw, tid);
+        float* mag_a = mag + f * nbins;
+        float* mag_b = mag_a + nbins;
         for (int k = tid; k < nbins; k += kMelThreads) {
-            const int nk = (a.n_fft - k) & (a.n_fft - 1);
-            const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+            const int nk = fft_pad((kN - k) & (kN - 1)), pk = fft_pad(k);
+            const float zr = re[pk], zi = im[pk], yr = re[nk], yi = im[nk];
             const float ar = 0.5f * (zr + yr), ai = 0.5f * (zi - yi);      // X_a[k]
             const float br = 0.5f * (zi + yi), bi = -0.5f * (zr - yr);     // X_b[k]
             mag_a[k] = sqrtf(ar * ar + ai * ai);
             mag_b[k] = sqrtf(br * br + bi * bi);
         }
-        __syncthreads();
-        // one warp per mel band, lanes over the band's bins (a contiguous run), both frames of the pair at once
-        for (int m = warp; m < a.n_mels; m += kMelThreads / 32) {
-            const int s = a.band_start[m], c = a.band_count[m];
-            const float* w = a.weights + a.band_off[m];
-            float acc_a = 0.f, acc_b = 0.f;
-            for (int i = lane; i < c; i += 32) {
-                const float wi = __ldg(w + i);
-                acc_a = fmaf(wi, mag_a[s + i], acc_a);
-                acc_b = fmaf(wi, mag_b[s + i], acc_b);
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                acc_a += __shfl_xor_sync(0xffffffffu, acc_a, d);
-                acc_b += __shfl_xor_sync(0xffffffffu, acc_b, d);
-            }
-            if (lane == 0) {
-                mel_s[m * kFramesPerCta + f] = a.log_output ? logf(fmaxf(acc_a, a.clip)) : acc_a;
-                mel_s[m * kFramesPerCta + f + 1] = a.log_output ? logf(fmaxf(acc_b, a.clip)) : acc_b;
-            }
-        }
     }
     __syncthreads();
+    // Sparse triangular mel filters for all frames of the CTA at once: one thread per (band, frame), serial over the band's
+    // contiguous run of bins (13 on average, 2 .. 60); the 8 frames of a band leave as one run of consecutive floats.
     const int nf = min(kFramesPerCta, a.T - t0);
-    for (int i = tid; i < a.n_mels * kFramesPerCta; i += kMelThreads) {
-        const int m = i / kFramesPerCta, f = i - m * kFramesPerCta;
-        if (f < nf) a.out[((size_t)b * a.n_mels + m) * a.T + t0 + f] = mel_s[i];
+    for (int it = tid; it < a.n_mels * kFramesPerCta; it += kMelThreads) {
+        const int m = it / kFramesPerCta, f = it - m * kFramesPerCta;
+        if (f >= nf) continue;
+        const int s = band[m], c = band[a.n_mels + m];
+        const float* w = wts + band[2 * a.n_mels + m];
+        const float* mg = mag + f * nbins + s;
+        float acc = 0.f;
+        for (int i = 0; i < c; ++i) acc = fmaf(w[i], mg[i], acc);
+        a.out[((size_t)b * a.n_mels + m) * a.T + t0 + f] = a.log_output ? logf(fmaxf(acc, a.clip)) : acc;
     }
 }
 
@@ -157,28 +189,29 @@ struct GlArgs {
 
 // y_acc += window * irfft(S * angles), two frames per complex FFT: Z = X_a + i X_b with both spectra Hermitian-extended, and
 // ifft(Z) = x_a + i x_b;  ifft(Z) = conj(fft(conj Z)) / n.
+template <int kLog2N>
 __global__ void __launch_bounds__(kMelThreads) gl_istft_kernel(const GlArgs a) {
+    constexpr int kN = 1 << kLog2N;
     extern __shared__ __align__(16) float smem[];
     float* re = smem;
-    float* im = re + a.n_fft;
-    float2* tw = reinterpret_cast<float2*>(im + a.n_fft);
-    float* win = reinterpret_cast<float*>(tw + a.n_fft / 2);
-    float* ola = win + a.n_fft;               // [n_fft + (kFramesPerCta-1)*hop]  this CTA's overlap-add
+    float* im = re + fft_padded_len(kN);
+    float2* tw = reinterpret_cast<float2*>(im + fft_padded_len(kN));
+    float* win = reinterpret_cast<float*>(tw + kN);
+    float* ola = win + kN;               // [n_fft + (kFramesPerCta-1)*hop]  this CTA's overlap-add
     const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kFramesPerCta;
-    const int nbins = a.n_fft / 2 + 1, half = a.n_fft / 2;
-    const int span = a.n_fft + (kFramesPerCta - 1) * a.hop;
-    for (int i = tid; i < half; i += kMelThreads) tw[i] = a.twiddle[i];
-    for (int i = tid; i < a.n_fft; i += kMelThreads) win[i] = a.window[i];
+    const int nbins = kN / 2 + 1, half = kN / 2;
+    const int span = kN + (kFramesPerCta - 1) * a.hop;
+    for (int i = tid; i < kN; i += kMelThreads) { tw[i] = a.twiddle[i]; win[i] = a.window[i]; }
     for (int i = tid; i < span; i += kMelThreads) ola[i] = 0.f;
-    const float inv_n = 1.0f / (float)a.n_fft;
+    const float inv_n = 1.0f / (float)kN;
     for (int f = 0; f < kFramesPerCta; f += 2) {
         const int ta = t0 + f, tb = ta + 1;
         if (ta >= a.T) break;
         const bool has_b = tb < a.T;
         const size_t ba = ((size_t)b * a.T + ta) * nbins, bb = ba + nbins;
         __syncthreads();
-        for (int k = tid; k < a.n_fft; k += kMelThreads) {
-            const int kk = k <= half ? k : a.n_fft - k;          // Hermitian extension: X[n-k] = conj X[k]
+        for (int k = tid; k < kN; k += kMelThreads) {
+            const int kk = k <= half ? k : kN - k;          // Hermitian extension: X[n-k] = conj X[k]
             const float sgn = k <= half ? 1.f : -1.f;
             const float2 ga = a.angles[ba + kk];
             const float ma = a.mag[ba + kk];
@@ -191,24 +224,24 @@ __global__ void __launch_bounds__(kMelThreads) gl_istft_kernel(const GlArgs a) {
             }
             if (kk == 0 || kk == half) { ai = 0.f; bi = 0.f; }   // irfft ignores the imaginary part of the DC and Nyquist bins
             // Z = X_a + i X_b ; load conj(Z) bit-reversed
-            const int j = (int)(__brev((unsigned)k) >> (32 - a.log2n));
+            const int j = fft_pad((int)(__brev((unsigned)k) >> (32 - kLog2N)));
             re[j] = ar - bi;
             im[j] = -(ai + br);
         }
-        fft_stages(re, im, tw, a.n_fft, a.log2n, tid);
+        fft_stages<kLog2N>(re, im, tw, tid);
         // ifft(Z) = conj(fft(conj Z)) / n:  x_a = re / n,  x_b = -im / n
-        for (int i = tid; i < a.n_fft; i += kMelThreads) {
+        for (int i = tid; i < kN; i += kMelThreads) {
             const float w = win[i] * inv_n;
-            ola[f * a.hop + i] += re[i] * w;
+            ola[f * a.hop + i] += re[fft_pad(i)] * w;
         }
         __syncthreads();
         if (has_b)
-            for (int i = tid; i < a.n_fft; i += kMelThreads) ola[(f + 1) * a.hop + i] -= im[i] * win[i] * inv_n;
+            for (int i = tid; i < kN; i += kMelThreads) ola[(f + 1) * a.hop + i] -= im[fft_pad(i)] * win[i] * inv_n;
     }
     __syncthreads();
-    const size_t ylen = (size_t)a.n_fft + (size_t)a.hop * (a.T - 1);
+    const size_t ylen = (size_t)kN + (size_t)a.hop * (a.T - 1);
     const int nf = min(kFramesPerCta, a.T - t0);
-    const int used = a.n_fft + (nf - 1) * a.hop;
+    const int used = kN + (nf - 1) * a.hop;
     for (int i = tid; i < used; i += kMelThreads) atomicAdd(a.y_acc + (size_t)b * ylen + (size_t)t0 * a.hop + i, ola[i]);
 }
 
@@ -225,36 +258,37 @@ __global__ void gl_norm_kernel(const GlArgs a) {
 }
 
 // X = stft(y) (two frames per FFT) ; angles = X - mom * prev ; angles /= |angles| + tiny ; prev = X
+template <int kLog2N>
 __global__ void __launch_bounds__(kMelThreads) gl_stft_update_kernel(const GlArgs a) {
+    constexpr int kN = 1 << kLog2N;
     extern __shared__ __align__(16) float smem[];
     float* re = smem;
-    float* im = re + a.n_fft;
-    float2* tw = reinterpret_cast<float2*>(im + a.n_fft);
-    float* win = reinterpret_cast<float*>(tw + a.n_fft / 2);
+    float* im = re + fft_padded_len(kN);
+    float2* tw = reinterpret_cast<float2*>(im + fft_padded_len(kN));
+    float* win = reinterpret_cast<float*>(tw + kN);
     const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kFramesPerCta;
-    const int nbins = a.n_fft / 2 + 1;
+    const int nbins = kN / 2 + 1;
     const float* x = a.y + (size_t)b * a.N;
-    for (int i = tid; i < a.n_fft / 2; i += kMelThreads) tw[i] = a.twiddle[i];
-    for (int i = tid; i < a.n_fft; i += kMelThreads) win[i] = a.window[i];
+    for (int i = tid; i < kN; i += kMelThreads) { tw[i] = a.twiddle[i]; win[i] = a.window[i]; }
     for (int f = 0; f < kFramesPerCta; f += 2) {
         const int ta = t0 + f, tb = ta + 1;
         if (ta >= a.T) break;
         const bool has_b = tb < a.T;
         __syncthreads();
-        const int sa = ta * a.hop - a.n_fft / 2, sb = sa + a.hop;
-        for (int i = tid; i < a.n_fft; i += kMelThreads) {
+        const int sa = ta * a.hop - kN / 2, sb = sa + a.hop;
+        for (int i = tid; i < kN; i += kMelThreads) {
             const int ia = sa + i, ib = sb + i;
             const float w = win[i];
             const float va = (ia >= 0 && ia < a.N) ? __ldg(x + ia) * w : 0.f;
             const float vb = (has_b && ib >= 0 && ib < a.N) ? __ldg(x + ib) * w : 0.f;
-            const int j = (int)(__brev((unsigned)i) >> (32 - a.log2n));
+            const int j = fft_pad((int)(__brev((unsigned)i) >> (32 - kLog2N)));
             re[j] = va;
             im[j] = vb;
         }
-        fft_stages(re, im, tw, a.n_fft, a.log2n, tid);
+        fft_stages<kLog2N>(re, im, tw, tid);
         for (int k = tid; k < nbins; k += kMelThreads) {
-            const int nk = (a.n_fft - k) & (a.n_fft - 1);
-            const float zr = re[k], zi = im[k], yr = re[nk], yi = im[nk];
+            const int nk = fft_pad((kN - k) & (kN - 1)), pk = fft_pad(k);
+            const float zr = re[pk], zi = im[pk], yr = re[nk], yi = im[nk];
             const float2 xa = make_float2(0.5f * (zr + yr), 0.5f * (zi - yi));
             const float2 xb = make_float2(0.5f * (zi + yi), -0.5f * (zr - yr));
 #pragma unroll
@@ -282,6 +316,21 @@ double mel_to_hz(double m) {
     return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
 }
 
+// The FFT kernels are compiled per transform length (n_fft = 64 .. 4096): f receives std::integral_constant<int, log2(n_fft)>.
+template <typename F>
+cudaError_t mel_dispatch(int log2n, F&& f) {
+    switch (log2n) {
+        case 6: return f(std::integral_constant<int, 6>{});
+        case 7: return f(std::integral_constant<int, 7>{});
+        case 8: return f(std::integral_constant<int, 8>{});
+        case 9: return f(std::integral_constant<int, 9>{});
+        case 10: return f(std::integral_constant<int, 10>{});
+        case 11: return f(std::integral_constant<int, 11>{});
+        case 12: return f(std::integral_constant<int, 12>{});
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 int mel_fail(int code, const std::string& msg) {
     set_error(msg);
     return code;
@@ -305,6 +354,7 @@ struct hfg_logmel {
     float* d_out = nullptr;
     size_t audio_cap = 0, out_cap = 0;
     size_t smem = 0;
+    int n_weights = 0;
 };
 
 namespace {
@@ -348,8 +398,10 @@ int hfg_logmel_create(const hfg_logmel_config* cfg, int device, hfg_logmel** out
     std::vector<float> win((size_t)n, 0.f);
     const int lpad = (n - c.win_length) / 2;
     for (int i = 0; i < c.win_length; ++i) win[lpad + i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / c.win_length));
-    std::vector<float2> tw((size_t)n / 2);
-    for (int k = 0; k < n / 2; ++k) tw[k] = make_float2((float)cos(2.0 * M_PI * k / n), (float)(-sin(2.0 * M_PI * k / n)));
+    // per-stage compact twiddle table (fft_stages): entry h - 1 + k = exp(-2 pi i k / 2h), k < h, h = 1, 2, 4 ... n / 2
+    std::vector<float2> tw((size_t)n, make_float2(0.f, 0.f));
+    for (int hh = 1; hh < n; hh <<= 1)
+        for (int k = 0; k < hh; ++k) tw[hh - 1 + k] = make_float2((float)cos(M_PI * k / hh), (float)(-sin(M_PI * k / hh)));
     // librosa.filters.mel(htk=False, norm='slaney')
     std::vector<double> mel_f((size_t)c.n_mels + 2);
     const double m_lo = hz_to_mel(c.fmin), m_hi = hz_to_mel(fmax);
@@ -383,8 +435,11 @@ int hfg_logmel_create(const hfg_logmel_config* cfg, int device, hfg_logmel** out
     MCK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     MCK(cudaMemcpy(h->d_band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice));
     MCK(cudaMemcpy(h->d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice));
-    h->smem = (size_t)(2 * n + n + n + 2 * nbins + c.n_mels * kFramesPerCta) * sizeof(float);
-    if (h->smem > 48 * 1024) MCK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    h->n_weights = (int)weights.size();
+    h->smem = (size_t)(2 * fft_padded_len(n) + 2 * n + n + kFramesPerCta * nbins + weights.size() + 3 * c.n_mels) * sizeof(float);
+    if (h->smem > 48 * 1024) MCK(mel_dispatch(log2n, [&](auto tag) {
+        return cudaFuncSetAttribute(logmel_kernel<decltype(tag)::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+    }));
     *out = h.release();
     return HFG_OK;
 }
@@ -435,12 +490,14 @@ int hfg_logmel_forward(hfg_logmel* h, const float* audio, int32_t B, int32_t N, 
     MelArgs a;
     a.audio = d_in; a.out = d_o; a.window = h->d_window; a.twiddle = h->d_twiddle;
     a.band_start = h->d_band; a.band_count = h->d_band + h->cfg.n_mels; a.band_off = h->d_band + 2 * h->cfg.n_mels;
-    a.weights = h->d_weights;
+    a.weights = h->d_weights; a.n_weights = h->n_weights;
     a.N = N; a.T = T; a.n_fft = h->cfg.n_fft; a.log2n = h->log2n; a.hop = h->cfg.hop_length; a.n_mels = h->cfg.n_mels;
     a.clip = h->cfg.clip; a.log_output = h->cfg.log_output;
     dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
-    logmel_kernel<<<grid, kMelThreads, h->smem, h->stream>>>(a);
-    MCK(cudaGetLastError());
+    MCK(mel_dispatch(h->log2n, [&](auto tag) {
+        logmel_kernel<decltype(tag)::value><<<grid, kMelThreads, h->smem, h->stream>>>(a);
+        return cudaGetLastError();
+    }));
     if (!out_dev) MCK(cudaMemcpyAsync(mel, d_o, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     MCK(cudaStreamSynchronize(h->stream));
     return HFG_OK;
@@ -492,20 +549,29 @@ int hfg_griffin_lim(hfg_logmel* h, const float* mag, const float* angles0, int32
     a.mag = d_mag; a.angles = d_ang; a.prev = d_prev; a.y_acc = d_yacc; a.y = d_y; a.wss = d_wss;
     a.window = h->d_window; a.twiddle = h->d_twiddle;
     a.T = T; a.n_fft = n; a.log2n = h->log2n; a.hop = hop; a.N = N; a.mom = 0.f;
-    const size_t smem_i = (size_t)(4 * n + n + (kFramesPerCta - 1) * hop) * sizeof(float);
-    const size_t smem_s = (size_t)(4 * n) * sizeof(float);
-    if (smem_i > 48 * 1024) GCK(cudaFuncSetAttribute(gl_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
-    if (smem_s > 48 * 1024) GCK(cudaFuncSetAttribute(gl_stft_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    const size_t smem_i = (size_t)(2 * fft_padded_len(n) + 3 * n + n + (kFramesPerCta - 1) * hop) * sizeof(float);
+    const size_t smem_s = (size_t)(2 * fft_padded_len(n) + 3 * n) * sizeof(float);
+    if (smem_i > 48 * 1024) GCK(mel_dispatch(h->log2n, [&](auto tag) {
+        return cudaFuncSetAttribute(gl_istft_kernel<decltype(tag)::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i);
+    }));
+    if (smem_s > 48 * 1024) GCK(mel_dispatch(h->log2n, [&](auto tag) {
+        return cudaFuncSetAttribute(gl_stft_update_kernel<decltype(tag)::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+    }));
     const dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
     const dim3 ngrid((unsigned)std::min<size_t>(((size_t)N + 255) / 256, 1024), B);
     for (int it = 0; it <= n_iter; ++it) {
         GCK(cudaMemsetAsync(d_yacc, 0, (size_t)B * ylen * sizeof(float), st));
-        gl_istft_kernel<<<grid, kMelThreads, smem_i, st>>>(a);
+        GCK(mel_dispatch(h->log2n, [&](auto tag) {
+            gl_istft_kernel<decltype(tag)::value><<<grid, kMelThreads, smem_i, st>>>(a);
+            return cudaGetLastError();
+        }));
         gl_norm_kernel<<<ngrid, 256, 0, st>>>(a);
         if (it == n_iter) break;                                            // the last inverse transform is the result
         a.mom = it == 0 ? 0.f : momentum / (1.0f + momentum);
-        gl_stft_update_kernel<<<grid, kMelThreads, smem_s, st>>>(a);
-        GCK(cudaGetLastError());
+        GCK(mel_dispatch(h->log2n, [&](auto tag) {
+            gl_stft_update_kernel<decltype(tag)::value><<<grid, kMelThreads, smem_s, st>>>(a);
+            return cudaGetLastError();
+        }));
     }
     GCK(cudaGetLastError());
     GCK(cudaMemcpyAsync(audio, d_y, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, st));
