@@ -353,6 +353,8 @@ struct hfg_logmel {
     float* d_audio = nullptr;    // staging for host pointers
     float* d_out = nullptr;
     size_t audio_cap = 0, out_cap = 0;
+    char* d_gl = nullptr;        // Griffin-Lim workspace (one grow-only allocation: cudaMalloc / cudaFree per call cost more than the iteration)
+    size_t gl_cap = 0;
     size_t smem = 0;
     int n_weights = 0;
 };
@@ -448,7 +450,7 @@ void hfg_logmel_destroy(hfg_logmel* h) {
     if (!h) return;
     MelDeviceGuard guard(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_band); cudaFree(h->d_weights); cudaFree(h->d_audio); cudaFree(h->d_out);
+    cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_band); cudaFree(h->d_weights); cudaFree(h->d_audio); cudaFree(h->d_out); cudaFree(h->d_gl);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -524,21 +526,30 @@ int hfg_griffin_lim(hfg_logmel* h, const float* mag, const float* angles0, int32
             for (int i = 0; i < n; ++i) acc[(size_t)t * hop + i] += w2[i];
         for (size_t i = 0; i < ylen; ++i) wss[i] = (float)acc[i];
     }
-    float *d_mag_cf = nullptr, *d_mag = nullptr, *d_yacc = nullptr, *d_y = nullptr, *d_wss = nullptr;
-    float2 *d_ang = nullptr, *d_prev = nullptr;
-    auto release = [&]() { cudaFree(d_mag_cf); cudaFree(d_mag); cudaFree(d_yacc); cudaFree(d_y); cudaFree(d_wss); cudaFree(d_ang); cudaFree(d_prev); };
 #define GCK(expr)                                                                                                       \
     do {                                                                                                                \
         cudaError_t _e = (expr);                                                                                        \
-        if (_e != cudaSuccess) { release(); return mel_fail(HFG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } \
+        if (_e != cudaSuccess) return mel_fail(HFG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
     } while (0)
-    GCK(cudaMalloc(&d_mag_cf, nspec * sizeof(float)));
-    GCK(cudaMalloc(&d_mag, nspec * sizeof(float)));
-    GCK(cudaMalloc(&d_ang, nspec * sizeof(float2)));
-    GCK(cudaMalloc(&d_prev, nspec * sizeof(float2)));
-    GCK(cudaMalloc(&d_yacc, (size_t)B * ylen * sizeof(float)));
-    GCK(cudaMalloc(&d_y, (size_t)B * N * sizeof(float)));
-    GCK(cudaMalloc(&d_wss, ylen * sizeof(float)));
+    // workspace: | mag (librosa layout) | mag (frame-major) | angles | prev | y_acc | y | wss |, each 256-byte aligned
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_mag_cf = 0, o_mag = o_mag_cf + al(nspec * sizeof(float)), o_ang = o_mag + al(nspec * sizeof(float));
+    const size_t o_prev = o_ang + al(nspec * sizeof(float2)), o_yacc = o_prev + al(nspec * sizeof(float2));
+    const size_t o_y = o_yacc + al((size_t)B * ylen * sizeof(float)), o_wss = o_y + al((size_t)B * N * sizeof(float));
+    const size_t need = o_wss + al(ylen * sizeof(float));
+    if (need > h->gl_cap) {
+        GCK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_gl); h->d_gl = nullptr; h->gl_cap = 0;
+        GCK(cudaMalloc(&h->d_gl, need));
+        h->gl_cap = need;
+    }
+    float* d_mag_cf = reinterpret_cast<float*>(h->d_gl + o_mag_cf);
+    float* d_mag = reinterpret_cast<float*>(h->d_gl + o_mag);
+    float2* d_ang = reinterpret_cast<float2*>(h->d_gl + o_ang);
+    float2* d_prev = reinterpret_cast<float2*>(h->d_gl + o_prev);
+    float* d_yacc = reinterpret_cast<float*>(h->d_gl + o_yacc);
+    float* d_y = reinterpret_cast<float*>(h->d_gl + o_y);
+    float* d_wss = reinterpret_cast<float*>(h->d_gl + o_wss);
     cudaStream_t st = h->stream;
     GCK(cudaMemcpyAsync(d_mag_cf, mag, nspec * sizeof(float), cudaMemcpyHostToDevice, st));
     GCK(launch_transpose_cf_to_cl(d_mag_cf, d_mag, B, nbins, T, st));     // [B][nbins][T] (librosa layout) -> frame-major [B][T][nbins]
@@ -577,7 +588,6 @@ int hfg_griffin_lim(hfg_logmel* h, const float* mag, const float* angles0, int32
     GCK(cudaMemcpyAsync(audio, d_y, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
 #undef GCK
-    release();
     return HFG_OK;
 }
 

@@ -51,7 +51,6 @@ def griffin_lim(mag: np.ndarray, n_iter: int = 60, hop_length: int = 256, win_le
     import ctypes
 
     from . import _abi
-    from .mel import LogMel
 
     m = np.asarray(mag, dtype=np.float32)
     squeeze = m.ndim == 2
@@ -74,12 +73,24 @@ def griffin_lim(mag: np.ndarray, n_iter: int = 60, hop_length: int = 256, win_le
     a0 = np.ascontiguousarray(np.transpose(a0, (0, 2, 1)))                     # frame-major [B][T][nbins] (re, im) pairs
     m = np.ascontiguousarray(m)
     out = np.empty((B, hop_length * (T - 1)), dtype=np.float32)
-    fe = LogMel(sample_rate, n_fft, hop_length, win_length, device=device)
-    try:
-        _abi.check(fe._lib.hfg_griffin_lim(fe._h, m.ctypes.data, a0.ctypes.data, B, T, int(n_iter), float(momentum), out.ctypes.data))
-    finally:
-        fe.close()
+    fe = _handle(sample_rate, n_fft, hop_length, win_length, device)
+    _abi.check(fe._lib.hfg_griffin_lim(fe._h, m.ctypes.data, a0.ctypes.data, B, T, int(n_iter), float(momentum), out.ctypes.data))
     return out[0] if squeeze else out
+
+
+_HANDLES: dict = {}
+
+
+def _handle(sample_rate: int, n_fft: int, hop_length: int, win_length: int, device: int):
+    """One STFT handle (tables, stream, grow-only workspace) per geometry and device, kept for the life of the process: creating and
+    freeing device memory per call costs more than the 60 iterations do."""
+    from .mel import LogMel
+
+    key = (int(sample_rate), int(n_fft), int(hop_length), int(win_length), int(device))
+    fe = _HANDLES.get(key)
+    if fe is None or not fe._h.value:
+        fe = _HANDLES[key] = LogMel(sample_rate, n_fft, hop_length, win_length, device=device)
+    return fe
 
 
 def griffin_lim_from_log_mel(log_mel: np.ndarray, sample_rate: int = 22050, hop_length: int = 256, n_fft: int = 1024,
