@@ -22,8 +22,13 @@ Restated from librosa's published source:
 
 The random phases are an INPUT here (the caller draws them), so the CUDA kernels can be compared with this oracle on identical
 phases.  ``mel_to_stft`` solves a non-negative least-squares problem with L-BFGS-B in librosa; ``mel_to_linear`` below is the
-pseudo-inverse-and-clip projection the product uses instead -- stated, not a restatement of librosa's solver.  **Parity unpinned
-against librosa** (nothing to execute); the pin is kernel-vs-this-oracle.
+pseudo-inverse-and-clip projection the product uses instead -- stated, not a restatement of librosa's solver.
+
+Pinning (tests/test_logmel_cpu.py): ``stft`` equals ``transformers.audio_utils.spectrogram`` (1e-6); ``istft(stft(y)) == y`` (1e-12);
+the whole recursion equals ``torchaudio.functional.griffinlim`` (an independent implementation of the same fast Griffin-Lim; zero
+start phases on both sides) to 1e-12 after 0, 1 and 3 iterations wherever torchaudio's REFLECT-padded re-analysis has not arrived
+from the edges (librosa 0.11 pads with zeros, as here).  **Unpinned against librosa's own bytes** (nothing to execute), and
+``mel_to_linear`` is unpinned by construction.
 """
 from __future__ import annotations
 

@@ -84,3 +84,33 @@ def test_griffinlim_oracle_transforms_are_consistent():
     out = G.griffinlim(S, ang, n_iter=20)
     assert out.shape == y.shape
     assert np.abs(np.abs(G.stft(out)) - S).mean() < 0.35 * err0
+
+
+def test_oracles_against_torchaudio():
+    """A second independent implementation (torchaudio 2.11, the one audio library this image has).  Log-mel: its MelSpectrogram
+    with librosa's conventions (slaney scale and norm, power 1, constant padding) -- its filterbank is float32, hence 1e-6.
+    Griffin-Lim: torchaudio.functional.griffinlim is the same fast-Griffin-Lim recursion (momentum / (1 + momentum), 1e-16 in the
+    normalisation) but re-analyses with REFLECT padding where librosa 0.11 pads with zeros, so the two agree exactly only where the
+    edge has not arrived yet: 4 frames per iteration from either end.  Zero start phases (rand_init=False) on both sides."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    from oracle import griffinlim_oracle as G
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal(22050) * 0.1
+    ms = torchaudio.transforms.MelSpectrogram(sample_rate=22050, n_fft=1024, win_length=1024, hop_length=256, f_min=0.0, f_max=8000.0,
+                                              n_mels=80, power=1.0, center=True, pad_mode="constant", norm="slaney", mel_scale="slaney").double()
+    np.testing.assert_allclose(LO.mel_linear(y), ms(torch.from_numpy(y)).numpy(), atol=2e-6)
+    np.testing.assert_allclose(LO.mel_filterbank(22050, 1024, 80, 0.0, 8000.0), ms.mel_scale.fb.numpy().T, atol=2e-7)
+
+    y = rng.standard_normal(256 * 59) * 0.1
+    S = np.abs(G.stft(y))
+    win = torch.hann_window(1024, periodic=True, dtype=torch.float64)
+    for n_iter in (0, 1, 3):
+        mine = G.griffinlim(S, np.ones(S.shape, dtype=complex), n_iter=n_iter)
+        ta = torchaudio.functional.griffinlim(torch.from_numpy(S), win, 1024, 256, 1024, power=1.0, n_iter=n_iter, momentum=0.99,
+                                              length=None, rand_init=False).numpy()
+        assert mine.shape == ta.shape
+        inner = slice(256 * 20, 256 * 38)
+        np.testing.assert_allclose(mine[inner], ta[inner], atol=1e-12)
+        if n_iter == 0:
+            np.testing.assert_allclose(mine, ta, atol=1e-12)      # no re-analysis yet: no padding difference
