@@ -108,7 +108,9 @@ int hfg_layer_name(const hfg_engine* e, int index, char* buf, size_t buflen);
 /* Repack + upload; every layer must have been set. */
 int hfg_finalize(hfg_engine* e);
 
-/* mel [B][in_channels][T] fp32 -> wave [B][T*hop] fp32. */
+/* mel [B][in_channels][T] fp32 -> wave [B][T*hop] fp32.
+ * Limits (HFG_ERR_UNSUPPORTED beyond them, nothing launched): B <= 65535; a stage's per-item plane < 2^31 elements, which for
+ * the V1 generator means T < 262144 frames per call -- longer input is synthesized in chunks (receptive field: 15 frames). */
 int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wave,
                 int32_t precision, uint32_t flags);
 int hfg_sync(hfg_engine* e);

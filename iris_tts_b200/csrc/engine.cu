@@ -1180,8 +1180,25 @@ int hfg_finalize(hfg_engine* e) {
 
 int32_t hfg_hop(const hfg_engine* e) { return e ? e->hop : 0; }
 
+// The kernels index one batch item's plane ([L][C], at most 2 planes) with 32-bit element offsets and put the batch on a grid axis
+// (<= 65535): refuse what would wrap instead of computing garbage.  V1: T < 262144 frames (50 minutes) per call -- long-form input
+// goes through sharding.synthesize_longform / synthesize_streaming in chunks long before that.
+static int check_sizes(const hfg_engine* e, int B, int T) {
+    if (B > 65535) return fail(HFG_ERR_UNSUPPORTED, "batch larger than 65535: split it");
+    long long L = T, worst = (long long)T * std::max(e->cfg.in_channels, 32);
+    int ch = e->cfg.upsample_initial_channel;
+    worst = std::max(worst, L * ch);
+    for (int i = 0; i < e->cfg.num_upsamples; ++i) {
+        L *= e->cfg.upsample_rates[i];
+        ch /= 2;
+        worst = std::max(worst, L * std::max(ch, 32));
+    }
+    if (worst >= (1ll << 31)) return fail(HFG_ERR_UNSUPPORTED, "T too large for one call (a stage's per-item plane exceeds 2^31 elements): synthesize in chunks");
+    return HFG_OK;
+}
+
 size_t hfg_workspace_bytes(const hfg_engine* e, int32_t B, int32_t T, int32_t precision) {
-    if (!e || B <= 0 || T <= 0 || check_prec(precision) != HFG_OK) return 0;
+    if (!e || B <= 0 || T <= 0 || check_prec(precision) != HFG_OK || check_sizes(e, B, T) != HFG_OK) return 0;
     size_t bytes = 0;
     if (build_plan(const_cast<hfg_engine*>(e), B, T, precision, false, nullptr, nullptr, &bytes) != HFG_OK) return 0;
     return bytes;
@@ -1235,6 +1252,7 @@ int hfg_sync(hfg_engine* e) {
 int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wave, int32_t precision, uint32_t flags) {
     if (!e || !mel || !wave) return fail(HFG_ERR_INVALID, "hfg_forward: null argument");
     if (B <= 0 || T <= 0) return fail(HFG_ERR_INVALID, "hfg_forward: B and T must be positive");
+    RET(check_sizes(e, B, T));
     RET(check_prec(precision));
     if (!e->finalized) return fail(HFG_ERR_STATE, "hfg_forward: call hfg_finalize first");
     const bool mel_dev = flags & HFG_MEL_ON_DEVICE, wave_dev = flags & HFG_WAVE_ON_DEVICE;

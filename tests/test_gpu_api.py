@@ -241,3 +241,23 @@ def test_cli_copy_synthesis_from_a_wav(loud_ckpt, tmp_path):
     assert cli.main(["--audio_wav", str(src), "--output_wav", str(out), "--checkpoint", str(loud_ckpt)]) == 0
     with wave.open(str(out)) as w:
         assert w.getframerate() == 22050 and w.getnframes() == (1 + n // 256) * 256
+
+
+def test_oversized_calls_are_refused_not_wrapped():
+    """32-bit indexing inside the kernels: a call whose per-item plane would exceed 2^31 elements (V1: T >= 262144 frames), or a
+    batch beyond the grid axis, fails with HFG_ERR_UNSUPPORTED before anything is allocated or launched."""
+    import ctypes
+    import iris.hifigan_pretrained as hp
+    from iris_tts_b200 import _abi
+    m = hp.HiFiGANModel()
+    m.to("cuda:0")
+    eng = m.engine
+    lib = _abi.load()
+    assert lib.hfg_workspace_bytes(eng._h, 1, 262144, _abi.PREC_BF16) == 0
+    assert lib.hfg_workspace_bytes(eng._h, 1, 1000, _abi.PREC_BF16) > 0
+    dummy = (ctypes.c_float * 4)()
+    rc = lib.hfg_forward(eng._h, ctypes.cast(dummy, ctypes.c_void_p), 70000, 4, ctypes.cast(dummy, ctypes.c_void_p), _abi.PREC_BF16, 0)
+    assert rc == _abi.ERR_UNSUPPORTED, rc
+    rc = lib.hfg_forward(eng._h, ctypes.cast(dummy, ctypes.c_void_p), 1, 300000, ctypes.cast(dummy, ctypes.c_void_p), _abi.PREC_BF16, 0)
+    assert rc == _abi.ERR_UNSUPPORTED, rc
+    assert b"chunks" in lib.hfg_last_error()
