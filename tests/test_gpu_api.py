@@ -261,3 +261,41 @@ def test_oversized_calls_are_refused_not_wrapped():
     rc = lib.hfg_forward(eng._h, ctypes.cast(dummy, ctypes.c_void_p), 1, 300000, ctypes.cast(dummy, ctypes.c_void_p), _abi.PREC_BF16, 0)
     assert rc == _abi.ERR_UNSUPPORTED, rc
     assert b"chunks" in lib.hfg_last_error()
+
+
+def test_two_engines_driven_from_two_threads_concurrently():
+    """A handle is not thread-safe, but two handles are independent: each owns its stream, arena, plans and graphs, and the
+    library's only process-wide state is the thread-local error string and idempotent one-time kernel attributes.  Two
+    threads (ctypes drops the GIL during the calls) run 30 forwards each, different shapes and modes, while the other is
+    running; every result equals the one the same engine gave when it ran alone."""
+    import threading
+    import iris.hifigan_pretrained as hp
+    rng = np.random.default_rng(5)
+    jobs = []
+    for seed, (B, T, mode) in enumerate([(3, 211, "bf16x3"), (2, 333, "fp16")]):
+        torch.manual_seed(seed)
+        m = hp.HiFiGANModel()
+        m.to("cuda:0")
+        mel = rng.standard_normal((B, 80, T)).astype(np.float32)
+        alone = m.engine.forward(mel, precision=mode)
+        jobs.append((m, mel, mode, alone))
+    errors = []
+    start = threading.Barrier(2)
+
+    def run(m, mel, mode, alone):
+        try:
+            start.wait()
+            for _ in range(30):
+                got = m.engine.forward(mel, precision=mode)
+                if not np.array_equal(got, alone):
+                    errors.append(f"{mode}: differs from the solo run by {np.abs(got - alone).max():.3e}")
+                    return
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=run, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
