@@ -11,6 +11,7 @@ import ctypes
 import dataclasses
 import logging
 import os
+import threading
 import re
 from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
 
@@ -119,6 +120,19 @@ def canonical_key(key: str) -> Optional[Tuple[str, str]]:
     return (m.group(1), m.group(2)) if m else None
 
 
+def _locked(fn):
+    """A handle (stream, arena, plan cache, staging buffers) serves one call at a time: calls from several threads on ONE engine queue
+    up here instead of corrupting it (the reference's torch module tolerates concurrent callers of its singleton vocoder,
+    hifigan_pretrained.py:245-283, so a drop-in must too).  Two engines do run concurrently."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self._lock:
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class Engine:
     """One generator instance on one CUDA device."""
 
@@ -132,6 +146,7 @@ class Engine:
         self.hop = int(self._lib.hfg_hop(self._h))
         self._finalized = False
         self._pin_in = None
+        self._lock = threading.RLock()
         self._layer_names = [n for n, *_ in config.layer_specs()]
 
     # -- lifetime -----------------------------------------------------------
@@ -157,6 +172,7 @@ class Engine:
         _abi.check(self._lib.hfg_layer_shape(self._h, name.encode(), ctypes.byref(dims), ctypes.byref(tr)))
         return (dims[0], dims[1], dims[2]), bool(tr.value)
 
+    @_locked
     def load_state_dict(self, state_dict: Mapping[str, object], strict: bool = False) -> Tuple[List[str], List[str]]:
         """Accepts the reference's keys (``<layer>.weight_g/.weight_v/.bias``), already-folded
         ``<layer>.weight``, and speechbrain's ``<layer>.conv.*`` aliases.  Weight-norm is folded
@@ -199,11 +215,13 @@ class Engine:
         self._finalized = False
         return missing, unexpected
 
+    @_locked
     def finalize(self) -> None:
         _abi.check(self._lib.hfg_finalize(self._h))
         self._finalized = True
 
     # -- compute ------------------------------------------------------------
+    @_locked
     def forward_ptr(self, mel_ptr: int, B: int, T: int, wave_ptr: int, precision: str = "fp32", *, mel_on_device=False,
                     wave_on_device=False, keep_taps=False, sync=True) -> None:
         """Raw-pointer forward: mel [B][in_channels][T] fp32 -> wave [B][T*hop] fp32."""
@@ -212,6 +230,7 @@ class Engine:
         _abi.check(self._lib.hfg_forward(self._h, ctypes.c_void_p(mel_ptr), B, T, ctypes.c_void_p(wave_ptr),
                                          _abi.PRECISIONS[precision], flags))
 
+    @_locked
     def forward(self, mel: np.ndarray, precision: str = "fp32", keep_taps: bool = False, pinned: bool = True) -> np.ndarray:
         """numpy [B, in_channels, T] (any float dtype) -> new float32 numpy [B, T*hop].
 
@@ -257,9 +276,11 @@ class Engine:
         self.forward_ptr(m.ctypes.data, B, T, out.ctypes.data, precision, keep_taps=keep_taps)
         return out
 
+    @_locked
     def sync(self) -> None:
         _abi.check(self._lib.hfg_sync(self._h))
 
+    @_locked
     def run_layer(self, name: str, x: np.ndarray, pre_lrelu: bool = False, precision: str = "fp32") -> np.ndarray:
         """One F.conv1d / F.conv_transpose1d of the forward in isolation (reference layouts, host arrays)."""
         (d0, d1, k), tr = self.layer_shape(name)
@@ -279,6 +300,7 @@ class Engine:
                                            _abi.PRECISIONS[precision]))
         return y
 
+    @_locked
     def run_pair(self, resblock: int, m: int, x: np.ndarray, precision: str = "bf16x3", mrf_sum: Optional[np.ndarray] = None,
                  out_scale: float = 1.0):
         """One ResBlock step x + c2(lrelu(c1(lrelu(x)))) (hifigan_pretrained.py:66-70) in isolation; returns (y, fused).
@@ -300,6 +322,7 @@ class Engine:
                                               _abi.PRECISIONS[precision], ctypes.byref(fused)))
         return y, bool(fused.value)
 
+    @_locked
     def get_tap(self, name: str, shape: Optional[Sequence[int]] = None) -> np.ndarray:
         n = ctypes.c_size_t(0)
         _abi.check(self._lib.hfg_get_tap(self._h, name.encode(), None, ctypes.byref(n)))
@@ -308,9 +331,11 @@ class Engine:
         return out.reshape(shape) if shape is not None else out
 
     # -- per-launch timing ---------------------------------------------------
+    @_locked
     def profile(self, on: bool = True) -> None:
         _abi.check(self._lib.hfg_profile_enable(self._h, int(on)))
 
+    @_locked
     def profile_records(self) -> List[Dict[str, object]]:
         """Launches since profile(True): layer, kernel family, device ms, algorithmic flop and bytes."""
         out = []

@@ -74,7 +74,8 @@ def griffin_lim(mag: np.ndarray, n_iter: int = 60, hop_length: int = 256, win_le
     m = np.ascontiguousarray(m)
     out = np.empty((B, hop_length * (T - 1)), dtype=np.float32)
     fe = _handle(sample_rate, n_fft, hop_length, win_length, device)
-    _abi.check(fe._lib.hfg_griffin_lim(fe._h, m.ctypes.data, a0.ctypes.data, B, T, int(n_iter), float(momentum), out.ctypes.data))
+    with fe._lock:
+        _abi.check(fe._lib.hfg_griffin_lim(fe._h, m.ctypes.data, a0.ctypes.data, B, T, int(n_iter), float(momentum), out.ctypes.data))
     return out[0] if squeeze else out
 
 

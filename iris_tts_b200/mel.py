@@ -10,6 +10,7 @@ librosa 0.11.0 algorithm, pinned against ``transformers.audio_utils``) in tests/
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -28,6 +29,7 @@ class LogMel:
         cfg = _abi.HfgLogmelConfig(sample_rate, n_fft, hop_length, win_length, n_mels, float(fmin),
                                    float(fmax) if fmax is not None else 0.0, float(clip), int(log_output))
         self.n_mels, self.hop_length = n_mels, hop_length
+        self._lock = threading.RLock()   # one call at a time per handle (stream, staging buffers)
         self._h = ctypes.c_void_p()
         _abi.check(self._lib.hfg_logmel_create(ctypes.byref(cfg), int(device), ctypes.byref(self._h)))
 
@@ -50,12 +52,14 @@ class LogMel:
         a = np.ascontiguousarray(audio, dtype=np.float32)
         B, N = a.shape
         out = np.empty((B, self.n_mels, self.frames(N)), dtype=np.float32)
-        _abi.check(self._lib.hfg_logmel_forward(self._h, a.ctypes.data, B, N, out.ctypes.data, 0))
+        with self._lock:
+            _abi.check(self._lib.hfg_logmel_forward(self._h, a.ctypes.data, B, N, out.ctypes.data, 0))
         return out
 
     def forward_ptr(self, audio_ptr: int, B: int, N: int, out_ptr: int, audio_on_device: bool = True, out_on_device: bool = True) -> None:
         flags = (_abi.LOGMEL_AUDIO_ON_DEVICE if audio_on_device else 0) | (_abi.LOGMEL_OUT_ON_DEVICE if out_on_device else 0)
-        _abi.check(self._lib.hfg_logmel_forward(self._h, ctypes.c_void_p(audio_ptr), B, N, ctypes.c_void_p(out_ptr), flags))
+        with self._lock:
+            _abi.check(self._lib.hfg_logmel_forward(self._h, ctypes.c_void_p(audio_ptr), B, N, ctypes.c_void_p(out_ptr), flags))
 
 
 def compute_mel_spectrogram(audio: np.ndarray, sample_rate: int = 22050, n_fft: int = 1024, hop_length: int = 256,

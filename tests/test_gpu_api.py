@@ -299,3 +299,43 @@ def test_two_engines_driven_from_two_threads_concurrently():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_one_vocoder_called_from_several_threads():
+    """The reference's singleton vocoder is a torch module: concurrent callers (a threaded server) are fine there.  Here a handle
+    serves one call at a time, so the Python layer queues concurrent callers of ONE engine (engine.py:_locked); every thread gets
+    the result it would have got alone, for different shapes at once (plan cache, arena growth and staging buffers are shared)."""
+    import threading
+    import iris.hifigan_pretrained as hp
+    torch.manual_seed(3)
+    m = hp.HiFiGANModel()
+    m.to("cuda:0")
+    m.precision = "bf16x3"
+    rng = np.random.default_rng(9)
+    mels = [rng.standard_normal((b, 80, t)).astype(np.float32) for b, t in ((1, 97), (3, 160), (2, 233), (1, 311))]
+    alone = [m.engine.forward(x, precision="bf16x3") for x in mels]
+    from iris_tts_b200.mel import compute_mel_spectrogram
+    audio = (rng.standard_normal(22050) * 0.1).astype(np.float32)
+    mel_alone = compute_mel_spectrogram(audio)
+    errors = []
+    start = threading.Barrier(len(mels))
+
+    def run(i):
+        try:
+            start.wait()
+            for _ in range(15):
+                if not np.array_equal(m.engine.forward(mels[i], precision="bf16x3"), alone[i]):
+                    errors.append(f"thread {i}: vocoder output differs")
+                    return
+                if not np.array_equal(compute_mel_spectrogram(audio), mel_alone):
+                    errors.append(f"thread {i}: log-mel differs")
+                    return
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(mels))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
