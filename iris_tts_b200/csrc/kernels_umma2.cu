@@ -579,6 +579,7 @@ bool umma2_supported(const UmmaConvParams& p) {
     } else {   // polyphase upsampler with k = 2s (two taps, pad = s/2) whose whole N = s*C_out fits one tile
         if (env_i("HFG_U2_UPS", 1) == 0) return false;
         if (g.taps != 2 || g.tap_off0 != 0 || g.tap_step != -1 || g.ups_s % 2 != 0 || g.ups_p * 2 != g.ups_s) return false;
+        if (g.Cout > 256) return false;   // the bias of a column tile is staged as bias_s[n0 % C_out + c], 256 entries (generators with c0 >= 1024: first-generation kernel)
         if (g.Np != g.ups_s * g.Cout || g.Np % 64 != 0 || p.res_hi) return false;   // halves of <= 64 columns, or
         if (g.Np > 128 && (g.Np % 256 != 0 || env_i("HFG_U2_UPS_WIDE", 1) == 0)) return false;   // wide: 128-column tiles, each inside one half
     }

@@ -321,3 +321,53 @@ def test_random_architectures_match_the_oracle(seed):
             err = float(np.abs(out - ref).max())
             assert err <= e2e_tol(mode, ref), f"{cfg} B={B} T={T} {mode}: {err:.3e} > {e2e_tol(mode, ref):.3e} (std {ref.std():.3f})"
     eng.close()
+
+
+ODD_CONFIGS = {
+    "128 mel channels": (128, (8, 8, 2, 2), (16, 16, 4, 4), 512, (3, 7, 11), ((1, 3, 5),) * 3),
+    "rates 5,4,4,2,2 with kernels 11,8,8,4,4": (80, (5, 4, 4, 2, 2), (11, 8, 8, 4, 4), 512, (3, 7, 11), ((1, 3, 5),) * 3),
+    "upsample kernel = rate": (80, (4, 4), (4, 4), 128, (3, 5), ((1, 2), (1, 2))),
+    "upsample kernel = 3 x rate": (80, (4, 4), (12, 12), 128, (3, 5), ((1, 2), (1, 2))),
+    "rate 3 with kernel 7": (80, (3, 2), (7, 4), 128, (3,), ((1, 3),)),
+    "13-tap ResBlock with dilation 7": (80, (8, 4), (16, 8), 128, (13,), ((1, 7),)),
+    "one upsampler": (80, (8,), (16,), 64, (3, 7), ((1, 3), (1, 3))),
+    "1024 initial channels (C = 512 ResBlocks, 1024 -> 512 upsampler)": (80, (8, 8, 2, 2), (16, 16, 4, 4), 1024, (3, 7, 11), ((1, 3, 5),) * 3),
+    "2048 initial channels": (80, (4, 4, 2, 2), (8, 8, 4, 4), 2048, (3,), ((1, 3),)),
+}
+
+
+@pytest.mark.parametrize("name", list(ODD_CONFIGS))
+def test_constructor_arguments_outside_the_named_generators(name):
+    """The reference builds whatever its constructor is given (hifigan_pretrained.py:77-121).  Configurations no named generator
+    uses -- odd upsampling rates, kernels that are not twice the rate, other mel widths, very wide first stages (which leave the
+    persistent kernel's limits and run on the first-generation one) -- against the oracle in every mode, loud weights.
+    (Found by this test: the wide polyphase upsampler read its bias tile out of bounds for C_out > 256.)"""
+    from iris_tts_b200 import Engine
+    from iris_tts_b200.engine import GeneratorConfig
+    cfg = GeneratorConfig(*ODD_CONFIGS[name])
+    ocfg = O.OracleConfig(cfg.in_channels, cfg.upsample_rates, cfg.upsample_kernel_sizes, cfg.upsample_initial_channel,
+                          cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes)
+    sd = O.random_state_dict(ocfg, seed=1, loud=True)
+    eng = Engine(cfg, 0)
+    eng.load_state_dict(sd, strict=True)
+    eng.finalize()
+    mel = np.random.default_rng(3).standard_normal((2, cfg.in_channels, 45)).astype(np.float32)
+    ref = O.infer(sd, mel, ocfg)
+    for mode in ("fp32", "bf16x3", "fp16", "bf16"):
+        for _ in range(2):
+            out = eng.forward(mel, precision=mode)
+        assert out.shape == ref.shape
+        err = float(np.abs(out - ref).max())
+        assert err <= e2e_tol(mode, ref), f"{name} {mode}: {err:.3e} > {e2e_tol(mode, ref):.3e}"
+    eng.close()
+
+
+def test_unsupported_constructor_arguments_are_refused_with_a_reason():
+    """What the engine does not take, it says so at construction (never a wrong waveform): mel widths that are not a multiple of 8
+    (TMA rows are 16-byte multiples) and final channel counts that are not a power of two in [8, 128]."""
+    from iris_tts_b200 import Engine, _abi
+    from iris_tts_b200.engine import GeneratorConfig
+    for args, word in (((100, (8, 8, 2, 2), (16, 16, 4, 4), 512, (3, 7, 11), ((1, 3, 5),) * 3), "multiple of 8"),
+                       ((80, (8, 8, 2, 2), (16, 16, 4, 4), 384, (3, 7, 11), ((1, 3, 5),) * 3), "power of two")):
+        with pytest.raises(_abi.HfgError, match=word):
+            Engine(GeneratorConfig(*args), 0)
