@@ -51,18 +51,41 @@ def length_buckets(lengths: Sequence[int], max_pad: float = 0.15, max_batch: Opt
     return buckets
 
 
-def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Sequence[np.ndarray], hop: int = 256,
-                        halo: int = HALO_FRAMES, max_pad: float = 0.15, max_batch: Optional[int] = None,
+def _generator_config(vocoder):
+    """The GeneratorConfig behind a vocoder object of this package (HiFiGANGenerator, HiFiGANVocoder, HiFiGANModel, Engine), or None."""
+    for path in (("model", "engine", "config"), ("engine", "config"), ("model", "config"), ("config",)):
+        obj = vocoder
+        for name in path:
+            obj = getattr(obj, name, None)
+            if obj is None:
+                break
+        if obj is not None and hasattr(obj, "upsample_rates") and hasattr(obj, "resblock_kernel_sizes"):
+            return obj
+    return None
+
+
+def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Sequence[np.ndarray], hop: Optional[int] = None,
+                        halo: Optional[int] = None, max_pad: float = 0.15, max_batch: Optional[int] = None,
                         stats: Optional[dict] = None, length_quantum: int = 1) -> List[np.ndarray]:
     """``mels``: list of [n_mels, T_i] arrays -> list of [T_i * hop] float32 waveforms (same order), each equal to what
     ``vocoder(mel_i[None])[0]`` returns.  ``vocoder`` maps [B, n_mels, T] -> [B, T * hop] (e.g. ``get_pretrained_hifigan(...)``);
-    ``halo`` must cover the generator's receptive field (``sharding.halo_frames(config)``).  ``stats`` (optional dict) receives
+    ``halo`` must cover the generator's receptive field and ``hop`` is its samples per frame: both are read from the vocoder's
+    own configuration when it is one of this package's objects (``sharding.halo_frames(config)``: 15 for V1), else they default to
+    the V1 values (16 frames, 256 samples) -- pass them for any other generator behind a plain callable.  ``stats`` (optional dict) receives
     the number of dense calls and the padded / real frame counts.  ``length_quantum`` > 1 rounds every bucket's padded length up
     to a multiple of it: a serving loop then meets a handful of (batch, frames) shapes again and again, and the engine's per-shape
     launch plans and CUDA graphs are reused instead of rebuilt (the padding is exact for the same reason the bucket padding is)."""
     for m in mels:
         if m.ndim != 2:
             raise ValueError(f"each mel must be [n_mels, T], got {m.shape}")
+    if halo is None or hop is None:
+        from .sharding import halo_frames
+
+        cfg = _generator_config(vocoder)
+        if halo is None:
+            halo = max(1, halo_frames(cfg)) if cfg is not None else HALO_FRAMES
+        if hop is None:
+            hop = int(np.prod(cfg.upsample_rates)) if cfg is not None else 256
     if halo <= 0:
         raise ValueError("halo must be positive")
     n = len(mels)

@@ -339,3 +339,38 @@ def test_one_vocoder_called_from_several_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_ragged_batching_reads_the_receptive_field_from_the_generator():
+    """synthesize_variable's body / tail split is exact only if its halo covers the generator's receptive field.  For a generator
+    that sees much further than V1 (15-tap ResBlocks with dilation 9 in the first stage: 34 frames instead of 15) the halo and the
+    hop are taken from the vocoder's own configuration; the result equals the per-utterance forwards bit for bit -- and the V1
+    default of 16 frames, forced, does not."""
+    from iris_tts_b200 import Engine
+    from iris_tts_b200.batching import synthesize_variable
+    from iris_tts_b200.engine import GeneratorConfig
+    from iris_tts_b200.sharding import halo_frames
+    cfg = GeneratorConfig(80, (4, 4), (8, 8), 128, (15, 3), ((1, 9), (1, 3)))
+    assert halo_frames(cfg) > 16
+    ocfg = O.OracleConfig(80, cfg.upsample_rates, cfg.upsample_kernel_sizes, 128, cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes)
+    eng = Engine(cfg, 0)
+    eng.load_state_dict(O.random_state_dict(ocfg, seed=4, loud=True), strict=True)
+    eng.finalize()
+
+    class Voc:
+        engine = eng
+
+        def __call__(self, mel):
+            return eng.forward(np.asarray(mel) if np.ndim(mel) == 3 else np.asarray(mel)[None], precision="bf16x3")
+
+    voc = Voc()
+    rng = np.random.default_rng(2)
+    mels = [rng.standard_normal((80, t)).astype(np.float32) for t in (150, 163, 171, 140, 90, 75, 200)]
+    want = [voc(m)[0] for m in mels]
+    got = synthesize_variable(voc, mels)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape == (b.size,) and a.size % 16 == 0
+        np.testing.assert_array_equal(a, b)
+    short = synthesize_variable(voc, mels, halo=16, hop=16)
+    assert any(not np.array_equal(a, b) for a, b in zip(short, want))
+    eng.close()
