@@ -24,7 +24,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .sharding import HALO_FRAMES
+from .sharding import resolve_geometry
 
 
 def group_by_length(lengths: Sequence[int]) -> Dict[int, List[int]]:
@@ -51,19 +51,6 @@ def length_buckets(lengths: Sequence[int], max_pad: float = 0.15, max_batch: Opt
     return buckets
 
 
-def _generator_config(vocoder):
-    """The GeneratorConfig behind a vocoder object of this package (HiFiGANGenerator, HiFiGANVocoder, HiFiGANModel, Engine), or None."""
-    for path in (("model", "engine", "config"), ("engine", "config"), ("model", "config"), ("config",)):
-        obj = vocoder
-        for name in path:
-            obj = getattr(obj, name, None)
-            if obj is None:
-                break
-        if obj is not None and hasattr(obj, "upsample_rates") and hasattr(obj, "resblock_kernel_sizes"):
-            return obj
-    return None
-
-
 def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Sequence[np.ndarray], hop: Optional[int] = None,
                         halo: Optional[int] = None, max_pad: float = 0.15, max_batch: Optional[int] = None,
                         stats: Optional[dict] = None, length_quantum: int = 1) -> List[np.ndarray]:
@@ -78,14 +65,7 @@ def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Seque
     for m in mels:
         if m.ndim != 2:
             raise ValueError(f"each mel must be [n_mels, T], got {m.shape}")
-    if halo is None or hop is None:
-        from .sharding import halo_frames
-
-        cfg = _generator_config(vocoder)
-        if halo is None:
-            halo = max(1, halo_frames(cfg)) if cfg is not None else HALO_FRAMES
-        if hop is None:
-            hop = int(np.prod(cfg.upsample_rates)) if cfg is not None else 256
+    hop, halo = resolve_geometry(vocoder, hop, halo)
     if halo <= 0:
         raise ValueError("halo must be positive")
     n = len(mels)

@@ -14,6 +14,7 @@ frames of input (probed on the reference), so
 from __future__ import annotations
 
 import dataclasses
+import math
 from typing import Callable, List, Optional, Tuple
 
 import numpy as np
@@ -47,6 +48,31 @@ def halo_frames(config) -> int:
     import math
 
     return int(math.ceil(receptive_field_frames(config)))
+
+
+def generator_config(vocoder):
+    """The GeneratorConfig behind a vocoder object of this package (HiFiGANGenerator, HiFiGANVocoder, HiFiGANModel, Engine, or any
+    callable carrying one of them as ``.model`` / ``.engine``), or None for a plain callable."""
+    for path in (("model", "engine", "config"), ("engine", "config"), ("model", "config"), ("config",)):
+        obj = vocoder
+        for name in path:
+            obj = getattr(obj, name, None)
+            if obj is None:
+                break
+        if obj is not None and hasattr(obj, "upsample_rates") and hasattr(obj, "resblock_kernel_sizes"):
+            return obj
+    return None
+
+
+def resolve_geometry(vocoder, hop: Optional[int], halo: Optional[int]) -> Tuple[int, int]:
+    """(hop, halo) for the chunking helpers: what the caller passed, else the vocoder's own configuration (its product of rates and
+    ``halo_frames``), else the V1 values (256 samples, 16 frames) -- a plain callable around another generator must pass them."""
+    cfg = generator_config(vocoder) if (hop is None or halo is None) else None
+    if hop is None:
+        hop = int(math.prod(cfg.upsample_rates)) if cfg is not None else 256
+    if halo is None:
+        halo = max(1, halo_frames(cfg)) if cfg is not None else HALO_FRAMES
+    return int(hop), int(halo)
 
 
 def batch_shards(batch: int, world: int) -> List[Tuple[int, int]]:
@@ -115,26 +141,30 @@ def stream_chunks(frames: int, chunk_frames: int, halo: int = HALO_FRAMES) -> Li
             for s in range(0, frames, chunk_frames)]
 
 
-def synthesize_streaming(synth: Callable, mel, chunk_frames: int, hop: int = 256, halo: int = HALO_FRAMES):
+def synthesize_streaming(synth: Callable, mel, chunk_frames: int, hop: Optional[int] = None, halo: Optional[int] = None):
     """Streaming output on one device: yields the waveform of one long mel [1, C, T] piece by piece (``chunk_frames * hop``
     samples each), every piece synthesised from its frames plus the receptive-field halo.  The concatenation of the pieces is
     the waveform of the whole mel (same halo argument as ``synthesize_longform``); the first audio is available after one
     chunk instead of after the whole utterance.  The reference has no streaming path (hifigan_pretrained.py:208-242 returns
-    the complete array)."""
+    the complete array).  ``hop`` / ``halo``: see ``resolve_geometry``."""
+    hop, halo = resolve_geometry(synth, hop, halo)
     for c in stream_chunks(int(mel.shape[-1]), chunk_frames, halo):
         yield synthesize_chunk(synth, mel, c, hop)
 
 
-def synthesize_longform(synth: Callable, mel, hop: int = 256, group=None, dst: int = 0, halo: int = HALO_FRAMES,
+def synthesize_longform(synth: Callable, mel, hop: Optional[int] = None, group=None, dst: int = 0, halo: Optional[int] = None,
                         all_ranks: bool = False):
     """Time-sharded synthesis of ONE long mel across the ranks of ``group``.
 
     ``mel``: tensor [1, C, T] or [C, T], identical on every rank, on the device ``synth`` computes on.
     Returns the stitched waveform tensor [T*hop] on rank ``dst`` (every rank with ``all_ranks``), ``None`` elsewhere.
     Exactly one collective: ``gather`` (``all_gather`` with ``all_ranks``) of ``ceil(T/world)*hop`` fp32 samples per rank.
+    ``hop`` / ``halo``: see ``resolve_geometry``.
     """
     import torch
     import torch.distributed as dist
+
+    hop, halo = resolve_geometry(synth, hop, halo)
 
     if mel.dim() == 2:
         mel = mel.unsqueeze(0)

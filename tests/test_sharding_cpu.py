@@ -204,3 +204,31 @@ def test_numa_binding_is_a_no_op_without_nvml_or_gpu():
         assert numa.gpu_local_cpus(0) is None and numa.bind_process_to_gpu(0) is None
     assert numa.bind_process_to_gpu(10 ** 6) is None          # no such GPU
     assert os.sched_getaffinity(0) == before
+
+
+def test_chunking_helpers_read_hop_and_halo_from_the_vocoder():
+    """resolve_geometry: explicit arguments win; else the generator configuration found on the vocoder object (as .model.engine.config,
+    .engine.config, .model.config or .config); else the V1 values for a plain callable."""
+    from iris_tts_b200 import sharding
+    from iris_tts_b200.engine import V1, V3, GeneratorConfig
+
+    class Eng:
+        def __init__(self, cfg):
+            self.config = cfg
+
+    class Model:
+        def __init__(self, cfg):
+            self.engine = Eng(cfg)
+
+    class Gen:
+        def __init__(self, cfg):
+            self.model = Model(cfg)
+
+    assert sharding.resolve_geometry(lambda m: m, None, None) == (256, 16)
+    assert sharding.resolve_geometry(lambda m: m, 64, 20) == (64, 20)
+    assert sharding.resolve_geometry(Gen(V1), None, None) == (256, sharding.halo_frames(V1)) == (256, 15)
+    assert sharding.resolve_geometry(Model(V3), None, None) == (256, 13)
+    wide = GeneratorConfig(80, (4, 4), (8, 8), 128, (15, 3), ((1, 9), (1, 3)))
+    hop, halo = sharding.resolve_geometry(Eng(wide), None, None)
+    assert hop == 16 and halo == sharding.halo_frames(wide) > 16
+    assert sharding.resolve_geometry(Eng(wide), None, 40) == (16, 40)
