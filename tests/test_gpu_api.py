@@ -374,3 +374,24 @@ def test_ragged_batching_reads_the_receptive_field_from_the_generator():
     short = synthesize_variable(voc, mels, halo=16, hop=16)
     assert any(not np.array_equal(a, b) for a, b in zip(short, want))
     eng.close()
+
+
+def test_a_batch_that_does_not_fit_fails_cleanly_and_the_engine_lives_on():
+    """A workspace the device cannot hold (4096 x 862 frames in bf16x3: 0.9 TB) comes back as HFG_ERR_NOMEM with a message -- no
+    sticky CUDA error: the next forward on the same engine is correct."""
+    import ctypes
+    import iris.hifigan_pretrained as hp
+    from iris_tts_b200 import _abi
+    torch.manual_seed(0)
+    m = hp.HiFiGANModel()
+    m.to("cuda:0")
+    eng = m.engine
+    lib = _abi.load()
+    assert lib.hfg_workspace_bytes(eng._h, 4096, 862, _abi.PREC_BF16X3) > 500e9
+    dummy = (ctypes.c_float * 4)()
+    p = ctypes.cast(dummy, ctypes.c_void_p)
+    assert lib.hfg_forward(eng._h, p, 4096, 862, p, _abi.PREC_BF16X3, 0) == _abi.ERR_NOMEM
+    assert b"out of memory" in lib.hfg_last_error()
+    mel = O.synthetic_mel(2, 50, seed=8)
+    ref = O.infer({k: v for k, v in m.state_dict().items()}, mel)
+    assert np.abs(eng.forward(mel, precision="bf16x3") - ref).max() <= 1e-3
