@@ -198,7 +198,10 @@ int validate_cfg(const hfg_config& c) {
         return fail(HFG_ERR_INVALID, "config: upsample_initial_channel must be divisible by 2^num_upsamples");
     for (int i = 0; i < c.num_upsamples; ++i) {
         const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
-        if (u <= 0 || k < u || (k - u) % 2 != 0) return fail(HFG_ERR_INVALID, "config: upsample kernel must be >= rate with even difference");
+        if (u <= 0 || k <= 0) return fail(HFG_ERR_INVALID, "config: upsample rates and kernel sizes must be positive");
+        // the reference builds these too (padding = (k - u) // 2, hifigan_pretrained.py:98-104), but their output is not T * hop samples
+        // long (k < u leaves gaps, an odd k - u adds one sample per stage): no generator uses them, and this engine does not take them
+        if (k < u || (k - u) % 2 != 0) return fail(HFG_ERR_UNSUPPORTED, "config: upsample kernel must be >= rate with even difference");
     }
     for (int j = 0; j < c.num_kernels; ++j) {
         if (c.resblock_kernel_sizes[j] <= 0 || c.resblock_kernel_sizes[j] % 2 == 0)

@@ -364,10 +364,12 @@ def test_constructor_arguments_outside_the_named_generators(name):
 
 def test_unsupported_constructor_arguments_are_refused_with_a_reason():
     """What the engine does not take, it says so at construction (never a wrong waveform): mel widths that are not a multiple of 8
-    (TMA rows are 16-byte multiples) and final channel counts that are not a power of two in [8, 128]."""
+    (TMA rows are 16-byte multiples) final channel counts that are not a power of two in [8, 128], and
+    upsamplers whose kernel minus rate is odd (the reference's output would be one sample longer per stage than T * hop)."""
     from iris_tts_b200 import Engine, _abi
     from iris_tts_b200.engine import GeneratorConfig
     for args, word in (((100, (8, 8, 2, 2), (16, 16, 4, 4), 512, (3, 7, 11), ((1, 3, 5),) * 3), "multiple of 8"),
-                       ((80, (8, 8, 2, 2), (16, 16, 4, 4), 384, (3, 7, 11), ((1, 3, 5),) * 3), "power of two")):
+                       ((80, (8, 8, 2, 2), (16, 16, 4, 4), 384, (3, 7, 11), ((1, 3, 5),) * 3), "power of two"),
+                       ((80, (3, 2), (6, 4), 128, (3,), ((1,),)), "even difference")):
         with pytest.raises(_abi.HfgError, match=word):
             Engine(GeneratorConfig(*args), 0)
