@@ -48,9 +48,12 @@ def test_library_has_no_libcuda_link_dependency(lib):
 
 def test_config_validation_and_no_cpu_fallback(lib):
     h = ctypes.c_void_p()
-    bad = GeneratorConfig(upsample_rates=(8, 8), upsample_kernel_sizes=(15, 16)).to_abi()
-    assert lib.hfg_create(ctypes.byref(bad), 0, ctypes.byref(h)) == _abi.ERR_INVALID
+    # an upsampler the reference would build but whose output is not T * hop long (odd kernel - rate): unsupported, with the reason
+    odd = GeneratorConfig(upsample_rates=(8, 8), upsample_kernel_sizes=(15, 16)).to_abi()
+    assert lib.hfg_create(ctypes.byref(odd), 0, ctypes.byref(h)) == _abi.ERR_UNSUPPORTED
     assert b"upsample" in lib.hfg_last_error()
+    bad = GeneratorConfig(upsample_rates=(8, 8), upsample_kernel_sizes=(0, 16)).to_abi()
+    assert lib.hfg_create(ctypes.byref(bad), 0, ctypes.byref(h)) == _abi.ERR_INVALID
     even = GeneratorConfig(resblock_kernel_sizes=(4, 7, 11)).to_abi()
     assert lib.hfg_create(ctypes.byref(even), 0, ctypes.byref(h)) == _abi.ERR_INVALID
     if lib.hfg_device_count() == 0:
