@@ -196,6 +196,14 @@ int hfg_logmel_forward(hfg_logmel* h, const float* audio, int32_t B, int32_t N, 
 int hfg_griffin_lim(hfg_logmel* h, const float* mag, const float* angles0, int32_t B, int32_t T, int32_t n_iter, float momentum,
                     float* audio);
 
+/* The step before it, scripts/synthesize.py:180-192: linear magnitudes from a log-mel,
+ *   mag[b][k][t] = max(0, sum_m proj[k][m] * exp(min(max(logmel[b][m][t], lo), hi)))
+ * with proj [n_bins][n_mels] supplied by the caller (the reference solves librosa.feature.inverse.mel_to_stft's non-negative
+ * least squares there; the host mirror passes the pseudo-inverse of the Slaney filterbank).  logmel [B][n_mels][T] -> mag [B][n_bins][T].
+ * Host pointers; n_bins and n_mels are the handle's 1 + n_fft/2 and any positive mel count. */
+int hfg_mel_to_linear(hfg_logmel* h, const float* proj, const float* logmel, int32_t B, int32_t n_mels, int32_t T, float lo, float hi,
+                      float* mag);
+
 #ifdef __cplusplus
 }
 #endif

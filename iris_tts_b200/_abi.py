@@ -77,6 +77,7 @@ SIGNATURES = {
     "hfg_logmel_frames": (c_int32, [c_void_p, c_int32]),
     "hfg_logmel_forward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_uint32]),
     "hfg_griffin_lim": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "hfg_mel_to_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p]),
     "hfg_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_size_t)]),
 }
 

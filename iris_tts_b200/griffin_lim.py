@@ -94,11 +94,41 @@ def _handle(sample_rate: int, n_fft: int, hop_length: int, win_length: int, devi
     return fe
 
 
+def mel_to_linear(log_mel: np.ndarray, proj: np.ndarray, lo: float = -11.513, hi: float = 2.0, sample_rate: int = 22050, n_fft: int = 1024,
+                  hop_length: int = 256, device: int = 0) -> np.ndarray:
+    """``max(0, proj @ exp(clip(log_mel, lo, hi)))`` on the GPU (``hfg_mel_to_linear``): log-mel [n_mels, T] or [B, n_mels, T] and a
+    projection [1 + n_fft // 2, n_mels] -> linear magnitudes [(B,) 1 + n_fft // 2, T] (scripts/synthesize.py:180-192)."""
+    from . import _abi
+
+    m = np.ascontiguousarray(log_mel, dtype=np.float32)
+    squeeze = m.ndim == 2
+    if squeeze:
+        m = m[None]
+    p = np.ascontiguousarray(proj, dtype=np.float32)
+    if m.ndim != 3 or p.shape != (1 + n_fft // 2, m.shape[1]):
+        raise ValueError(f"log_mel must be [n_mels, T] or [B, n_mels, T] and proj [{1 + n_fft // 2}, n_mels], got {np.shape(log_mel)} and {p.shape}")
+    B, n_mels, T = m.shape
+    out = np.empty((B, 1 + n_fft // 2, T), dtype=np.float32)
+    fe = _handle(sample_rate, n_fft, hop_length, n_fft, device)
+    with fe._lock:
+        _abi.check(fe._lib.hfg_mel_to_linear(fe._h, p.ctypes.data, m.ctypes.data, B, n_mels, T, float(lo), float(hi), out.ctypes.data))
+    return out[0] if squeeze else out
+
+
+_PROJECTIONS: dict = {}
+
+
 def griffin_lim_from_log_mel(log_mel: np.ndarray, sample_rate: int = 22050, hop_length: int = 256, n_fft: int = 1024,
                              n_iter: int = 60, seed: int = 0) -> np.ndarray:
-    """log-mel [n_mels, T] (natural log of magnitudes) -> waveform float32 [hop_length * (T - 1)] (scripts/synthesize.py:174-194)."""
-    m = np.exp(np.clip(np.asarray(log_mel, dtype=np.float64), -11.513, 2.0))          # :180-181
-    fb = mel_filterbank(sample_rate, n_fft, m.shape[0]).astype(np.float64)            # mel_to_stft's default fmax = sr / 2 (:187-192)
-    mag = np.maximum(np.linalg.pinv(fb) @ m, 0.0)                                     # power = 1
+    """log-mel [n_mels, T] (natural log of magnitudes) -> waveform float32 [hop_length * (T - 1)] (scripts/synthesize.py:174-194).
+    The projection matrix (pseudo-inverse of the Slaney filterbank, mel_to_stft's default fmax = sr / 2) is set-up work, computed once
+    per geometry on the host like a folded weight; exp / clip / projection / clip and the 60 iterations run on the GPU."""
+    lm = np.asarray(log_mel, dtype=np.float32)
+    key = (int(sample_rate), int(n_fft), int(lm.shape[0]))
+    proj = _PROJECTIONS.get(key)
+    if proj is None:
+        fb = mel_filterbank(sample_rate, n_fft, lm.shape[0]).astype(np.float64)
+        proj = _PROJECTIONS[key] = np.linalg.pinv(fb).astype(np.float32)
+    mag = mel_to_linear(lm, proj, -11.513, 2.0, sample_rate, n_fft, hop_length)       # :180-181, :187-192 (power = 1)
     wav = griffin_lim(mag, n_iter=n_iter, hop_length=hop_length, win_length=n_fft, n_fft=n_fft, seed=seed, sample_rate=sample_rate)
     return np.clip(wav, -1.0, 1.0).astype(np.float32)

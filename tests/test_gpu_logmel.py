@@ -137,3 +137,22 @@ def test_griffin_lim_batches_and_other_geometries():
     assert wav.dtype == np.float32 and wav.shape == (hop * (T - 1),) and np.abs(wav).max() <= 1.0
     spec = np.abs(np.fft.rfft(wav))
     assert abs(np.argmax(spec) * sr / wav.size - 1000.0) < 60.0
+
+
+def test_mel_to_linear_projection_on_the_gpu():
+    """hfg_mel_to_linear: max(0, proj @ exp(clip(log_mel))) against the float64 oracle (pseudo-inverse of the Slaney filterbank),
+    batches, ragged frame counts, other mel widths."""
+    from iris_tts_b200.griffin_lim import mel_filterbank, mel_to_linear
+    from oracle import griffinlim_oracle as G
+    rng = np.random.default_rng(4)
+    for n_mels, n_fft, sr, B, T in ((80, 1024, 22050, 1, 45), (80, 1024, 22050, 3, 97), (40, 512, 16000, 2, 33), (128, 2048, 44100, 1, 7)):
+        log_mel = (rng.standard_normal((B, n_mels, T)) * 3.0 - 5.0).astype(np.float32)       # reaches both clip bounds
+        proj = np.linalg.pinv(mel_filterbank(sr, n_fft, n_mels).astype(np.float64)).astype(np.float32)
+        got = mel_to_linear(log_mel, proj, sample_rate=sr, n_fft=n_fft, hop_length=n_fft // 4)
+        assert got.shape == (B, 1 + n_fft // 2, T) and got.dtype == np.float32 and (got >= 0).all()
+        for b in range(B):
+            want = G.mel_to_linear(np.exp(np.clip(log_mel[b].astype(np.float64), -11.513, 2.0)), sr, n_fft)
+            scale = np.abs(np.linalg.pinv(mel_filterbank(sr, n_fft, n_mels).astype(np.float64))).sum(axis=1).max() * np.exp(2.0)
+            assert np.abs(got[b] - want).max() <= 2e-6 * scale, (n_mels, n_fft, float(np.abs(got[b] - want).max()), scale)
+    one = mel_to_linear(log_mel[0], proj, sample_rate=sr, n_fft=n_fft, hop_length=n_fft // 4)
+    np.testing.assert_array_equal(one, got[0])
