@@ -418,8 +418,9 @@ def griffin_lim_leg(frames, n_iter=60, reps=3):
 
 def ragged_leg(voc, max_frames, n_utt=32, reps=3):
     """32 utterances of 32 DISTINCT lengths (300 .. max_frames frames) end to end (numpy in, numpy out) in the
-    bf16 mode: exact length-bucketed batching (iris_tts_b200.batching.synthesize_variable: a padded body pass per bucket + one
-    tail pass) against the reference's only option, one batch-1 call per utterance.  Both produce the same bits."""
+    bf16 mode, three ways that produce the same bits: the engine's native ragged plan (hfg_forward_ragged: one padded call per
+    length bucket, every item ended where it ends), the dense-call scheme for plain callables (a padded body pass per bucket + one
+    tail pass; HFG_RAGGED=0), and the reference's only option, one batch-1 call per utterance."""
     import numpy as np
 
     from iris_tts_b200.batching import synthesize_variable
@@ -429,14 +430,28 @@ def ragged_leg(voc, max_frames, n_utt=32, reps=3):
     rng = np.random.default_rng(7)
     lengths = sorted(set(int(x) for x in np.linspace(300, max_frames, n_utt)))
     mels = [rng.standard_normal((80, t)).astype(np.float32) for t in lengths]
-    stats = {}
-    a = synthesize_variable(voc, mels, stats=stats, length_quantum=64)      # builds the plans
     b = [voc(m) for m in mels]
-    same = all(np.array_equal(x, y) for x, y in zip(a, b))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        synthesize_variable(voc, mels, length_quantum=64)
-    ms_b = 1e3 * (time.perf_counter() - t0) / reps
+
+    def timed(env):
+        prev = os.environ.get("HFG_RAGGED")
+        os.environ["HFG_RAGGED"] = env
+        try:
+            stats = {}
+            a = synthesize_variable(voc, mels, stats=stats, length_quantum=64)      # builds the plans
+            synthesize_variable(voc, mels, length_quantum=64)                         # captures their graphs
+            same = all(np.array_equal(x, y) for x, y in zip(a, b))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                synthesize_variable(voc, mels, length_quantum=64)
+            return 1e3 * (time.perf_counter() - t0) / reps, stats, same
+        finally:
+            if prev is None:
+                os.environ.pop("HFG_RAGGED", None)
+            else:
+                os.environ["HFG_RAGGED"] = prev
+
+    ms_n, st_n, same_n = timed("1")
+    ms_b, st_b, same_b = timed("0")
     t0 = time.perf_counter()
     for _ in range(reps):
         for m in mels:
@@ -445,9 +460,13 @@ def ragged_leg(voc, max_frames, n_utt=32, reps=3):
     voc.model.precision = old
     samples = sum(lengths) * 256
     return {"workload": f"{len(lengths)} utterances, {len(lengths)} distinct lengths {lengths[0]}..{lengths[-1]} frames, bf16, numpy in -> numpy out",
+            "native_ragged_ms": ms_n, "native_ragged_value": samples / (ms_n * 1e-3), "native_calls": st_n["calls"],
+            "native_frames_run": st_n["frames_run"], "native_path_taken": bool(st_n.get("native_ragged")),
             "bucketed_ms": ms_b, "bucketed_value": samples / (ms_b * 1e-3), "per_utterance_calls_ms": ms_u,
-            "per_utterance_value": samples / (ms_u * 1e-3), "unit": "samples/s", "speedup": ms_u / ms_b, "dense_calls": stats["calls"],
-            "frames_real": stats["frames_real"], "frames_run": stats["frames_run"], "bit_identical_to_per_utterance": bool(same)}
+            "per_utterance_value": samples / (ms_u * 1e-3), "unit": "samples/s", "speedup": ms_u / ms_n,
+            "speedup_dense_call_scheme": ms_u / ms_b, "dense_calls": st_b["calls"],
+            "frames_real": st_b["frames_real"], "frames_run": st_b["frames_run"],
+            "bit_identical_to_per_utterance": bool(same_n and same_b)}
 
 
 def longform_leg(model, precision, world, rank, reps=5):

@@ -117,6 +117,12 @@ class HiFiGANGenerator:
 
     __call__ = call
 
+    def forward_ragged(self, mel, lengths):
+        """Channels-FIRST numpy ``[B, 80, T]`` whose item b holds ``lengths[b]`` real frames -> float32 ``[B, T*hop]``; the first
+        ``lengths[b]*hop`` samples of row b equal the dense forward of that item alone (``hfg_forward_ragged``; the Keras
+        reference has no ragged call, vocoder.py:177-209)."""
+        return self._ensure_engine().forward_ragged(np.asarray(mel), lengths, self.precision)
+
     def get_weights(self) -> List[np.ndarray]:
         return [self.weights[k] for k in self.weights]
 

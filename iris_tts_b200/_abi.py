@@ -59,6 +59,7 @@ SIGNATURES = {
     "hfg_layer_name": (c_int, [c_void_p, c_int, c_char_p, c_size_t]),
     "hfg_finalize": (c_int, [c_void_p]),
     "hfg_forward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_uint32]),
+    "hfg_forward_ragged": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_uint32]),
     "hfg_sync": (c_int, [c_void_p]),
     "hfg_hop": (c_int32, [c_void_p]),
     "hfg_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32, c_int32]),

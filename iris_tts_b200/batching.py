@@ -13,6 +13,11 @@ constructor arguments; 16 is used).  That gives an exact scheme with dense calls
   last ``halo`` frames are kept -- their left context lies inside the window, their right edge is the true end of the utterance,
   so the generator's own zero padding is applied exactly where the reference applies it.
 
+When the vocoder is one of this package's objects in a tensor-core precision, the engine does the same thing natively and the tail
+pass disappears: ``hfg_forward_ragged`` takes the padded batch WITH its lengths, zeroes what lies behind each item's own end after
+every layer (and inside the fused ResBlock kernel), and returns every item's samples bit-identical to its solo forward -- one dense
+launch plan per bucket, no second pass, no stitching (``ragged_forward_of``).
+
 Utterances shorter than ``2 * halo`` frames have no room for that split and run grouped by exact length.  On the GPU engine a
 sample's bits do not depend on where its tile lies (tests/test_gpu_api.py: chunked long-form output is bit-identical to the
 unchunked one), so the result equals the per-utterance forwards bit for bit, at 2 + (number of buckets) launches of the plan
@@ -51,6 +56,21 @@ def length_buckets(lengths: Sequence[int], max_pad: float = 0.15, max_batch: Opt
     return buckets
 
 
+def ragged_forward_of(vocoder) -> Optional[Callable]:
+    """``forward_ragged(mel [B, n_mels, T], lengths) -> [B, T*hop]`` of a vocoder of this package (HiFiGANGenerator / HiFiGANVocoder
+    via ``.model``, or a model object itself) when its precision has the native ragged path; None for plain callables, for the exact
+    fp32 mode and when ``HFG_RAGGED=0``."""
+    import os
+
+    if os.environ.get("HFG_RAGGED", "1") == "0":
+        return None
+    for obj in (vocoder, getattr(vocoder, "model", None)):
+        fn = getattr(obj, "forward_ragged", None) if obj is not None else None
+        if callable(fn) and getattr(obj, "precision", None) in ("bf16x3", "bf16", "fp16"):
+            return fn
+    return None
+
+
 def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Sequence[np.ndarray], hop: Optional[int] = None,
                         halo: Optional[int] = None, max_pad: float = 0.15, max_batch: Optional[int] = None,
                         stats: Optional[dict] = None, length_quantum: int = 1) -> List[np.ndarray]:
@@ -72,6 +92,31 @@ def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Seque
     out: List[np.ndarray] = [None] * n   # type: ignore[list-item]
     lengths = [int(m.shape[1]) for m in mels]
     calls = frames_run = 0
+    ragged = ragged_forward_of(vocoder)
+    if ragged is not None:
+        # native path: one padded call per length bucket, the engine ends every item where it ends
+        live = [i for i in range(n) if lengths[i] > 0]
+        for i in range(n):
+            if lengths[i] == 0:
+                out[i] = np.zeros((0,), dtype=np.float32)
+        n_mels = mels[live[0]].shape[0] if live else 0
+        for bucket in length_buckets([lengths[i] for i in live], max_pad, max_batch):
+            ids = [live[j] for j in bucket]
+            tb = max(lengths[i] for i in ids)
+            if length_quantum > 1:
+                tb = -(-tb // length_quantum) * length_quantum
+            batch = np.zeros((len(ids), n_mels, tb), dtype=np.float32)
+            for j, i in enumerate(ids):
+                batch[j, :, : lengths[i]] = mels[i]
+            wav = np.asarray(ragged(batch, [lengths[i] for i in ids]))
+            calls += 1
+            frames_run += tb * len(ids)
+            for j, i in enumerate(ids):
+                out[i] = wav[j, : lengths[i] * hop]     # a view of the call's result: no second copy
+        if stats is not None:
+            stats.update({"calls": calls, "frames_run": frames_run, "frames_real": sum(lengths),
+                          "distinct_lengths": len(set(lengths)), "native_ragged": True})
+        return out
     long_idx = [i for i in range(n) if lengths[i] >= 2 * halo]
     short_idx = [i for i in range(n) if lengths[i] < 2 * halo]
 
@@ -114,5 +159,5 @@ def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Seque
             out[i] = np.concatenate([body[i], wav[j, halo * hop:]])
     if stats is not None:
         stats.update({"calls": calls, "frames_run": frames_run, "frames_real": sum(lengths),
-                      "distinct_lengths": len(set(lengths))})
+                      "distinct_lengths": len(set(lengths)), "native_ragged": False})
     return out

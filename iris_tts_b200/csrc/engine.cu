@@ -45,7 +45,10 @@ struct DeviceGuard {
     cudaError_t err = cudaSuccess;
     explicit DeviceGuard(int d) : dev(d) {
         if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
-        if (prev != d) err = cudaSetDevice(d);
+        // ALWAYS: a thread that has made no CUDA call yet reports device 0 as current without having a context bound, and the
+        // driver entry points the planner calls (cuTensorMapEncodeTiled) then fail with CUDA_ERROR_INVALID_CONTEXT (seen from a
+        // worker thread whose page-locked buffers came out of torch's host cache, i.e. with no runtime call before this one)
+        err = cudaSetDevice(d);
     }
     ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
 };
@@ -81,6 +84,7 @@ struct Layer {
 };
 
 enum StepKind { S_CONV32, S_UMMA, S_UMMA2, S_PAIR, S_POST32, S_ACCUM, S_MEL_CL32, S_MEL_CLBF, S_P2RAW, S_MRF, S_POSTMRF, S_TAP,
+                S_STRIP,            // ragged batches: zero the rows behind each item's own end of the planes the previous step wrote
                 S_FORK, S_JOIN };   // the branch lanes of a stage start after / end before this point (no kernel)
 
 struct Step {
@@ -114,6 +118,7 @@ struct Plan {
     std::vector<Step> steps;
     float* mel_dev = nullptr;   // [B][Cin][T] staging when the caller passes a host pointer
     float* wave_dev = nullptr;  // [B][T*hop]
+    int32_t* lens_dev = nullptr; // ragged plans: [B] mel frames per item (copied in before every launch of the plan)
     size_t bytes = 0;
     bool keep_taps = false;
     std::vector<size_t> guards;   // HFG_GUARD: canary regions between the workspace buffers
@@ -548,7 +553,15 @@ int env_flag(const char* name, int dflt) {
 // recovers x by inverting leaky_relu.  The MRF mean (:133-137) is one elementwise pass over the nk branch
 // outputs per stage.  Stages narrower than 32 channels (V2's tail) run on the fp32 family inside a
 // tensor-core plan; the hand-over is the fp32 output of that MRF pass.
-int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* base, Plan* plan, size_t* bytes_out) {
+//
+// ragged (hfg_forward_ragged; tensor-core plans only): the items of the batch have their own lengths (plan->lens_dev, mel frames).
+// Every layer of the reference zero-pads its input at the true end of the sequence (:49-59, :92-94), which a dense plan gets from
+// TMA's out-of-bounds zero fill at row L.  A ragged plan makes the same true at every item's OWN end: after each conv an S_STRIP
+// step zeroes the `halo` rows behind the end of the planes just written (halo >= the widest tap span of any layer, so no row inside
+// an item ever reads further), and the fused pair kernel -- whose intermediate never reaches HBM -- masks it per item itself.
+// Rows are independent dot products and their bits do not depend on the tile they fall in, so an item's samples equal those of
+// a dense forward of that item alone, bit for bit.
+int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* base, Plan* plan, size_t* bytes_out, bool ragged = false) {
     typedef __nv_bfloat16 bf;
     const hfg_config& c = e->cfg;
     const bool x3 = prec == HFG_PREC_BF16X3;
@@ -596,7 +609,15 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
 
     float* mel_dev = bump.take<float>((size_t)B * c.in_channels * T);
     float* wave_dev = bump.take<float>((size_t)B * T * e->hop);
-    if (real) { plan->mel_dev = mel_dev; plan->wave_dev = wave_dev; plan->keep_taps = keep_taps; }
+    int32_t* lens_dev = ragged ? bump.take<int32_t>((size_t)B) : nullptr;
+    if (real) { plan->mel_dev = mel_dev; plan->wave_dev = wave_dev; plan->keep_taps = keep_taps; plan->lens_dev = lens_dev; }
+    if (ragged && (!any_tc || any_32 || keep_taps))
+        return fail(HFG_ERR_UNSUPPORTED, "ragged batches run on the tensor-core plans only (precision bf16x3 / bf16 / fp16, upsample_initial_channel % 32 == 0, no taps)");
+    // rows to zero behind an item's end: the widest reach of any layer's taps (in the rows of its own stage), in whole 8-row groups
+    int halo_rows = 8;
+    for (const Layer& Ly : e->layers) halo_rows = std::max(halo_rows, Ly.transposed ? Ly.k : Ly.dil * (Ly.k - 1) / 2 + 1);
+    halo_rows = (halo_rows + 7) / 8 * 8;
+    bool strip_bad = false;
 
     // fp32 streams: the fp32 family's working set, and the tap staging buffer of the tensor-core family
     float* u_raw = any_32 ? bump.take<float>(smax) : nullptr;
@@ -645,6 +666,14 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         }
     }
     int cur_lane = 0;   // lane of the steps being emitted
+    // ragged plans: zero the rows behind each item's end of planes [B][rows][row_elems] (rows = mul * T)
+    auto strip = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, int rows, int row_elems) {
+        if (!ragged || !real) return;
+        if (rows % T != 0 || row_elems % 8 != 0) { strip_bad = true; return; }
+        Step s{}; s.kind = S_STRIP; s.b_out = hi; s.b_out_lo = x3 ? lo : nullptr; s.B = B; s.L = rows; s.C = row_elems; s.k = rows / T;
+        s.flag0 = halo_rows; s.lane = cur_lane; s.label = "zero_tail";
+        plan->steps.push_back(std::move(s));
+    };
 
     // F_l = 2*Cin*Cout*k*L (L = L_out for Conv1d, L_in for ConvTranspose1d); Q_l = activations in + out + weights
     auto work = [&](Step& s, const Layer& L, int Lin, int act_bytes) {
@@ -677,6 +706,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         }
         s.lane = cur_lane;
         plan->steps.push_back(std::move(s));
+        if (y.hi) strip(y.hi, y.lo, p.g.Lout, p.g.Cout);
         return HFG_OK;
     };
     // convs1[m] -> lrelu -> convs2[m] -> + x  (:66-70) as one launch where the fused kernel applies (C <= 64); false otherwise
@@ -693,6 +723,10 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.y_hi = y.hi; p.y_lo = x3 ? y.lo : nullptr;
         p.mrf_hi = mrf.hi; p.mrf_lo = x3 ? mrf.lo : nullptr; p.out_scale = out_scale;
         p.reverse = snake ? (n_umma2 & 1) : 0;
+        if (ragged) {
+            if (Lrows % T != 0) { strip_bad = true; return false; }
+            p.lens = lens_dev; p.len_mul = Lrows / T;
+        }
         if (!pair_supported(p)) return false;
         Step s{};
         if (plan_conv_pair(&s.pl, p, e->sm_count) != HFG_OK) return false;
@@ -709,6 +743,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.bytes = 2.0 * r1.cin * (double)rL * B * act_b + 2.0 * (double)r1.cin * r1.cout * r1.k * act_b;
         s.lane = cur_lane;
         plan->steps.push_back(std::move(s));
+        strip(y.hi, y.lo, Lrows, p.C);
         return true;
     };
     auto c32 = [&](const Layer& L, int Lin, const float* x, float* y, const float* res, int pre_lrelu, int accumulate, float out_div) {
@@ -738,6 +773,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     if (any_tc) {
         { Step s{}; s.kind = S_MEL_CLBF; s.f_in = mel_dev; s.b_out = mel_p.hi; s.b_out_lo = mel_p.lo; s.B = B; s.C = c.in_channels;
           s.L = T; s.cpad = pre.cin_pad; s.f16 = f16; push(std::move(s)); }
+        strip(mel_p.hi, mel_p.lo, T, pre.cin_pad);   // whatever the caller left behind an item's end is not part of it
         RET(umma(pre, T, mel_p, Planes(), x0_raw, n_tc > 0 ? x0_p : Planes()));
         if (n_tc > 0) tap_planes("conv_pre", x0_p, c0, T); else tap("conv_pre", x0_raw, c0, T);
         x_raw = x0_raw; xp = x0_p;
@@ -874,6 +910,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         push(std::move(s));
         if (!pass) tap("conv_post", post_tap, 1, L);
     }
+    if (strip_bad) return fail(HFG_ERR_UNSUPPORTED, "ragged batches: a stage of this generator is not a whole number of rows per mel frame");
     if (bytes_out) *bytes_out = bump.off;
     return HFG_OK;
 }
@@ -904,6 +941,7 @@ const char* kind_label(StepKind k) {
         case S_ACCUM: return "accum";
         case S_MEL_CL32: return "transpose";
         case S_MEL_CLBF: return "mel_to_cl_bf16";
+        case S_STRIP: return "zero_tail_rows";
         default: return "copy";
     }
 }
@@ -990,6 +1028,7 @@ int run_plan(hfg_engine* e, Plan* plan) {
             case S_ACCUM: CK(launch_accum_fp32(s.f_out, s.f_in, s.n, s.flag0, s.fval, st)); break;
             case S_MEL_CL32: CK(launch_transpose_cf_to_cl(s.f_in, s.f_out, s.B, s.C, s.L, st)); break;
             case S_MEL_CLBF: CK(launch_mel_to_cl_bf16(s.f_in, s.b_out, s.b_out_lo, s.B, s.C, s.L, s.cpad, 0, s.f16, st)); break;
+            case S_STRIP: CK(launch_zero_tail_rows(s.b_out, s.b_out_lo, plan->lens_dev, s.k, s.B, s.L, s.C, s.flag0, st)); break;
             case S_TAP: RET(store_tap(e, s)); break;   // a copy, not one of our kernels
             case S_FORK: case S_JOIN: break;
         }
@@ -1252,7 +1291,8 @@ int hfg_sync(hfg_engine* e) {
     return HFG_OK;
 }
 
-int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wave, int32_t precision, uint32_t flags) {
+static int forward_impl(hfg_engine* e, const float* mel, int32_t B, int32_t T, const int32_t* lengths, float* wave, int32_t precision,
+                        uint32_t flags) {
     if (!e || !mel || !wave) return fail(HFG_ERR_INVALID, "hfg_forward: null argument");
     if (B <= 0 || T <= 0) return fail(HFG_ERR_INVALID, "hfg_forward: B and T must be positive");
     RET(check_sizes(e, B, T));
@@ -1260,13 +1300,19 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     if (!e->finalized) return fail(HFG_ERR_STATE, "hfg_forward: call hfg_finalize first");
     const bool mel_dev = flags & HFG_MEL_ON_DEVICE, wave_dev = flags & HFG_WAVE_ON_DEVICE;
     const bool keep = flags & HFG_KEEP_TAPS;
+    const bool ragged = lengths != nullptr;
+    if (ragged) {
+        if (keep) return fail(HFG_ERR_INVALID, "hfg_forward_ragged: HFG_KEEP_TAPS is not available for ragged batches");
+        for (int b = 0; b < B; ++b)
+            if (lengths[b] < 1 || lengths[b] > T) return fail(HFG_ERR_INVALID, "hfg_forward_ragged: every length must lie in [1, T]");
+    }
     // HFG_NO_SYNC with HOST pointers: both must be page-locked and stay valid until hfg_sync (the copies are asynchronous);
     // not combined with taps or the canary mode, which read results back inside the call
     const bool async_host = (flags & HFG_NO_SYNC) && !(mel_dev && wave_dev);
     if (async_host && (keep || env_flag("HFG_GUARD", 0))) return fail(HFG_ERR_INVALID, "hfg_forward: HFG_NO_SYNC with host pointers excludes HFG_KEEP_TAPS / HFG_GUARD");
     GUARD(e);
 
-    const auto key = std::make_tuple((int)B, (int)T, (int)precision, keep ? 1 : 0);
+    const auto key = std::make_tuple((int)B, (int)T, (int)precision, (keep ? 1 : 0) | (ragged ? 2 : 0));
     auto it = e->plans.find(key);
     if (it == e->plans.end()) {
         if (e->plans.size() >= 64) {   // variable-length traffic: bound the cache (plans are cheap to rebuild)
@@ -1274,12 +1320,12 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
             e->plans.clear();
         }
         size_t bytes = 0;
-        RET(build_plan(e, B, T, precision, keep, nullptr, nullptr, &bytes));
+        RET(build_plan(e, B, T, precision, keep, nullptr, nullptr, &bytes, ragged));
         RET(ensure_arena(e, bytes));
         std::unique_ptr<Plan> plan(new Plan());
         plan->bytes = bytes;
         // All plans share the arena from offset 0: they run one after another on one stream.
-        RET(build_plan(e, B, T, precision, keep, e->arena, plan.get(), nullptr));
+        RET(build_plan(e, B, T, precision, keep, e->arena, plan.get(), nullptr, ragged));
         for (const Step& st : plan->steps) plan->kernels += is_kernel_step(st.kind);
         it = e->plans.emplace(key, std::move(plan)).first;
     }
@@ -1290,6 +1336,8 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     // stand-in for a memcheck pass: a kernel that writes past the end (or before the start) of a plane trips the next canary.
     for (size_t off : plan->guards) CK(cudaMemsetAsync(e->arena + off, kGuardByte, kGuardBytes, e->stream));
     CK(cudaMemcpyAsync(plan->mel_dev, mel, mel_bytes, mel_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    // (pageable source: the runtime stages it before returning, the caller's array may go away at once)
+    if (ragged) CK(cudaMemcpyAsync(plan->lens_dev, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
     RET(launch_plan(e, plan));
     if (!plan->guards.empty()) {
         if (env_flag("HFG_GUARD_SELFTEST", 0))   // prove the check itself: clobber one canary byte like a stray store would
@@ -1330,6 +1378,16 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
     CK(cudaMemcpyAsync(wave, plan->wave_dev, wave_bytes, wave_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     if (!(flags & HFG_NO_SYNC)) CK(cudaStreamSynchronize(e->stream));
     return HFG_OK;
+}
+
+int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wave, int32_t precision, uint32_t flags) {
+    return forward_impl(e, mel, B, T, nullptr, wave, precision, flags);
+}
+
+int hfg_forward_ragged(hfg_engine* e, const float* mel, int32_t B, int32_t T, const int32_t* lengths, float* wave, int32_t precision,
+                       uint32_t flags) {
+    if (!lengths) return fail(HFG_ERR_INVALID, "hfg_forward_ragged: null lengths");
+    return forward_impl(e, mel, B, T, lengths, wave, precision, flags);
 }
 
 int hfg_run_layer(hfg_engine* e, const char* layer, const float* x, int32_t B, int32_t L, int32_t pre_lrelu, float* y,

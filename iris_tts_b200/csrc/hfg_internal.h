@@ -150,6 +150,8 @@ struct PairParams {
     int reverse;
     const __nv_bfloat16 *mrf_hi, *mrf_lo;   // running MRF sum added in epilogue 2 (see UmmaConvParams), or nullptr
     float out_scale;
+    const int32_t* lens;  // ragged batch (device, [B]): item b ends at row lens[b] * len_mul -- c2 sees zeros from there on; or nullptr
+    int len_mul;
     const float* bias1;
     const float* bias2;
     const __nv_bfloat16 *x_hi, *x_lo;
@@ -185,6 +187,10 @@ cudaError_t launch_mrf_combine(const MrfArgs& a, size_t n, cudaStream_t s);
 // through the operand-plane format exactly as launch_mrf_combine would store it, so both plans give identical bits.
 cudaError_t launch_conv_post_mrf(const MrfArgs& a, const float* w /*[k][C]*/, const float* bias, float* wave, int B, int L, int C,
                                  int k, int apply_tanh, cudaStream_t s);
+
+// Ragged batches: zero the H rows behind each item's own end (lens[b] * mul rows) of a [B][L][row_elems] plane (pair)
+cudaError_t launch_zero_tail_rows(__nv_bfloat16* hi, __nv_bfloat16* lo, const int32_t* lens, int mul, int B, int L, int row_elems,
+                                  int H, cudaStream_t s);
 
 void set_error(const std::string& msg);
 

@@ -603,6 +603,36 @@ cudaError_t launch_planes_to_raw(const __nv_bfloat16* hi, const __nv_bfloat16* l
     return cudaGetLastError();
 }
 
+// Ragged batches (hfg_forward_ragged): item b is lens[b] mel frames long, i.e. lens[b] * mul rows of this [B][L][row_elems]
+// 16-bit plane (pair).  The first H rows behind an item's own end are set to zero, so that the next layer's taps read there what
+// they read behind the end of a dense batch (TMA's out-of-bounds zero fill == the reference's zero padding,
+// hifigan_pretrained.py:49-59,92-94); rows further out never reach a row inside the item (H covers the widest tap span).
+__global__ void zero_tail_rows_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, const int32_t* __restrict__ lens,
+                                      int mul, int L, int row_elems, int H) {
+    const int b = blockIdx.y;
+    const long long r0 = (long long)lens[b] * mul;
+    if (r0 >= L) return;
+    const long long r1 = r0 + H < L ? r0 + H : L;
+    const size_t first = ((size_t)b * L + (size_t)r0) * row_elems;          // element offsets; row_elems % 8 == 0: 16-byte aligned
+    const size_t n8 = (size_t)(r1 - r0) * row_elems / 8;
+    uint4* ph = reinterpret_cast<uint4*>(hi + first);
+    uint4* pl = lo ? reinterpret_cast<uint4*>(lo + first) : nullptr;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        ph[i] = z;
+        if (pl) pl[i] = z;
+    }
+}
+
+cudaError_t launch_zero_tail_rows(__nv_bfloat16* hi, __nv_bfloat16* lo, const int32_t* lens, int mul, int B, int L, int row_elems,
+                                  int H, cudaStream_t s) {
+    if (!hi || !lens || row_elems % 8 != 0 || mul < 1 || H < 1 || B < 1 || B > 65535) return cudaErrorInvalidValue;
+    const size_t n8 = (size_t)H * row_elems / 8;
+    dim3 grid((unsigned)std::max<size_t>(1, std::min<size_t>((n8 + 255) / 256, 8)), (unsigned)B);
+    zero_tail_rows_kernel<<<grid, 256, 0, s>>>(hi, lo, lens, mul, L, row_elems, H);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mrf_combine(const MrfArgs& a, size_t n, cudaStream_t s) {
     if (n % 8 != 0 || a.nk < 1 || a.nk > HFG_MAX_KERNELS) return cudaErrorInvalidValue;
     const size_t n8 = n / 8;

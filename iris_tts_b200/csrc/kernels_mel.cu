@@ -387,7 +387,10 @@ struct MelDeviceGuard {
     cudaError_t err = cudaSuccess;
     explicit MelDeviceGuard(int d) : dev(d) {
         if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
-        if (prev != d) err = cudaSetDevice(d);
+        // ALWAYS: a thread that has made no CUDA call yet reports device 0 as current without having a context bound, and the
+        // driver entry points the planner calls (cuTensorMapEncodeTiled) then fail with CUDA_ERROR_INVALID_CONTEXT (seen from a
+        // worker thread whose page-locked buffers came out of torch's host cache, i.e. with no runtime call before this one)
+        err = cudaSetDevice(d);
     }
     ~MelDeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
 };

@@ -59,6 +59,8 @@ struct PairArgs {
     float out_scale;
     uint32_t m_plane_bytes, off_m;
     int dbg;                     // HFG_PAIR_DBG (timing experiments only): 1 = epilogue 2 idle, 2 = no MMAs, 3 = epilogue 1 idle, 4 = no TMA stores
+    const int32_t* lens;         // ragged batch: item b is lens[b] * len_mul rows long (nullptr: every item is L rows)
+    int len_mul;
     uint32_t x_plane_bytes, t_plane_bytes, w_plane_bytes, o_plane_bytes;
     uint32_t off_w, off_t, off_o;
     const float* bias1;
@@ -357,11 +359,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             mbar_wait(bar_t_empty + 8 * st, pt ^ 1u);
             tc_fence_after();
             const uint32_t t_slot = smem_t + st * t_stage;
-            const bool edge_tile = g0 < 0 || g0 + a.R > a.L;
+            // ragged batch: t rows at or behind the item's OWN end are c2's zero padding, as rows >= L are in a dense batch
+            const int Lb = a.lens ? min(a.L, __ldg(a.lens + b) * a.len_mul) : a.L;
+            const bool edge_tile = g0 < 0 || g0 + a.R > Lb;
             for (int ms = 0; ms < (a.dbg == 3 ? 0 : a.mt); ++ms) {
                 const uint32_t row_t = (uint32_t)(ms * 128 + q * 32 + lane);
                 const int g = g0 + (int)row_t;
-                const bool inside = g >= 0 && g < a.L;
+                const bool inside = g >= 0 && g < Lb;
                 const uint32_t dst = t_slot + row_t * row_bytes;
                 const uint32_t sx = swz(row_t, row_bytes);
                 for (int h = 0; h < nch; ++h) {
@@ -613,6 +617,7 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     a.out_scale = a.has_mrf ? p.out_scale : 1.0f;
     a.dbg = penv("HFG_PAIR_DBG", 0);
     a.bias1 = p.bias1; a.bias2 = p.bias2;
+    a.lens = p.lens; a.len_mul = p.len_mul;
     a.w_plane_bytes = rup((uint32_t)N * row_bytes, 1024);
     if (a.concat && a.w_plane_bytes != (uint32_t)N * row_bytes) return HFG_ERR_UNSUPPORTED;
     a.o_plane_bytes = 32u * row_bytes;

@@ -277,6 +277,33 @@ class Engine:
         return out
 
     @_locked
+    def forward_ragged(self, mel: np.ndarray, lengths: Sequence[int], precision: str = "bf16x3") -> np.ndarray:
+        """Ragged batch in ONE dense launch plan (``hfg_forward_ragged``): numpy [B, in_channels, T] whose item b holds
+        ``lengths[b]`` real frames (the rest is ignored) -> float32 [B, T*hop]; ``out[b, :lengths[b]*hop]`` equals
+        ``forward(mel[b:b+1, :, :lengths[b]])[0]`` bit for bit, the rest of row b is unspecified.  The reference has no
+        such call (hifigan_pretrained.py:221-242: one dense array, equal T).  Tensor-core precisions only."""
+        if mel.ndim != 3 or mel.shape[1] != self.config.in_channels:
+            raise ValueError(f"mel must be [batch, {self.config.in_channels}, time], got {mel.shape}")
+        B, _, T = mel.shape
+        lens = np.ascontiguousarray(np.asarray(lengths).reshape(-1), dtype=np.int32)
+        if lens.shape[0] != B:
+            raise ValueError(f"lengths must have one entry per item: {lens.shape[0]} vs batch {B}")
+        if B == 0 or T == 0:
+            return np.zeros((B, T * self.hop), dtype=np.float32)
+        if lens.min() < 1 or lens.max() > T:
+            raise ValueError(f"every length must lie in [1, {T}]")
+        import torch
+
+        if self._pin_in is None or self._pin_in.numel() < mel.size:
+            self._pin_in = torch.empty(mel.size, dtype=torch.float32, pin_memory=True)
+        stage = self._pin_in[: mel.size].view(B, mel.shape[1], T)
+        out_t = torch.empty((B, T * self.hop), dtype=torch.float32, pin_memory=True)
+        np.copyto(stage.numpy(), mel, casting="unsafe")
+        _abi.check(self._lib.hfg_forward_ragged(self._h, ctypes.c_void_p(stage.data_ptr()), B, T, ctypes.c_void_p(lens.ctypes.data),
+                                                ctypes.c_void_p(out_t.data_ptr()), _abi.PRECISIONS[precision], 0))
+        return out_t.numpy()
+
+    @_locked
     def sync(self) -> None:
         _abi.check(self._lib.hfg_sync(self._h))
 

@@ -125,10 +125,13 @@ def test_variable_length_batches_are_exact(loud_ckpt):
 
 
 @pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
-def test_ragged_batch_by_buckets_and_tails_equals_per_utterance_forwards(loud_ckpt, mode):
+def test_ragged_batch_by_buckets_and_tails_equals_per_utterance_forwards(loud_ckpt, mode, monkeypatch):
     """f4: 12 utterances of 12 distinct lengths (33 .. 400 frames) in a handful of dense calls -- a zero-padded body pass per
-    length bucket plus ONE tail pass over every utterance's last 32 frames -- bit-identical to twelve batch-1 forwards."""
+    length bucket plus ONE tail pass over every utterance's last 32 frames -- bit-identical to twelve batch-1 forwards.  This is
+    the scheme for plain callables and the fp32 mode (HFG_RAGGED=0 forces it here); the engine's native ragged plan is
+    tests/test_gpu_ragged.py."""
     import iris.hifigan_pretrained as hp
+    monkeypatch.setenv("HFG_RAGGED", "0")
     from iris_tts_b200 import sharding
     from iris_tts_b200.batching import synthesize_variable
     gen = hp.get_pretrained_hifigan(loud_ckpt)
@@ -140,7 +143,7 @@ def test_ragged_batch_by_buckets_and_tails_equals_per_utterance_forwards(loud_ck
         mels = [O.synthetic_mel(1, t, seed=50 + i, realistic=(i % 2 == 0))[0] for i, t in enumerate(lengths)]
         stats = {}
         outs = synthesize_variable(gen, mels, stats=stats)
-        assert stats["distinct_lengths"] == 12 and stats["calls"] <= 7, stats
+        assert stats["distinct_lengths"] == 12 and stats["calls"] <= 7 and not stats["native_ragged"], stats
         for m, o in zip(mels, outs):
             np.testing.assert_array_equal(o, gen(m))
         ref = O.infer(O.random_state_dict(O.V1, seed=0, loud=True), mels[5])
@@ -339,6 +342,34 @@ def test_one_vocoder_called_from_several_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_first_cuda_call_of_a_thread_may_be_a_new_shape():
+    """A worker thread whose very first CUDA-touching call is a forward of a shape the engine has not planned yet: the ABI entry
+    binds the device's context to the thread itself (the planner calls driver entry points, which fail with
+    CUDA_ERROR_INVALID_CONTEXT on a thread that has none).  Pageable numpy buffers: nothing before the call touches CUDA."""
+    import threading
+    eng_sd = O.random_state_dict(O.V1, seed=0, loud=True)
+    from iris_tts_b200 import Engine
+    from iris_tts_b200.engine import V1
+    eng = Engine(V1, 0)
+    eng.load_state_dict(eng_sd, strict=True)
+    eng.finalize()
+    mel = O.synthetic_mel(1, 23, seed=8)
+    got = {}
+
+    def run():
+        try:
+            got["out"] = eng.forward(mel, precision="bf16x3", pinned=False)
+        except Exception as exc:  # noqa: BLE001
+            got["err"] = repr(exc)
+
+    t = threading.Thread(target=run)
+    t.start()
+    t.join()
+    assert "err" not in got, got
+    assert np.abs(got["out"] - O.infer(eng_sd, mel)).max() <= 1e-3
+    eng.close()
 
 
 def test_ragged_batching_reads_the_receptive_field_from_the_generator():

@@ -197,6 +197,60 @@ def test_ragged_batch_scheme_is_exact_against_per_utterance_forwards():
         synthesize_variable(vocoder, [np.zeros((1, 80, 5), np.float32)])
 
 
+def test_native_ragged_path_host_logic(monkeypatch):
+    """A vocoder that offers ``forward_ragged`` in a tensor-core precision gets ONE padded call per length bucket with the items'
+    lengths and no tail pass; the fp32 mode, plain callables and HFG_RAGGED=0 keep the dense-call scheme.  (The oracle stands in
+    for the engine: the fake forward_ragged runs every item alone, which is what the engine's ragged plan must equal.)"""
+    from iris_tts_b200.batching import ragged_forward_of, synthesize_variable
+    sd = O.random_state_dict(O.V2, seed=0, loud=True)
+
+    class Model:
+        precision = "bf16"
+        ragged_calls = []
+        dense_calls = 0
+
+        def forward_ragged(self, mel, lengths):
+            assert mel.shape[0] == len(lengths) and max(lengths) <= mel.shape[2]
+            self.ragged_calls.append((mel.shape, tuple(lengths)))
+            out = np.full((mel.shape[0], mel.shape[2] * 256), np.nan, dtype=np.float32)   # behind an item's end: unspecified
+            for b, n in enumerate(lengths):
+                out[b, : n * 256] = O.infer(sd, np.ascontiguousarray(mel[b:b + 1, :, :n]), O.V2)[0]
+            return out
+
+    class Voc:
+        model = Model()
+
+        def __call__(self, batch):
+            self.model.dense_calls += 1
+            return O.infer(sd, batch, O.V2)
+
+    voc = Voc()
+    lengths = (90, 33, 84, 64, 7, 70, 0, 31)
+    mels = [O.synthetic_mel(1, t, seed=40 + i)[0] if t else np.zeros((80, 0), np.float32) for i, t in enumerate(lengths)]
+    stats = {}
+    outs = synthesize_variable(voc, mels, stats=stats, hop=256, halo=16)
+    assert stats["native_ragged"] and stats["calls"] == len(voc.model.ragged_calls) < len(set(lengths)) and voc.model.dense_calls == 0
+    assert sum(len(l) for _s, l in voc.model.ragged_calls) == len([t for t in lengths if t])
+    for m, o, t in zip(mels, outs, lengths):
+        assert o.shape == (t * 256,) and o.dtype == np.float32 and np.isfinite(o).all()
+        if t:
+            np.testing.assert_allclose(o, O.infer(sd, m[None], O.V2)[0], atol=2e-6)
+    outs_q = synthesize_variable(voc, mels, hop=256, halo=16, length_quantum=64)
+    assert all(shape[2] % 64 == 0 for shape, _l in voc.model.ragged_calls[stats["calls"]:])
+    for a, b_ in zip(outs, outs_q):
+        np.testing.assert_array_equal(a, b_)
+    # no native path: exact fp32 mode, plain callables, HFG_RAGGED=0
+    voc.model.precision = "fp32"
+    assert ragged_forward_of(voc) is None
+    voc.model.precision = "fp16"
+    assert ragged_forward_of(voc) is not None and ragged_forward_of(lambda m: m) is None
+    monkeypatch.setenv("HFG_RAGGED", "0")
+    assert ragged_forward_of(voc) is None
+    stats2 = {}
+    synthesize_variable(voc, mels[:3], stats=stats2, hop=256, halo=16)
+    assert not stats2["native_ragged"] and voc.model.dense_calls > 0
+
+
 def test_numa_binding_is_a_no_op_without_nvml_or_gpu():
     from iris_tts_b200 import numa
     before = os.sched_getaffinity(0)
