@@ -304,6 +304,11 @@ class HiFiGANModel:
         Tensor-core precisions only (``iris_tts_b200.batching.synthesize_variable`` falls back to dense calls otherwise)."""
         return self._ensure_engine().forward_ragged(np.asarray(mel), lengths, self.precision)
 
+    def forward_ragged_batches(self, batches):
+        """``[(mel [B, n_mels, T], lengths), ...]`` -> list of ``[B, T*hop]`` arrays: ``forward_ragged`` per batch, enqueued back
+        to back with one synchronisation at the end (host staging and copies overlap the GPU work)."""
+        return self._ensure_engine().forward_ragged_batches([(np.asarray(m), l) for m, l in batches], self.precision)
+
 
 class HiFiGANGenerator:
     """Wrapper for pre-trained HiFiGAN generator from PyTorch checkpoint (reference :146-242)."""

@@ -123,6 +123,11 @@ class HiFiGANGenerator:
         reference has no ragged call, vocoder.py:177-209)."""
         return self._ensure_engine().forward_ragged(np.asarray(mel), lengths, self.precision)
 
+    def forward_ragged_batches(self, batches):
+        """``[(mel [B, n_mels, T], lengths), ...]`` -> list of ``[B, T*hop]`` arrays: ``forward_ragged`` per batch, enqueued back
+        to back with one synchronisation at the end (host staging and copies overlap the GPU work)."""
+        return self._ensure_engine().forward_ragged_batches([(np.asarray(m), l) for m, l in batches], self.precision)
+
     def get_weights(self) -> List[np.ndarray]:
         return [self.weights[k] for k in self.weights]
 

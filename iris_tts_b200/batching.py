@@ -100,6 +100,7 @@ def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Seque
             if lengths[i] == 0:
                 out[i] = np.zeros((0,), dtype=np.float32)
         n_mels = mels[live[0]].shape[0] if live else 0
+        work = []
         for bucket in length_buckets([lengths[i] for i in live], max_pad, max_batch):
             ids = [live[j] for j in bucket]
             tb = max(lengths[i] for i in ids)
@@ -108,9 +109,14 @@ def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Seque
             batch = np.zeros((len(ids), n_mels, tb), dtype=np.float32)
             for j, i in enumerate(ids):
                 batch[j, :, : lengths[i]] = mels[i]
-            wav = np.asarray(ragged(batch, [lengths[i] for i in ids]))
+            work.append((ids, batch, [lengths[i] for i in ids]))
             calls += 1
             frames_run += tb * len(ids)
+        # all buckets enqueued back to back when the vocoder offers it (copies and staging overlap the GPU work), else one by one
+        many = getattr(getattr(ragged, "__self__", None), "forward_ragged_batches", None)
+        wavs = many([(b, l) for _ids, b, l in work]) if callable(many) else [ragged(b, l) for _ids, b, l in work]
+        for (ids, _b, _l), wav in zip(work, wavs):
+            wav = np.asarray(wav)
             for j, i in enumerate(ids):
                 out[i] = wav[j, : lengths[i] * hop]     # a view of the call's result: no second copy
         if stats is not None:

@@ -556,11 +556,12 @@ int env_flag(const char* name, int dflt) {
 //
 // ragged (hfg_forward_ragged; tensor-core plans only): the items of the batch have their own lengths (plan->lens_dev, mel frames).
 // Every layer of the reference zero-pads its input at the true end of the sequence (:49-59, :92-94), which a dense plan gets from
-// TMA's out-of-bounds zero fill at row L.  A ragged plan makes the same true at every item's OWN end: after each conv an S_STRIP
-// step zeroes the `halo` rows behind the end of the planes just written (halo >= the widest tap span of any layer, so no row inside
-// an item ever reads further), and the fused pair kernel -- whose intermediate never reaches HBM -- masks it per item itself.
-// Rows are independent dot products and their bits do not depend on the tile they fall in, so an item's samples equal those of
-// a dense forward of that item alone, bit for bit.
+// TMA's out-of-bounds zero fill at row L.  A ragged plan makes the same true at every item's OWN end: the kRagged instantiations
+// of conv_umma2 and conv_pair write zeros for every output row at or behind it (the pair kernel also for its shared-memory
+// intermediate), and the few layers on the first-generation kernel (conv_pre, upsamplers wider than one tile) and the staged mel
+// are followed by an S_STRIP step that zeroes the `halo` rows behind the end (halo >= the widest tap span of any layer, so no
+// row inside an item ever reads further).  Rows are independent dot products and their bits do not depend on the tile they fall
+// in, so an item's samples equal those of a dense forward of that item alone, bit for bit.
 int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* base, Plan* plan, size_t* bytes_out, bool ragged = false) {
     typedef __nv_bfloat16 bf;
     const hfg_config& c = e->cfg;
@@ -696,6 +697,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
         p.a_per_tap = a_per_tap;
         p.reverse = snake ? (n_umma2++ & 1) : 0;
+        if (ragged) { p.lens = lens_dev; p.len_T = T; }
         if (acct) work(s, *acct, acct_Lin, x3 ? 4 : 2);   // a time-folded twin: report the reference layer's algorithmic work
         else work(s, L, Lin, x3 ? 4 : 2);   // two bf16 planes carry what an fp32 activation would
         if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, wts_hi(L), L.d_wb_lo, e->sm_count) == HFG_OK) {
@@ -705,8 +707,9 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
             RET(plan_conv_umma(&s.ul, p, x.hi, x.lo, wts_hi(L), L.d_wb_lo));
         }
         s.lane = cur_lane;
+        const bool masked = s.kind == S_UMMA2;   // conv_umma2 writes the zeros behind every item's end itself
         plan->steps.push_back(std::move(s));
-        if (y.hi) strip(y.hi, y.lo, p.g.Lout, p.g.Cout);
+        if (y.hi && !masked) strip(y.hi, y.lo, p.g.Lout, p.g.Cout);
         return HFG_OK;
     };
     // convs1[m] -> lrelu -> convs2[m] -> + x  (:66-70) as one launch where the fused kernel applies (C <= 64); false otherwise
@@ -742,8 +745,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         s.kind = S_PAIR; s.label = label; s.flops += w2.flops;
         s.bytes = 2.0 * r1.cin * (double)rL * B * act_b + 2.0 * (double)r1.cin * r1.cout * r1.k * act_b;
         s.lane = cur_lane;
-        plan->steps.push_back(std::move(s));
-        strip(y.hi, y.lo, Lrows, p.C);
+        plan->steps.push_back(std::move(s));   // (both epilogues of the pair kernel mask per item: no zero-fill step)
         return true;
     };
     auto c32 = [&](const Layer& L, int Lin, const float* x, float* y, const float* res, int pre_lrelu, int accumulate, float out_div) {

@@ -105,6 +105,8 @@ struct UmmaConvParams {
     int xs_read, xs_write;
     float out_div;
     int reverse;          // conv_umma2: walk tiles last-to-first (L2 reuse between consecutive kernels)
+    const int32_t* lens;  // conv_umma2, ragged batch (device, [B] mel frames of len_T per item): rows behind an item's end are written as zeros
+    int len_T;
     int a_per_tap;        // debug/A-B: reload the A tile per tap instead of shifting descriptors
 };
 

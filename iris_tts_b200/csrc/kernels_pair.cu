@@ -108,7 +108,8 @@ __device__ __forceinline__ void issue_taps(bool leader, int k, uint32_t d0, uint
     }
 }
 
-template <int kPlanes, bool kF16>
+// kRagged: per-item sequence ends (hfg_forward_ragged) as a separate instantiation; the dense kernels carry none of its code.
+template <int kPlanes, bool kF16, bool kRagged>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                  const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
@@ -360,7 +361,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             tc_fence_after();
             const uint32_t t_slot = smem_t + st * t_stage;
             // ragged batch: t rows at or behind the item's OWN end are c2's zero padding, as rows >= L are in a dense batch
-            const int Lb = a.lens ? min(a.L, __ldg(a.lens + b) * a.len_mul) : a.L;
+            const int Lb = kRagged ? min(a.L, __ldg(a.lens + b) * a.len_mul) : a.L;
             const bool edge_tile = g0 < 0 || g0 + a.R > Lb;
             for (int ms = 0; ms < (a.dbg == 3 ? 0 : a.mt); ++ms) {
                 const uint32_t row_t = (uint32_t)(ms * 128 + q * 32 + lane);
@@ -429,6 +430,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             tc_fence_after();
             const uint32_t x_slot = smem_x + sx * x_stage;
             const uint32_t m_slot = smem_m + buf * m_stage;
+            const int Lb = kRagged ? __ldg(a.lens + b) * a.len_mul : 0x7fffffff;   // ragged batch: rows from here on are written as zeros
             const f2 scale2 = f2_pack(a.out_scale, a.out_scale);
             for (int ms = 0; ms < (a.dbg == 1 ? 0 : a.mt); ++ms) {
                 const int rs = ms * 128 + q * 32;                    // first tile row of this warp's box
@@ -440,6 +442,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                 const uint32_t msrc = m_slot + (uint32_t)(rs + lane) * row_bytes;
                 const uint32_t msw = swz((uint32_t)(rs + lane), row_bytes);
                 const uint32_t slot = smem_o + (uint32_t)((grp * 4 + q) * a.n_o + so) * o_slot;
+                const bool dead = kRagged && o0 + rs + lane >= Lb;
                 if (lane == 0) { if (a.n_o == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the store that last used this slot has read it
                 __syncwarp();
                 for (int h = 0; h < nch; ++h) {
@@ -498,7 +501,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < CW / 2; ++i) v[i] = f2_lrelu(v[i]);
+                    for (int i = 0; i < CW / 2; ++i) v[i] = (kRagged && dead) ? 0ull : f2_lrelu(v[i]);
 #pragma unroll
                     for (int c = 0; c < CW / 8; ++c)
                         store_planes8<kPlanes, kF16>(&v[c * 4], slot + o_row_off + (((o_chunk0 + (uint32_t)(h * (CW / 8) + c)) ^ o_sx) << 4), a.o_plane_bytes);
@@ -758,9 +761,12 @@ cudaError_t launch_conv_pair(const PairLaunch& L, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev % 64]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        cudaError_t e = cudaSuccess;
+#define HFG_PAIR_ATTR(P, F)                                                                                                                    \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<P, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_pair_kernel<P, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
+        HFG_PAIR_ATTR(1, false); HFG_PAIR_ATTR(1, true); HFG_PAIR_ATTR(2, false);
+#undef HFG_PAIR_ATTR
         if (e != cudaSuccess) return e;
         configured[dev % 64] = true;
     }
@@ -774,13 +780,16 @@ cudaError_t launch_conv_pair(const PairLaunch& L, cudaStream_t s) {
     static const int use_pdl = penv("HFG_PDL", 1);
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
     cudaError_t e;
-#define HFG_PAIR_LAUNCH(P, F)                                                                                                        \
-    e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<P, F>, I.map_x[0], I.map_x[1], I.map_w1[0], I.map_w1[1], I.map_w2[0], I.map_w2[1], \
+#define HFG_PAIR_LAUNCH1(P, F, G)                                                                                                       \
+    e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<P, F, G>, I.map_x[0], I.map_x[1], I.map_w1[0], I.map_w1[1], I.map_w2[0], I.map_w2[1], \
                            I.map_y[0], I.map_y[1], I.map_yt[0], I.map_yt[1], I.map_m[0], I.map_m[1], I.a)
+#define HFG_PAIR_LAUNCH(P, F) \
+    do { if (I.a.lens) HFG_PAIR_LAUNCH1(P, F, true); else HFG_PAIR_LAUNCH1(P, F, false); } while (0)
     if (I.a.planes == 2) HFG_PAIR_LAUNCH(2, false);
     else if (I.a.f16) HFG_PAIR_LAUNCH(1, true);
     else HFG_PAIR_LAUNCH(1, false);
 #undef HFG_PAIR_LAUNCH
+#undef HFG_PAIR_LAUNCH1
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

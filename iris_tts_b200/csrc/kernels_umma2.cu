@@ -62,6 +62,8 @@ struct K2Args {
     int paired;   // C = 32: residual / output boxes address two 64-byte time rows as one 128-byte row (full-line TMA requests)
     int f16;   // operand planes are fp16 instead of bf16 (single-plane mode only)
     int dbg;   // HFG_U2_DBG (timing experiments only): 1 = epilogue does no work, 2 = MMA warp issues no MMAs
+    const int32_t* lens;   // ragged batch (device, [B] mel frames): output rows at or behind item b's own end, lens[b] * len_mul, are
+    int len_mul;           // written as zeros (what the next layer must read there); nullptr: dense batch.  Upsampler: in half-rows
     uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
     uint32_t off_w, off_e;
     const float* bias;
@@ -128,7 +130,9 @@ __device__ __forceinline__ void issue_taps_streamed(bool leader, int taps, uint3
     }
 }
 
-template <int kPlanes, bool kHasRes, bool kF16>
+// kRagged: the per-item masking of hfg_forward_ragged is a separate instantiation -- the dense kernels carry none of its code (a
+// select per output value in the issue-bound epilogue cost the bf16 forward 2 % when it was a run-time flag).
+template <int kPlanes, bool kHasRes, bool kF16, bool kRagged>
 __global__ void __launch_bounds__(threads_for(kPlanes), 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -359,6 +363,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const int m0 = (tm - b * a.tiles_per_item) * a.mt * 128;
             const int boff = n0 % a.cout;                     // bias of tile column c: bias_s[boff + c]
             const int buf = it & 1;
+            const int lim = kRagged ? __ldg(a.lens + b) * a.len_mul : 0x7fffffff;   // first (half-)row behind this item's own end
             mbar_wait(bar_acc_full + 8 * buf, ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
             if (a.dbg == 1 || a.dbg == 3) {   // timing experiment: drain nothing
@@ -382,6 +387,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     const int ucol = n0 + g * a.ecols;
                     const int uhalf = a.ups ? ucol / (a.n_total / 2) : 0;
                     const int ucg = a.ups ? ucol - uhalf * (a.n_total / 2) : 0;
+                    const bool dead = kRagged && (a.ups ? 2 * (row0 + row) - 1 + uhalf : row0 + row) >= lim;   // behind the item's end
                     for (int h = 0; h < (a.dbg == 5 ? 0 : halves); ++h) {
                         uint32_t r[32];
                         const int col = g * a.ecols + h * 32;
@@ -443,7 +449,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+                        for (int i = 0; i < 32; ++i) v[i] = (kRagged && dead) ? 0.f : lrelu(v[i]);
 #pragma unroll
                         for (int cidx = 0; cidx < 4; ++cidx) {
                             uint4 hi;
@@ -615,6 +621,11 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     a.dbg = env_i("HFG_U2_DBG", 0);
     a.reverse = p.reverse;
     a.f16 = p.f16 ? 1 : 0;
+    if (p.lens) {   // ragged batch: rows (upsampler: output half-rows) per mel frame must be whole
+        const int per_T = ups ? 2 * g.Lin : g.Lout;
+        if (p.len_T < 1 || per_T % p.len_T != 0) return HFG_ERR_UNSUPPORTED;
+        a.lens = p.lens; a.len_mul = per_T / p.len_T;
+    }
     // N = 32 always; N = 64 from 7 taps on (measured: k = 11 0.456 -> 0.420 ms, k = 7 0.316 -> 0.277 ms, k = 3 loses); wider layers
     // stream W, where halving MT would double that traffic.  Depends on the layer only: bits never depend on B or L.
     const int concat_maxn = env_i("HFG_U2_CONCAT_MAXN", 0);
@@ -772,8 +783,9 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
     cudaGetDevice(&dev);
     if (!configured[dev % 64]) {
         cudaError_t e = cudaSuccess;
-#define HFG_U2_ATTR(P, R, F) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<P, R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)
+#define HFG_U2_ATTR(P, R, F)                                                                                                                           \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<P, R, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<P, R, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)
         HFG_U2_ATTR(1, false, false); HFG_U2_ATTR(1, true, false); HFG_U2_ATTR(2, false, false); HFG_U2_ATTR(2, true, false);
         HFG_U2_ATTR(1, false, true); HFG_U2_ATTR(1, true, true);
 #undef HFG_U2_ATTR
@@ -789,15 +801,18 @@ cudaError_t launch_conv_umma2(const Umma2Launch& L, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     static const int use_pdl = env_i("HFG_PDL", 1);
     cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-#define HFG_U2_LAUNCH(P, R, F)                                                                                           \
-    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<P, R, F>, I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1], \
+#define HFG_U2_LAUNCH1(P, R, F, G)                                                                                                      \
+    e = cudaLaunchKernelEx(&cfg, conv_umma2_kernel<P, R, F, G>, I.map_a[0], I.map_a[1], I.map_w[0], I.map_w[1], I.map_r[0], I.map_r[1], \
                            I.map_m[0], I.map_m[1], I.map_y[0], I.map_y[1], I.a)
+#define HFG_U2_LAUNCH(P, R, F) \
+    do { if (I.a.lens) HFG_U2_LAUNCH1(P, R, F, true); else HFG_U2_LAUNCH1(P, R, F, false); } while (0)
     cudaError_t e;
     if (I.a.planes == 2) { if (I.a.has_res) HFG_U2_LAUNCH(2, true, false); else HFG_U2_LAUNCH(2, false, false); }
     else if (I.a.f16) { if (I.a.has_res) HFG_U2_LAUNCH(1, true, true); else HFG_U2_LAUNCH(1, false, true); }
     else { if (I.a.has_res) HFG_U2_LAUNCH(1, true, false); else HFG_U2_LAUNCH(1, false, false); }
     if (e != cudaSuccess) return e;
 #undef HFG_U2_LAUNCH
+#undef HFG_U2_LAUNCH1
     return cudaGetLastError();
 }
 

@@ -304,6 +304,46 @@ class Engine:
         return out_t.numpy()
 
     @_locked
+    def forward_ragged_batches(self, batches: Sequence[Tuple[np.ndarray, Sequence[int]]], precision: str = "bf16x3") -> List[np.ndarray]:
+        """Several ragged batches (the length buckets of one workload) enqueued back to back without waiting in between: the host
+        stages bucket i+1 while the GPU runs bucket i, and bucket i's waveform travels to the host on the copy stream while
+        bucket i+1 computes -- one synchronisation at the end.  Same results as ``forward_ragged`` per batch."""
+        import torch
+
+        todo = []
+        total = 0
+        for mel, lengths in batches:
+            if mel.ndim != 3 or mel.shape[1] != self.config.in_channels:
+                raise ValueError(f"mel must be [batch, {self.config.in_channels}, time], got {mel.shape}")
+            B, _, T = mel.shape
+            lens = np.ascontiguousarray(np.asarray(lengths).reshape(-1), dtype=np.int32)
+            if lens.shape[0] != B:
+                raise ValueError(f"lengths must have one entry per item: {lens.shape[0]} vs batch {B}")
+            if B and T and (lens.min() < 1 or lens.max() > T):
+                raise ValueError(f"every length must lie in [1, {T}]")
+            todo.append((mel, lens, total))
+            total += mel.size
+        if self._pin_in is None or self._pin_in.numel() < total:
+            self._pin_in = torch.empty(max(total, 1), dtype=torch.float32, pin_memory=True)
+        outs: List[np.ndarray] = []
+        keep = []
+        try:
+            for mel, lens, off in todo:
+                B, C, T = mel.shape
+                out_t = torch.empty((B, T * self.hop), dtype=torch.float32, pin_memory=True)
+                keep.append(out_t)
+                outs.append(out_t.numpy())
+                if B == 0 or T == 0:
+                    continue
+                stage = self._pin_in[off: off + mel.size].view(B, C, T)
+                np.copyto(stage.numpy(), mel, casting="unsafe")
+                _abi.check(self._lib.hfg_forward_ragged(self._h, ctypes.c_void_p(stage.data_ptr()), B, T, ctypes.c_void_p(lens.ctypes.data),
+                                                        ctypes.c_void_p(out_t.data_ptr()), _abi.PRECISIONS[precision], _abi.NO_SYNC))
+        finally:
+            _abi.check(self._lib.hfg_sync(self._h))   # nothing may still be writing into the page-locked buffers when this frame unwinds
+        return outs
+
+    @_locked
     def sync(self) -> None:
         _abi.check(self._lib.hfg_sync(self._h))
 

@@ -239,6 +239,18 @@ def test_native_ragged_path_host_logic(monkeypatch):
     assert all(shape[2] % 64 == 0 for shape, _l in voc.model.ragged_calls[stats["calls"]:])
     for a, b_ in zip(outs, outs_q):
         np.testing.assert_array_equal(a, b_)
+    # a vocoder that can take all buckets at once gets them in ONE call
+    many_calls = []
+
+    def forward_ragged_batches(self, batches):
+        many_calls.append(len(batches))
+        return [self.forward_ragged(m, l) for m, l in batches]
+
+    Model.forward_ragged_batches = forward_ragged_batches
+    outs_m = synthesize_variable(voc, mels, hop=256, halo=16)
+    assert many_calls == [stats["calls"]]
+    for a, b_ in zip(outs, outs_m):
+        np.testing.assert_array_equal(a, b_)
     # no native path: exact fp32 mode, plain callables, HFG_RAGGED=0
     voc.model.precision = "fp32"
     assert ragged_forward_of(voc) is None
