@@ -432,17 +432,17 @@ def ragged_leg(voc, max_frames, n_utt=32, reps=3):
     mels = [rng.standard_normal((80, t)).astype(np.float32) for t in lengths]
     b = [voc(m) for m in mels]
 
-    def timed(env):
+    def timed(env, max_pad=0.15):
         prev = os.environ.get("HFG_RAGGED")
         os.environ["HFG_RAGGED"] = env
         try:
             stats = {}
-            a = synthesize_variable(voc, mels, stats=stats, length_quantum=64)      # builds the plans
-            synthesize_variable(voc, mels, length_quantum=64)                         # captures their graphs
+            a = synthesize_variable(voc, mels, stats=stats, length_quantum=64, max_pad=max_pad)      # builds the plans
+            synthesize_variable(voc, mels, length_quantum=64, max_pad=max_pad)                         # captures their graphs
             same = all(np.array_equal(x, y) for x, y in zip(a, b))
             t0 = time.perf_counter()
             for _ in range(reps):
-                synthesize_variable(voc, mels, length_quantum=64)
+                synthesize_variable(voc, mels, length_quantum=64, max_pad=max_pad)
             return 1e3 * (time.perf_counter() - t0) / reps, stats, same
         finally:
             if prev is None:
@@ -452,6 +452,11 @@ def ragged_leg(voc, max_frames, n_utt=32, reps=3):
 
     ms_n, st_n, same_n = timed("1")
     ms_b, st_b, same_b = timed("0")
+    # the native plan skips the tiles behind an item's end, so wider buckets (more padding, fewer and larger calls) cost little
+    by_pad = {}
+    for mp in (0.3, 0.5, 1.0):
+        ms_p, st_p, same_p = timed("1", mp)
+        by_pad[str(mp)] = {"ms": ms_p, "calls": st_p["calls"], "frames_run": st_p["frames_run"], "bit_identical": bool(same_p)}
     # what the ragged plan's extra launches (one small zero-fill behind every conv) cost: the same padded batch with every length
     # equal to T through both plans, synchronous calls, numpy in / numpy out
     eng = voc.model.engine
@@ -475,6 +480,7 @@ def ragged_leg(voc, max_frames, n_utt=32, reps=3):
     return {"workload": f"{len(lengths)} utterances, {len(lengths)} distinct lengths {lengths[0]}..{lengths[-1]} frames, bf16, numpy in -> numpy out",
             "native_ragged_ms": ms_n, "native_ragged_value": samples / (ms_n * 1e-3), "native_calls": st_n["calls"],
             "native_frames_run": st_n["frames_run"], "native_path_taken": bool(st_n.get("native_ragged")),
+            "native_by_max_pad": by_pad,
             "bucketed_ms": ms_b, "bucketed_value": samples / (ms_b * 1e-3), "per_utterance_calls_ms": ms_u,
             "per_utterance_value": samples / (ms_u * 1e-3), "unit": "samples/s", "speedup": ms_u / ms_n,
             "speedup_dense_call_scheme": ms_u / ms_b, "dense_calls": st_b["calls"],

@@ -697,7 +697,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.y_raw = y_raw; p.y_act = y.hi; p.y_act_lo = x3 ? y.lo : nullptr;
         p.a_per_tap = a_per_tap;
         p.reverse = snake ? (n_umma2++ & 1) : 0;
-        if (ragged) { p.lens = lens_dev; p.len_T = T; }
+        if (ragged) { p.lens = lens_dev; p.len_T = T; p.len_skip = halo_rows; }
         if (acct) work(s, *acct, acct_Lin, x3 ? 4 : 2);   // a time-folded twin: report the reference layer's algorithmic work
         else work(s, L, Lin, x3 ? 4 : 2);   // two bf16 planes carry what an fp32 activation would
         if (umma2_supported(p) && plan_conv_umma2(&s.u2, p, x.hi, x.lo, wts_hi(L), L.d_wb_lo, e->sm_count) == HFG_OK) {
@@ -728,7 +728,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         p.reverse = snake ? (n_umma2 & 1) : 0;
         if (ragged) {
             if (Lrows % T != 0) { strip_bad = true; return false; }
-            p.lens = lens_dev; p.len_mul = Lrows / T;
+            p.lens = lens_dev; p.len_mul = Lrows / T; p.len_skip = halo_rows;
         }
         if (!pair_supported(p)) return false;
         Step s{};

@@ -107,6 +107,7 @@ struct UmmaConvParams {
     int reverse;          // conv_umma2: walk tiles last-to-first (L2 reuse between consecutive kernels)
     const int32_t* lens;  // conv_umma2, ragged batch (device, [B] mel frames of len_T per item): rows behind an item's end are written as zeros
     int len_T;
+    int len_skip;         // tiles that start this many rows behind an item's end are skipped (>= the widest tap span of any layer)
     int a_per_tap;        // debug/A-B: reload the A tile per tap instead of shifting descriptors
 };
 
@@ -154,6 +155,7 @@ struct PairParams {
     float out_scale;
     const int32_t* lens;  // ragged batch (device, [B]): item b ends at row lens[b] * len_mul -- c2 sees zeros from there on; or nullptr
     int len_mul;
+    int len_skip;         // tiles that start this many rows behind an item's end are skipped (>= the widest tap span of any layer)
     const float* bias1;
     const float* bias2;
     const __nv_bfloat16 *x_hi, *x_lo;

@@ -61,6 +61,7 @@ struct PairArgs {
     int dbg;                     // HFG_PAIR_DBG (timing experiments only): 1 = epilogue 2 idle, 2 = no MMAs, 3 = epilogue 1 idle, 4 = no TMA stores
     const int32_t* lens;         // ragged batch: item b is lens[b] * len_mul rows long (nullptr: every item is L rows)
     int len_mul;
+    int len_skip;                // tiles whose first output row lies this far behind the item's end are not computed (kRagged)
     uint32_t x_plane_bytes, t_plane_bytes, w_plane_bytes, o_plane_bytes;
     uint32_t off_w, off_t, off_o;
     const float* bias1;
@@ -88,6 +89,14 @@ __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t row_bytes) { retu
 // lane issues.  KS = K=16 slices per tap, NP = MMA passes per tap: 1 bf16 | 3 bf16x3 (hi,hi)(lo,hi)(hi,lo) | 2 concat (hi,[hi;lo])(lo,hi).
 // Per tap the descriptors advance by one add each; everything else is loop-invariant (the generic loop spent ~19 instructions
 // and ~100 cycles per MMA on rebuilding them, twice the tensor pipe's own time for N <= 64).
+// Ragged batch: tile `tile` lies wholly behind the rows anything inside its item can read.  Every role evaluates this for every tile
+// of its CTA and skips the same ones; ring positions and buffer parities count live tiles only.
+__device__ __forceinline__ bool pair_tile_skipped(const PairArgs& a, int tile) {
+    const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+    const int b = tl / a.tiles_per_item;
+    return (tl - b * a.tiles_per_item) * a.V >= __ldg(a.lens + b) * a.len_mul + a.len_skip;
+}
+
 template <int KS, int NP>
 __device__ __forceinline__ void issue_taps(bool leader, int k, uint32_t d0, uint32_t a_lo, uint32_t w_lo, uint32_t a_tap, uint32_t w_tap,
                                            uint32_t a_pl, uint32_t w_pl, uint32_t dhi, uint32_t id0, uint32_t id1, uint32_t acc_in = 0u) {
@@ -201,8 +210,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             int sx = 0;
             uint32_t px = 0;
             pdl_wait();   // activations of the previous kernel are complete and visible from here on
-            for (int it = 0; it < n_my; ++it) {
-                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            for (int t = 0; t < n_my; ++t) {
+                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                if (kRagged && pair_tile_skipped(a, tile)) continue;
                 const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
                 const int b = tl / a.tiles_per_item;
                 const int o0 = (tl - b * a.tiles_per_item) * a.V;
@@ -222,7 +232,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         if (lane == 0 && a.n_w2 > 0) {
             int sw = 0;
             uint32_t pw = 0;
-            for (int it = 0; it < n_my; ++it)
+            for (int t = 0; t < n_my; ++t) {
+                if (kRagged && pair_tile_skipped(a, (int)blockIdx.x + t * (int)gridDim.x)) continue;
                 for (int j = 0; j < a.k2; ++j) {
                     mbar_wait(bar_w2_empty + 8 * sw, pw ^ 1u);
                     mbar_expect_tx(bar_w2_full + 8 * sw, (uint32_t)a.N * row_bytes * planes);
@@ -231,14 +242,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
                                     bar_w2_full + 8 * sw, 0, j * a.N);
                     if (++sw == a.n_w2) { sw = 0; pw ^= 1u; }
                 }
+            }
         }
         __syncwarp();
     } else if (warp == 3) {
         // ===== MRF-sum tiles (only the last step of the second and later branches of a stage): R rows from output row o0 =====
         if (lane == 0 && a.has_mrf) {
             pdl_wait();
-            for (int it = 0; it < n_my; ++it) {
-                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            int it = -1;
+            for (int t = 0; t < n_my; ++t) {
+                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                if (kRagged && pair_tile_skipped(a, tile)) continue;
+                ++it;
                 const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
                 const int b = tl / a.tiles_per_item;
                 const int o0 = (tl - b * a.tiles_per_item) * a.V;
@@ -279,7 +294,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
             mbar_wait(bar_w, 0);
             int sx = 0;
             uint32_t px = 0;
-            for (int it = 0; it < n_my; ++it) {
+            int it = -1;   // live tiles so far, minus one
+            for (int t = 0; t < n_my; ++t) {
+                if (kRagged && pair_tile_skipped(a, (int)blockIdx.x + t * (int)gridDim.x)) continue;
+                ++it;
                 const int buf = it & 1;
                 const uint32_t pb = ((uint32_t)it >> 1) & 1u;
                 int slot;
@@ -346,10 +364,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         // With ONE t buffer the tiles must pass through epilogue 1 in order (the parity wait on bar_t_empty cannot tell "c2 of tile
         // i-1 is done" from "c2 of tile i-3 is done"): group 0 takes every tile and group 1 idles.  With two buffers each group
         // owns one and only ever waits for its own previous tile.
-        const int it0 = a.n_t == 1 ? (grp == 0 ? 0 : n_my) : grp;
-        const int it_step = a.n_t == 1 ? 1 : 2;
-        for (int it = it0; it < n_my; it += it_step) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        int it = -1;   // live tiles so far, minus one
+        for (int t = 0; t < n_my; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            if (kRagged && pair_tile_skipped(a, tile)) continue;
+            ++it;
+            if (a.n_t == 1 ? grp != 0 : (it & 1) != grp) continue;   // not this group's tile
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
             const int b = tl / a.tiles_per_item;
             const int g0 = (tl - b * a.tiles_per_item) * a.V - a.h2;      // sequence row of t tile row 0
@@ -416,10 +436,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_cons
         const int rshift = a.paired ? 1 : 0;
         pdl_wait();                                  // before the first global write (WAR against the previous kernel's reads)
         int so = 0;
-        for (int it = grp; it < n_my; it += 2) {
+        int it = -1;   // live tiles so far, minus one
+        for (int t = 0; t < n_my; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            if (kRagged && pair_tile_skipped(a, tile)) continue;
+            ++it;
+            if ((it & 1) != grp) continue;   // the other group's tile
             const int sx = it % a.n_x;
             const uint32_t px = (uint32_t)(it / a.n_x) & 1u;
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
             const int b = tl / a.tiles_per_item;
             const int o0 = (tl - b * a.tiles_per_item) * a.V;
@@ -620,7 +644,7 @@ int plan_conv_pair(PairLaunch* out, const PairParams& p, int sm_count) {
     a.out_scale = a.has_mrf ? p.out_scale : 1.0f;
     a.dbg = penv("HFG_PAIR_DBG", 0);
     a.bias1 = p.bias1; a.bias2 = p.bias2;
-    a.lens = p.lens; a.len_mul = p.len_mul;
+    a.lens = p.lens; a.len_mul = p.len_mul; a.len_skip = std::max(p.len_skip, 8);
     a.w_plane_bytes = rup((uint32_t)N * row_bytes, 1024);
     if (a.concat && a.w_plane_bytes != (uint32_t)N * row_bytes) return HFG_ERR_UNSUPPORTED;
     a.o_plane_bytes = 32u * row_bytes;

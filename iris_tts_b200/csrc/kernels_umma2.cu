@@ -64,6 +64,8 @@ struct K2Args {
     int dbg;   // HFG_U2_DBG (timing experiments only): 1 = epilogue does no work, 2 = MMA warp issues no MMAs
     const int32_t* lens;   // ragged batch (device, [B] mel frames): output rows at or behind item b's own end, lens[b] * len_mul, are
     int len_mul;           // written as zeros (what the next layer must read there); nullptr: dense batch.  Upsampler: in half-rows
+    int len_skip;          // a tile whose first (half-)row lies this far behind the item's end is not computed at all: nothing inside
+                           // an item reads that far (>= the widest tap span of any layer), so a ragged batch costs its real frames
     uint32_t a_plane_bytes, w_plane_bytes, e_plane_bytes;
     uint32_t off_w, off_e;
     const float* bias;
@@ -84,6 +86,12 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // (descriptors advance by one add per tap); only the elected lane issues.  KS = K=16 slices per tap; NP = passes per tap:
 // 1 bf16 | 3 bf16x3 (hi,hi)(lo,hi)(hi,lo) | 2 concat (hi,[hi;lo])(lo,hi).  The generic loop this replaces rebuilt descriptors and
 // instruction words per MMA (~19 instructions, 100-130 cycles per MMA from one thread).
+// Ragged batch: tile (item b, first GEMM row m0) lies wholly behind the rows anything inside the item can read.  Every role
+// evaluates this for every tile and skips the same ones (ring positions and accumulator parities count live tiles only).
+__device__ __forceinline__ bool tile_skipped(const K2Args& a, int b, int m0) {
+    return (a.ups ? 2 * m0 - 1 : m0) >= __ldg(a.lens + b) * a.len_mul + a.len_skip;
+}
+
 template <int KS, int NP>
 __device__ __forceinline__ void issue_taps_resident(bool leader, int taps, uint32_t d0, uint32_t a_lo, uint32_t w_lo, uint32_t a_tap,
                                                     uint32_t w_tap, uint32_t a_pl, uint32_t w_pl, uint32_t dhi, uint32_t id0, uint32_t id1,
@@ -219,6 +227,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int tm = tl / a.n_tiles, n0 = (tl - tm * a.n_tiles) * a.N;   // column tile fastest: neighbours share the A tile in L2
                 const int b = tm / a.tiles_per_item;
                 const int m0 = (tm - b * a.tiles_per_item) * a.mt * 128;
+                if (kRagged && tile_skipped(a, b, m0)) continue;
                 for (int c = 0; c < a.nchunks; ++c) {
                     if (a.dbg != 3) {
                         mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
@@ -270,8 +279,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int sa = 0, sw = 0;
             uint32_t pa = 0, pw = 0;
             if (resident) mbar_wait(bar_wres, 0);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            int it = 0;   // live tiles of this CTA so far
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                if (kRagged) {
+                    const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
+                    const int tm = tl / a.n_tiles, b = tm / a.tiles_per_item;
+                    if (tile_skipped(a, b, (tm - b * a.tiles_per_item) * a.mt * 128)) continue;
+                }
                 const int buf = it & 1;
                 mbar_wait(bar_acc_empty + 8 * buf, (((uint32_t)it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -299,6 +313,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 if (leader) umma_commit(bar_acc_full + 8 * buf);
                 __syncwarp();
+                ++it;
             }
         }
     } else if (warp == 1) {
@@ -311,6 +326,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;   // (a residual implies n_tiles == 1)
                 const int b = tl / a.tiles_per_item;
                 const int m0 = (tl - b * a.tiles_per_item) * a.mt * 128;
+                if (kRagged && tile_skipped(a, b, m0)) continue;
                 for (int ms = 0; ms < a.mt; ++ms) {
                     const int row0 = m0 + ms * 128;
                     if (row0 >= a.L) break;
@@ -355,12 +371,14 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         int hist[2] = {-1, -1};                      // slots of the last `depth` stores (lane 0)
         const int grp = warp >= 12 ? 1 : 0;          // epilogue group of this warp
         int step = 0;                                // (tile, subtile, column group) steps alternate between the groups
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        int it = -1;   // live tiles of this CTA so far, minus one
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             const int tl = a.reverse ? a.total_tiles - 1 - tile : tile;
             const int tm = tl / a.n_tiles, n0 = (tl - tm * a.n_tiles) * a.N;
             const int b = tm / a.tiles_per_item;
             const int m0 = (tm - b * a.tiles_per_item) * a.mt * 128;
+            if (kRagged && tile_skipped(a, b, m0)) continue;
+            ++it;
             const int boff = n0 % a.cout;                     // bias of tile column c: bias_s[boff + c]
             const int buf = it & 1;
             const int lim = kRagged ? __ldg(a.lens + b) * a.len_mul : 0x7fffffff;   // first (half-)row behind this item's own end
@@ -624,7 +642,7 @@ int plan_conv_umma2(Umma2Launch* out, const UmmaConvParams& p, const __nv_bfloat
     if (p.lens) {   // ragged batch: rows (upsampler: output half-rows) per mel frame must be whole
         const int per_T = ups ? 2 * g.Lin : g.Lout;
         if (p.len_T < 1 || per_T % p.len_T != 0) return HFG_ERR_UNSUPPORTED;
-        a.lens = p.lens; a.len_mul = per_T / p.len_T;
+        a.lens = p.lens; a.len_mul = per_T / p.len_T; a.len_skip = std::max(p.len_skip, 8);
     }
     // N = 32 always; N = 64 from 7 taps on (measured: k = 11 0.456 -> 0.420 ms, k = 7 0.316 -> 0.277 ms, k = 3 loses); wider layers
     // stream W, where halving MT would double that traffic.  Depends on the layer only: bits never depend on B or L.
