@@ -23,7 +23,7 @@ def main():
            "# UTCHMMA = tcgen05.mma (kind::f16; loops are rolled, so the count is static code, not issued MMAs), UTCBAR = tcgen05.commit,",
            "# LDTM = tcgen05.ld (TMEM -> registers), UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA), SYNCS = mbarrier ops,",
            "# UTCATOMSWS = tcgen05.alloc/dealloc, F2FP = packed fp32 -> bf16/fp16, HADD2.F32 = fp16 -> fp32, FADD2/FMUL2 = packed fp32 pairs,",
-           "# HMMA = legacy mma.sync (expected: none).  Template arguments: conv_umma2<planes, residual, fp16>, conv_pair<planes, fp16>.", ""]
+           "# HMMA = legacy mma.sync (expected: none).  Template arguments: conv_umma2<planes, residual, fp16, ragged>, conv_pair<planes, fp16, ragged>.", ""]
     tot = collections.Counter()
     for f in re.split(r"\n\s*Function : ", txt)[1:]:
         name = f.split("\n", 1)[0].strip()
