@@ -88,6 +88,24 @@ def batch_shards(batch: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+def ragged_shards(lengths, world: int) -> List[List[int]]:
+    """Utterances of DIFFERENT lengths over ``world`` ranks, balanced by frames rather than by count (a ragged batch costs its
+    real frames on the engine, ``hfg_forward_ragged``): longest-first greedy assignment to the least-loaded rank.  Returns one
+    list of utterance indices per rank (possibly empty); deterministic, so every rank computes the same partition without a
+    collective -- like ``batch_shards``, nothing is exchanged on the data path."""
+    if world <= 0:
+        raise ValueError("world must be positive")
+    load = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in sorted(range(len(lengths)), key=lambda j: (-int(lengths[j]), j)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += int(lengths[i])
+    for part in out:
+        part.sort()
+    return out
+
+
 @dataclasses.dataclass(frozen=True)
 class TimeChunk:
     start: int      # first mel frame this rank is responsible for

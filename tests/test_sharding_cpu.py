@@ -197,6 +197,22 @@ def test_ragged_batch_scheme_is_exact_against_per_utterance_forwards():
         synthesize_variable(vocoder, [np.zeros((1, 80, 5), np.float32)])
 
 
+def test_ragged_shards_balance_frames_not_counts():
+    from iris_tts_b200.sharding import ragged_shards
+    rng = np.random.default_rng(0)
+    lengths = [int(x) for x in rng.integers(50, 900, size=37)]
+    for world in (1, 2, 3, 8):
+        parts = ragged_shards(lengths, world)
+        assert sorted(i for p in parts for i in p) == list(range(37))          # a partition
+        loads = [sum(lengths[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(lengths)                          # LPT bound
+        assert parts == ragged_shards(lengths, world)                           # deterministic: no collective needed
+    assert ragged_shards([5, 7], 4) == [[1], [0], [], []]
+    assert ragged_shards([], 2) == [[], []]
+    with pytest.raises(ValueError):
+        ragged_shards([1], 0)
+
+
 def test_native_ragged_path_host_logic(monkeypatch):
     """A vocoder that offers ``forward_ragged`` in a tensor-core precision gets ONE padded call per length bucket with the items'
     lengths and no tail pass; the fp32 mode, plain callables and HFG_RAGGED=0 keep the dense-call scheme.  (The oracle stands in
