@@ -115,8 +115,13 @@ def _as_f32(a) -> np.ndarray:
 _ALIAS = re.compile(r"^(?:generator\.|module\.)?(.*?)(?:\.conv)?\.(weight_g|weight_v|weight|bias)$")
 
 
+_PLAIN = re.compile(r"^(.*?)\.(weight_g|weight_v|weight|bias)$")
+
+
 def canonical_key(key: str) -> Optional[Tuple[str, str]]:
-    m = _ALIAS.match(key)
+    """(layer, parameter) of a checkpoint key.  With ``IRIS_HIFIGAN_STRICT_KEYS=1`` only the reference's own names match, i.e. the
+    speechbrain aliases are treated as the reference's ``load_state_dict(strict=False)`` treats them (ignored, :190)."""
+    m = (_PLAIN if os.environ.get("IRIS_HIFIGAN_STRICT_KEYS", "0") == "1" else _ALIAS).match(key)
     return (m.group(1), m.group(2)) if m else None
 
 
@@ -187,6 +192,13 @@ class Engine:
                 unexpected.append(key)
                 continue
             grouped.setdefault(ck[0], {})[ck[1]] = val
+        aliased = sum(1 for key in state_dict if (ck := canonical_key(key)) and ck[0] in known and f"{ck[0]}.{ck[1]}" != key)
+        if aliased:
+            import logging
+
+            logging.getLogger(__name__).info(
+                "%d checkpoint keys matched through aliases (speechbrain '<layer>.conv.*' names, 'generator.' / 'module.' prefixes); "
+                "the reference's load_state_dict(strict=False) would ignore them -- IRIS_HIFIGAN_STRICT_KEYS=1 restores that", aliased)
         missing: List[str] = []
         for name in self._layer_names:
             g = grouped.get(name, {})

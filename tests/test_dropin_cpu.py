@@ -54,6 +54,16 @@ def test_load_state_dict_semantics():
     missing, unexpected = m.load_state_dict(extra, strict=False)
     assert unexpected == ["mpd.something"] and not missing
     assert float(m.state_dict()["conv_post.bias"]) == 0.25
+    # IRIS_HIFIGAN_STRICT_KEYS=1: the reference's own treatment of such keys (ignored, the parameter keeps its value)
+    import os
+    os.environ["IRIS_HIFIGAN_STRICT_KEYS"] = "1"
+    try:
+        extra["conv_post.conv.bias"] = torch.full((1,), 0.75)
+        missing, unexpected = m.load_state_dict(extra, strict=False)
+        assert sorted(unexpected) == ["conv_post.conv.bias", "mpd.something"] and missing == ["conv_post.bias"]
+        assert float(m.state_dict()["conv_post.bias"]) == 0.25
+    finally:
+        del os.environ["IRIS_HIFIGAN_STRICT_KEYS"]
     with pytest.raises(RuntimeError, match="size mismatch"):
         m.load_state_dict({"conv_pre.bias": torch.zeros(7)}, strict=False)
     with pytest.raises(RuntimeError):
