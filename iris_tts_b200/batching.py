@@ -114,15 +114,24 @@ def synthesize_variable(vocoder: Callable[[np.ndarray], np.ndarray], mels: Seque
             frames_run += tb * len(ids)
         # all buckets enqueued back to back when the vocoder offers it (copies and staging overlap the GPU work), else one by one
         many = getattr(getattr(ragged, "__self__", None), "forward_ragged_batches", None)
-        wavs = many([(b, l) for _ids, b, l in work]) if callable(many) else [ragged(b, l) for _ids, b, l in work]
-        for (ids, _b, _l), wav in zip(work, wavs):
-            wav = np.asarray(wav)
-            for j, i in enumerate(ids):
-                out[i] = wav[j, : lengths[i] * hop]     # a view of the call's result: no second copy
-        if stats is not None:
-            stats.update({"calls": calls, "frames_run": frames_run, "frames_real": sum(lengths),
-                          "distinct_lengths": len(set(lengths)), "native_ragged": True})
-        return out
+        try:
+            wavs = many([(b, l) for _ids, b, l in work]) if callable(many) else [ragged(b, l) for _ids, b, l in work]
+        except RuntimeError as exc:
+            # a generator the engine has no ragged plan for (HFG_ERR_UNSUPPORTED = -5: e.g. an initial channel count that is not
+            # a multiple of 32 runs on the fp32 family): the dense-call scheme below serves it
+            if getattr(exc, "code", None) != -5:
+                raise
+            wavs = None
+        if wavs is not None:
+            for (ids, _b, _l), wav in zip(work, wavs):
+                wav = np.asarray(wav)
+                for j, i in enumerate(ids):
+                    out[i] = wav[j, : lengths[i] * hop]     # a view of the call's result: no second copy
+            if stats is not None:
+                stats.update({"calls": calls, "frames_run": frames_run, "frames_real": sum(lengths),
+                              "distinct_lengths": len(set(lengths)), "native_ragged": True})
+            return out
+        calls = frames_run = 0
     long_idx = [i for i in range(n) if lengths[i] >= 2 * halo]
     short_idx = [i for i in range(n) if lengths[i] < 2 * halo]
 

@@ -267,6 +267,28 @@ def test_native_ragged_path_host_logic(monkeypatch):
     assert many_calls == [stats["calls"]]
     for a, b_ in zip(outs, outs_m):
         np.testing.assert_array_equal(a, b_)
+    # a generator the engine cannot plan ragged (HFG_ERR_UNSUPPORTED) falls back to the dense-call scheme; other errors surface
+    class Unsupported(RuntimeError):
+        code = -5
+
+    def refuse(self, batches):
+        raise Unsupported("no ragged plan")
+
+    Model.forward_ragged_batches = refuse
+    before = voc.model.dense_calls
+    stats_f = {}
+    outs_f = synthesize_variable(voc, mels, stats=stats_f, hop=256, halo=16)
+    assert not stats_f["native_ragged"] and voc.model.dense_calls > before
+    for a, b_ in zip(outs, outs_f):
+        np.testing.assert_allclose(a, b_, atol=2e-6)
+
+    def broken(self, batches):
+        raise RuntimeError("something else")
+
+    Model.forward_ragged_batches = broken
+    with pytest.raises(RuntimeError, match="something else"):
+        synthesize_variable(voc, mels, hop=256, halo=16)
+    Model.forward_ragged_batches = forward_ragged_batches
     # no native path: exact fp32 mode, plain callables, HFG_RAGGED=0
     voc.model.precision = "fp32"
     assert ragged_forward_of(voc) is None
