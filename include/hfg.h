@@ -118,7 +118,7 @@ int hfg_forward(hfg_engine* e, const float* mel, int32_t B, int32_t T, float* wa
  * hfg_forward returns for that item alone (B = 1, T = lengths[b]) -- every layer zero-pads at the item's OWN end, as the
  * reference does for a dense batch of that length (src/iris/hifigan_pretrained.py:49-59, 92-94; its __call__ :221-242 takes one
  * dense [B, 80, T] array and has no lengths, so ragged input costs it one forward per distinct length).  The rest of row b is
- * unspecified.  Tensor-core precisions only (HFG_ERR_UNSUPPORTED for HFG_PREC_FP32 and with HFG_KEEP_TAPS). */
+ * unspecified.  Every precision; not with HFG_KEEP_TAPS (HFG_ERR_INVALID). */
 int hfg_forward_ragged(hfg_engine* e, const float* mel, int32_t B, int32_t T, const int32_t* lengths, float* wave,
                        int32_t precision, uint32_t flags);
 int hfg_sync(hfg_engine* e);

@@ -301,7 +301,7 @@ class HiFiGANModel:
         """Not in the reference (its ``__call__`` takes one dense array of equal-length mels, :221-242): numpy ``[B, in_channels, T]``
         whose item b holds ``lengths[b]`` real frames -> float32 numpy ``[B, T*hop]`` with ``out[b, :lengths[b]*hop]`` equal, bit for
         bit, to the dense forward of that item alone; one launch plan for the whole ragged batch (``hfg_forward_ragged``).
-        Tensor-core precisions only (``iris_tts_b200.batching.synthesize_variable`` falls back to dense calls otherwise)."""
+        Every precision (``iris_tts_b200.batching.synthesize_variable`` builds on it)."""
         return self._ensure_engine().forward_ragged(np.asarray(mel), lengths, self.precision)
 
     def forward_ragged_batches(self, batches):

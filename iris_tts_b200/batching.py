@@ -13,7 +13,7 @@ constructor arguments; 16 is used).  That gives an exact scheme with dense calls
   last ``halo`` frames are kept -- their left context lies inside the window, their right edge is the true end of the utterance,
   so the generator's own zero padding is applied exactly where the reference applies it.
 
-When the vocoder is one of this package's objects in a tensor-core precision, the engine does the same thing natively and the tail
+When the vocoder is one of this package's objects, the engine does the same thing natively and the tail
 pass disappears: ``hfg_forward_ragged`` takes the padded batch WITH its lengths, zeroes what lies behind each item's own end after
 every layer (and inside the fused ResBlock kernel), and returns every item's samples bit-identical to its solo forward -- one dense
 launch plan per bucket, no second pass, no stitching (``ragged_forward_of``).
@@ -58,15 +58,14 @@ def length_buckets(lengths: Sequence[int], max_pad: float = 0.15, max_batch: Opt
 
 def ragged_forward_of(vocoder) -> Optional[Callable]:
     """``forward_ragged(mel [B, n_mels, T], lengths) -> [B, T*hop]`` of a vocoder of this package (HiFiGANGenerator / HiFiGANVocoder
-    via ``.model``, or a model object itself) when its precision has the native ragged path; None for plain callables, for the exact
-    fp32 mode and when ``HFG_RAGGED=0``."""
+    via ``.model``, or a model object itself); None for plain callables and when ``HFG_RAGGED=0``."""
     import os
 
     if os.environ.get("HFG_RAGGED", "1") == "0":
         return None
     for obj in (vocoder, getattr(vocoder, "model", None)):
         fn = getattr(obj, "forward_ragged", None) if obj is not None else None
-        if callable(fn) and getattr(obj, "precision", None) in ("bf16x3", "bf16", "fp16"):
+        if callable(fn) and getattr(obj, "precision", None) in ("bf16x3", "bf16", "fp16", "fp32"):
             return fn
     return None
 

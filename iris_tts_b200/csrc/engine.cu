@@ -554,14 +554,15 @@ int env_flag(const char* name, int dflt) {
 // outputs per stage.  Stages narrower than 32 channels (V2's tail) run on the fp32 family inside a
 // tensor-core plan; the hand-over is the fp32 output of that MRF pass.
 //
-// ragged (hfg_forward_ragged; tensor-core plans only): the items of the batch have their own lengths (plan->lens_dev, mel frames).
+// ragged (hfg_forward_ragged): the items of the batch have their own lengths (plan->lens_dev, mel frames).
 // Every layer of the reference zero-pads its input at the true end of the sequence (:49-59, :92-94), which a dense plan gets from
 // TMA's out-of-bounds zero fill at row L.  A ragged plan makes the same true at every item's OWN end: the kRagged instantiations
 // of conv_umma2 and conv_pair write zeros for every output row at or behind it (the pair kernel also for its shared-memory
 // intermediate), and the few layers on the first-generation kernel (conv_pre, upsamplers wider than one tile) and the staged mel
 // are followed by an S_STRIP step that zeroes the `halo` rows behind the end (halo >= the widest tap span of any layer, so no
 // row inside an item ever reads further).  Rows are independent dot products and their bits do not depend on the tile they fall
-// in, so an item's samples equal those of a dense forward of that item alone, bit for bit.
+// in, so an item's samples equal those of a dense forward of that item alone, bit for bit.  The fp32 family (HFG_PREC_FP32, and
+// generators whose initial channel count is not a multiple of 32) gets the zero-fill step after every conv.
 int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* base, Plan* plan, size_t* bytes_out, bool ragged = false) {
     typedef __nv_bfloat16 bf;
     const hfg_config& c = e->cfg;
@@ -612,8 +613,8 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     float* wave_dev = bump.take<float>((size_t)B * T * e->hop);
     int32_t* lens_dev = ragged ? bump.take<int32_t>((size_t)B) : nullptr;
     if (real) { plan->mel_dev = mel_dev; plan->wave_dev = wave_dev; plan->keep_taps = keep_taps; plan->lens_dev = lens_dev; }
-    if (ragged && (!any_tc || any_32 || keep_taps))
-        return fail(HFG_ERR_UNSUPPORTED, "ragged batches run on the tensor-core plans only (precision bf16x3 / bf16 / fp16, upsample_initial_channel % 32 == 0, no taps)");
+    if (ragged && (keep_taps || (any_tc && any_32)))
+        return fail(HFG_ERR_UNSUPPORTED, "ragged batches: not available with taps");
     // rows to zero behind an item's end: the widest reach of any layer's taps (in the rows of its own stage), in whole 8-row groups
     int halo_rows = 8;
     for (const Layer& Ly : e->layers) halo_rows = std::max(halo_rows, Ly.transposed ? Ly.k : Ly.dil * (Ly.k - 1) / 2 + 1);
@@ -751,7 +752,10 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
     auto c32 = [&](const Layer& L, int Lin, const float* x, float* y, const float* res, int pre_lrelu, int accumulate, float out_div) {
         Step s{}; s.kind = S_CONV32; s.cp = conv32(L, B, Lin, x, y, res, pre_lrelu, accumulate, out_div);
         work(s, L, Lin, 4);
+        const int Lout = s.cp.Lout;
         push(std::move(s));
+        // ragged plans of the fp32 family: the same zero-fill behind every item's end, on the fp32 stream (two 16-bit elements each)
+        strip(reinterpret_cast<__nv_bfloat16*>(y), nullptr, Lout, 2 * L.cout);
     };
     auto accum = [&](const float* r, size_t ne, int j) {
         Step s{}; s.kind = S_ACCUM; s.f_out = xs; s.f_in = r; s.n = ne; s.flag0 = j == 0;
@@ -781,6 +785,7 @@ int build_plan(hfg_engine* e, int B, int T, int prec, bool keep_taps, uint8_t* b
         x_raw = x0_raw; xp = x0_p;
     } else {
         { Step s{}; s.kind = S_MEL_CL32; s.f_in = mel_dev; s.f_out = mel_cl; s.B = B; s.C = c.in_channels; s.L = T; push(std::move(s)); }
+        strip(reinterpret_cast<__nv_bfloat16*>(mel_cl), nullptr, T, 2 * c.in_channels);
         c32(pre, T, mel_cl, x0_raw, nullptr, 0, 0, 0.f);
         tap("conv_pre", x0_raw, c0, T);
         x_raw = x0_raw;

@@ -293,7 +293,7 @@ class Engine:
         """Ragged batch in ONE dense launch plan (``hfg_forward_ragged``): numpy [B, in_channels, T] whose item b holds
         ``lengths[b]`` real frames (the rest is ignored) -> float32 [B, T*hop]; ``out[b, :lengths[b]*hop]`` equals
         ``forward(mel[b:b+1, :, :lengths[b]])[0]`` bit for bit, the rest of row b is unspecified.  The reference has no
-        such call (hifigan_pretrained.py:221-242: one dense array, equal T).  Tensor-core precisions only."""
+        such call (hifigan_pretrained.py:221-242: one dense array, equal T).  Every precision."""
         if mel.ndim != 3 or mel.shape[1] != self.config.in_channels:
             raise ValueError(f"mel must be [batch, {self.config.in_channels}, time], got {mel.shape}")
         B, _, T = mel.shape

@@ -289,8 +289,8 @@ def test_native_ragged_path_host_logic(monkeypatch):
     with pytest.raises(RuntimeError, match="something else"):
         synthesize_variable(voc, mels, hop=256, halo=16)
     Model.forward_ragged_batches = forward_ragged_batches
-    # no native path: exact fp32 mode, plain callables, HFG_RAGGED=0
-    voc.model.precision = "fp32"
+    # no native path: unknown precisions, plain callables, HFG_RAGGED=0
+    voc.model.precision = "int8"
     assert ragged_forward_of(voc) is None
     voc.model.precision = "fp16"
     assert ragged_forward_of(voc) is not None and ragged_forward_of(lambda m: m) is None
