@@ -447,6 +447,12 @@ def test_no_kernel_writes_outside_its_buffers(cfg_name):
                 out = eng.forward(mel, precision=mode)              # raises HfgError if a canary was overwritten
                 assert np.abs(out - ref).max() <= e2e_tol(mode, ref), (B, T, mode)
             eng.forward(mel, precision="bf16x3", keep_taps=True)
+            if B > 1:   # the ragged plan's zero-fill steps and masked epilogues under the same canaries
+                lens = [T] + [max(1, T // 2)] * (B - 1)
+                for mode in MODES:
+                    rag = eng.forward_ragged(mel, lens, precision=mode)
+                    np.testing.assert_array_equal(rag[1, : lens[1] * eng.hop],
+                                                  eng.forward(np.ascontiguousarray(mel[1:2, :, : lens[1]]), precision=mode)[0])
         eng.close()
     finally:
         del os.environ["HFG_GUARD"]
