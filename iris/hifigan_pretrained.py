@@ -301,8 +301,24 @@ class HiFiGANModel:
         """Not in the reference (its ``__call__`` takes one dense array of equal-length mels, :221-242): numpy ``[B, in_channels, T]``
         whose item b holds ``lengths[b]`` real frames -> float32 numpy ``[B, T*hop]`` with ``out[b, :lengths[b]*hop]`` equal, bit for
         bit, to the dense forward of that item alone; one launch plan for the whole ragged batch (``hfg_forward_ragged``).
-        Every precision (``iris_tts_b200.batching.synthesize_variable`` builds on it)."""
-        return self._ensure_engine().forward_ragged(np.asarray(mel), lengths, self.precision)
+        Every precision (``iris_tts_b200.batching.synthesize_variable`` builds on it).  A CUDA tensor is consumed and the
+        waveform produced on the device (``[B, T*hop]`` tensor), like ``forward``."""
+        e = self._ensure_engine()
+        if torch is not None and isinstance(mel, torch.Tensor):
+            if not mel.is_cuda:
+                return torch.from_numpy(e.forward_ragged(mel.detach().numpy(), lengths, self.precision))
+            if mel.device.index != self._device_index:
+                raise RuntimeError(f"input on {mel.device} but model on cuda:{self._device_index}")
+            if mel.dim() != 3 or mel.shape[1] != self.config.in_channels:
+                raise RuntimeError(f"Expected [batch, {self.config.in_channels}, time], got {tuple(mel.shape)}")
+            B, _, T = mel.shape
+            xin = mel.detach().to(torch.float32).contiguous()
+            out = torch.empty((B, T * e.hop), dtype=torch.float32, device=mel.device)
+            if B and T:
+                torch.cuda.current_stream(mel.device).synchronize()
+                e.forward_ragged_ptr(xin.data_ptr(), B, T, lengths, out.data_ptr(), self.precision, mel_on_device=True, wave_on_device=True)
+            return out
+        return e.forward_ragged(np.asarray(mel), lengths, self.precision)
 
     def forward_ragged_batches(self, batches):
         """``[(mel [B, n_mels, T], lengths), ...]`` -> list of ``[B, T*hop]`` arrays: ``forward_ragged`` per batch, enqueued back

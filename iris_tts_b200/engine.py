@@ -289,6 +289,18 @@ class Engine:
         return out
 
     @_locked
+    def forward_ragged_ptr(self, mel_ptr: int, B: int, T: int, lengths: Sequence[int], wave_ptr: int, precision: str = "bf16x3", *,
+                           mel_on_device=False, wave_on_device=False, sync=True) -> None:
+        """Raw-pointer ragged forward (``hfg_forward_ragged``): mel [B][in_channels][T] fp32 with ``lengths[b]`` real frames per item
+        -> wave [B][T*hop] fp32; host or device pointers like ``forward_ptr``."""
+        lens = np.ascontiguousarray(np.asarray(lengths).reshape(-1), dtype=np.int32)
+        if lens.shape[0] != B:
+            raise ValueError(f"lengths must have one entry per item: {lens.shape[0]} vs batch {B}")
+        flags = (_abi.MEL_ON_DEVICE if mel_on_device else 0) | (_abi.WAVE_ON_DEVICE if wave_on_device else 0) | (0 if sync else _abi.NO_SYNC)
+        _abi.check(self._lib.hfg_forward_ragged(self._h, ctypes.c_void_p(mel_ptr), B, T, ctypes.c_void_p(lens.ctypes.data),
+                                                ctypes.c_void_p(wave_ptr), _abi.PRECISIONS[precision], flags))
+
+    @_locked
     def forward_ragged(self, mel: np.ndarray, lengths: Sequence[int], precision: str = "bf16x3") -> np.ndarray:
         """Ragged batch in ONE dense launch plan (``hfg_forward_ragged``): numpy [B, in_channels, T] whose item b holds
         ``lengths[b]`` real frames (the rest is ignored) -> float32 [B, T*hop]; ``out[b, :lengths[b]*hop]`` equals

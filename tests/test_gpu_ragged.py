@@ -126,3 +126,23 @@ def test_synthesize_variable_takes_the_native_path(mode, tmp_path):
         assert y.shape == (m.shape[1] * 256,) and y.dtype == np.float32
         if m.shape[1]:
             np.testing.assert_array_equal(y, voc(m[None])[0])
+
+
+def test_ragged_forward_on_cuda_tensors():
+    """``HiFiGANModel.forward_ragged`` with a CUDA tensor: mel consumed and waveform produced on the device, same bits as the host path."""
+    import torch
+
+    import iris.hifigan_pretrained as hp
+    torch.manual_seed(0)
+    m = hp.HiFiGANModel().eval().to("cuda:0")
+    m.precision = "bf16"
+    mel = O.synthetic_mel(3, 50, seed=6)
+    lens = [50, 21, 38]
+    host = m.forward_ragged(mel, lens)
+    dev = m.forward_ragged(torch.from_numpy(mel).cuda(), lens)
+    assert dev.is_cuda and tuple(dev.shape) == host.shape
+    for b, n in enumerate(lens):
+        np.testing.assert_array_equal(dev[b, : n * 256].cpu().numpy(), host[b, : n * 256])
+    cpu_t = m.forward_ragged(torch.from_numpy(mel), lens)
+    assert not cpu_t.is_cuda
+    np.testing.assert_array_equal(cpu_t[1, : 21 * 256].numpy(), host[1, : 21 * 256])
